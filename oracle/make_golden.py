@@ -1,0 +1,127 @@
+"""TEST INFRASTRUCTURE ONLY: regenerate tests/golden/*.json from the UNMODIFIED reference.
+
+    python oracle/make_golden.py            # needs /root/reference (this container only)
+
+Every case is one shot of the reference's own Program.simulate on a seeded
+random circuit over ALL tableau-path gate kinds (13 unitaries, M, M_X, RESET,
+and N1 replayed as explicit Paulis).  Stored per case: the op list, the noise
+draws, the chronological records (whose values double as the replay vector for
+random measurements) and the six final arrays.  Cases where the reference
+overflows int64 in its lazy-reduction window (detected by
+ref_harness.ref_run_eager_modulo disagreeing) are dropped, and the count of
+dropped cases is stored in the file header.
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+UNITARY_1 = [1, 2, 3, 4, 5, 6, 7, 8]
+UNITARY_2 = [9, 10, 11, 12, 13]
+
+
+def random_ops(rng: random.Random, n: int, depth: int, d: int, p_meas=0.12, p_noise=0.08):
+    """Random op list over every opcode; returns (ops, n_meas, n_noise)."""
+    ops, k, j = [], 0, 0
+    for _ in range(depth):
+        u = rng.random()
+        if u < p_meas:
+            op = rng.choice([14, 14, 15, 16])
+            ops.append([op, rng.randrange(n), -1, k])
+            k += 1
+        elif u < p_meas + p_noise:
+            ops.append([17, rng.randrange(n), -1, j])
+            j += 1
+        elif n >= 2 and rng.random() < 0.4:
+            a, b = rng.sample(range(n), 2)
+            ops.append([rng.choice(UNITARY_2), a, b, -1])
+        else:
+            ops.append([rng.choice(UNITARY_1 + [0]), rng.randrange(n), -1, -1])
+    return ops, k, j
+
+
+def final_measure_all(ops, n, k):
+    for q in range(n):
+        ops.append([14, q, -1, k])
+        k += 1
+    return k
+
+
+def make_case(seed: int, n: int, d: int, depth: int):
+    rng = random.Random(seed)
+    ops, k, j = random_ops(rng, n, depth, d)
+    k = final_measure_all(ops, n, k)
+    noise = [[rng.randrange(d), rng.randrange(d)] if rng.random() < 0.7 else [0, 0] for _ in range(j)]
+    noise_arr = np.array(noise, dtype=np.int64).reshape(-1, 2)
+    recs, arrs = rh.ref_run(n, d, ops, noise_arr, draw_seed=seed)
+    recs2, arrs2 = rh.ref_run_eager_modulo(n, d, ops, noise_arr, draw_seed=seed)
+    overflow = recs != recs2 or any(not np.array_equal(arrs[key], arrs2[key]) for key in arrs)
+    if overflow:
+        return None
+    return {
+        "seed": seed, "n": n, "d": d, "ops": ops, "noise_ab": noise,
+        "records": [[q, int(det), m] for q, det, m in recs],
+        "final": {key: val.tolist() for key, val in arrs.items()},
+    }
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    plan = []
+    seed = 1000
+    for d in (2, 3, 5, 7, 11, 13):
+        for n, depth, reps in ((1, 24, 3), (2, 40, 4), (3, 60, 4), (5, 90, 4), (8, 140, 3), (13, 200, 2)):
+            for _ in range(reps):
+                plan.append((seed, n, d, depth))
+                seed += 1
+    cases, dropped = [], 0
+    for seed, n, d, depth in plan:
+        case = make_case(seed, n, d, depth)
+        if case is None:
+            dropped += 1
+        else:
+            cases.append(case)
+    out = {"generator": "oracle/make_golden.py", "reference": "events555/sdim @ /root/reference",
+           "dropped_for_reference_int64_overflow": dropped, "cases": cases}
+    path = os.path.join(GOLDEN_DIR, "random_circuits.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh, separators=(",", ":"))
+    print(f"wrote {len(cases)} cases ({dropped} dropped) -> {path} ({os.path.getsize(path)} bytes)")
+
+    # The two shipped circuits (SURVEY section 4 golden vectors), through the reference's own reader.
+    sdim = rh.load_reference()
+    shipped = {}
+    for name in ("circuits/css_steane_final.chp", "circuits/epr.chp"):
+        circ = sdim.read_circuit(name)
+        import sdim.tableau.tableau_prime as tp
+        saved = tp.random
+        tp.random = rh._ChoiceFeed(random.Random(7))
+        try:
+            prog = sdim.Program(circ)
+            res = prog.simulate(shots=1)
+        finally:
+            tp.random = saved
+        shipped[name] = {
+            "num_qudits": circ.num_qudits, "dimension": circ.dimension,
+            "ops": [[op.gate_id, op.qudit_index, -1 if op.target_index is None else op.target_index]
+                    for op in circ.operations],
+            "flat_results": [[r.qudit_index, int(r.deterministic), int(r.measurement_value)] for r in res],
+            "final": {k: v.tolist() for k, v in rh._final_arrays(prog.stabilizer_tableau).items()},
+        }
+    path = os.path.join(GOLDEN_DIR, "shipped_circuits.json")
+    with open(path, "w") as fh:
+        json.dump({"generator": "oracle/make_golden.py", "circuits": shipped}, fh, separators=(",", ":"))
+    print(f"wrote {path}")
+
+
+if __name__ == "__main__":
+    main()
