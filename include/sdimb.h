@@ -1,0 +1,139 @@
+/*
+ * sdimb.h — C ABI of libsdimb, the B200 (sm_100a) stabilizer-tableau engine.
+ *
+ * Drop-in boundary for the prime-dimension tableau hot path of events555/sdim.
+ * The reference has no native boundary (it is one Python package); its seam at
+ * the right granularity is the batch call
+ *     simulate_frame(ir_array, reference_results, n_qudits, dimension, extra_shots, noise_array)
+ *         reference: sdim/program.py:45-47, called at sdim/program.py:253-262
+ * i.e. "IR + noise in, records out, once per Program.simulate".  The entry points
+ * below are what an FFI binding for that seam binds; INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (SDIMB_OK) or a negative SDIMB_E* code; nothing throws
+ *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*,
+ *     NULL = legacy default stream) and never synchronise; pointers marked [device]
+ *     are plain CUDA device addresses owned by the caller (PyTorch in this repo)
+ *   - no global mutable state: calls on distinct (stream, buffer) sets may run concurrently
+ *   - there is NO CPU fallback: without a CUDA device every launch returns SDIMB_ECUDA
+ *
+ * Tableau store (one tableau per shot; replaces the six int64 arrays of
+ * sdim/tableau/dataclasses.py:24-39 + sdim/tableau/tableau_prime.py:24-26):
+ *   lanes  np = n rounded up to 16;  W = 2*np generator lanes per row
+ *          lane g in [0,n)      = stabilizer generator g   (reference column g of x_block/z_block)
+ *          lane np+g            = destabilizer generator g (reference column g of destab_*_block)
+ *          padding lanes hold 0 forever
+ *   shot s at  tab + s*shot_bytes:
+ *          row q (qudit q):  X[q][0..W) at q*2W,  Z[q][0..W) at q*2W + W      (uint8, reduced mod d)
+ *          phases:           P[0..W)    at n*2W                                 (uint8, reduced mod order)
+ *   order = 2d for d = 2, d for odd prime d (sdim/tableau/dataclasses.py:88-106)
+ */
+#ifndef SDIMB_H
+#define SDIMB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDIMB_VERSION 1
+
+enum {
+  SDIMB_OK = 0,
+  SDIMB_EINVAL = -1,   /* bad argument (null pointer, n < 1, shots < 0, bad struct_size ...) */
+  SDIMB_EDIM = -2,     /* dimension not a prime in [2, 127] */
+  SDIMB_EOP = -3,      /* invalid opcode / qudit index in the op stream ("Invalid gate value", sdim/program.py:381-382) */
+  SDIMB_ECUDA = -4,    /* CUDA runtime error (no device, launch failure, out of memory) */
+  SDIMB_ETOOBIG = -5   /* forced resident mode but one tableau does not fit in shared memory */
+};
+
+/* Opcodes = gate ids of the reference gate table (sdim/gatedata.py:65-102). */
+enum {
+  SDIMB_OP_I = 0, SDIMB_OP_X = 1, SDIMB_OP_X_INV = 2, SDIMB_OP_Z = 3, SDIMB_OP_Z_INV = 4,
+  SDIMB_OP_H = 5, SDIMB_OP_H_INV = 6, SDIMB_OP_P = 7, SDIMB_OP_P_INV = 8,
+  SDIMB_OP_CNOT = 9, SDIMB_OP_CNOT_INV = 10, SDIMB_OP_CZ = 11, SDIMB_OP_CZ_INV = 12, SDIMB_OP_SWAP = 13,
+  SDIMB_OP_M = 14, SDIMB_OP_M_X = 15, SDIMB_OP_RESET = 16, SDIMB_OP_N1 = 17
+};
+
+/* Record byte: low 7 bits = measured value, bit 7 = deterministic flag
+ * (MeasurementResult.measurement_value / .deterministic, sdim/tableau/dataclasses.py:166-180). */
+#define SDIMB_REC_DET 0x80u
+#define SDIMB_REC_VALUE 0x7Fu
+
+/* sdimb_run flags */
+#define SDIMB_FRESH 0x1u           /* start every shot from |0...0> (ignore/skip the contents of `tableau`) */
+#define SDIMB_WRITEBACK 0x2u       /* leave the final tableau of every shot in `tableau` */
+#define SDIMB_FORCE_GLOBAL 0x4u    /* never stage the tableau in shared memory */
+#define SDIMB_FORCE_RESIDENT 0x8u  /* require the shared-memory resident interpreter (else SDIMB_ETOOBIG) */
+
+typedef struct SdimbLayout {
+  int32_t n, d, np, lanes;   /* lanes = W = 2*np */
+  int32_t order, phase_order;
+  int64_t row_bytes;         /* 2*W: X row then Z row of one qudit */
+  int64_t phase_offset;      /* n*row_bytes */
+  int64_t shot_bytes;        /* phase_offset + W */
+} SdimbLayout;
+
+typedef struct SdimbRunArgs {
+  uint32_t struct_size;          /* = sizeof(SdimbRunArgs) */
+  uint32_t flags;
+  int32_t n, d;
+  int64_t shots;                 /* shots simulated by this call */
+  int64_t shot_offset;           /* global id of local shot 0 (Philox counter = shot_offset + local) */
+  void* tableau;                 /* [device] shots*shot_bytes; may be NULL iff FRESH && !WRITEBACK && resident fits */
+  const int32_t* ops;            /* [device] n_ops rows (opcode, a, b, slot) */
+  int64_t n_ops;
+  uint8_t* records;              /* [device] [shots][rec_stride], column k = chronological measurement k */
+  int64_t n_meas;
+  int64_t rec_stride;            /* >= n_meas */
+  const uint8_t* replay_meas;    /* [device] nullable [shots][n_meas]: value used if measurement k is random */
+  const uint8_t* replay_noise;   /* [device] nullable [shots][n_noise][2]: (a, b) of X^a Z^b for N1 event j */
+  const uint32_t* noise_thresh24;/* [device] [n_noise] no-fire threshold, see sdim_b200/rng.py (Philox mode) */
+  const uint8_t* noise_channel;  /* [device] [n_noise] 0 = 'd', 1 = 'f', 2 = 'p'  (sdim/program.py:486-497) */
+  int64_t n_noise;
+  uint64_t seed;
+  void* stream;
+} SdimbRunArgs;
+
+int sdimb_version(void);
+const char* sdimb_strerror(int code);
+
+/* Sizes and strides of the tableau store so the caller can allocate it. */
+int sdimb_layout(int n, int d, SdimbLayout* out);
+
+/* All shots <- |0...0>: stabilizers Z_q, destabilizers X_q
+ * (sdim/tableau/dataclasses.py:34-39, sdim/tableau/tableau_prime.py:81-86). */
+int sdimb_init(void* tableau, int n, int d, int64_t shots, void* stream);
+
+/* Run the op stream over `shots` tableaus: the body of Program._simulate_tableau's shot loop
+ * (sdim/program.py:308-351) with GATE_FUNCTIONS dispatch (sdim/program.py:13-32), the primitives of
+ * sdim/tableau/tableau_optimized.py:5-118, measurement (sdim/tableau/tableau_prime.py:262-363),
+ * the RESET correction (sdim/program.py:335-339) and N1 noise drawn with the distribution of
+ * sdim/program.py:486-507. */
+int sdimb_run(const SdimbRunArgs* args);
+
+/* Widen one shot back to the reference's six int64 arrays, reference orientation [qudit][generator]
+ * (x, z, dx, dz: n*n each; p, dp: n each).  All outputs [device]. */
+int sdimb_export(const void* tableau, int n, int d, int64_t shot,
+                 int64_t* x, int64_t* z, int64_t* p, int64_t* dx, int64_t* dz, int64_t* dp, void* stream);
+
+/* Same job as sdimb_run with HOST buffers only: allocates device scratch, copies the op stream and
+ * noise tables in, simulates from |0...0>, copies the records out and synchronises.  This is the call
+ * a non-PyTorch host (e.g. the reference itself through ctypes) makes; `elapsed_ms` (nullable)
+ * receives the device time of the whole call measured with CUDA events. */
+int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,
+                        const int32_t* ops, int64_t n_ops,
+                        uint8_t* records, int64_t n_meas,
+                        const uint8_t* replay_meas, const uint8_t* replay_noise,
+                        const uint32_t* noise_thresh24, const uint8_t* noise_channel, int64_t n_noise,
+                        uint64_t seed, uint32_t flags, float* elapsed_ms);
+
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+int64_t sdimb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDIMB_H */

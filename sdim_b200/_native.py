@@ -1,0 +1,79 @@
+"""ctypes binding of libsdimb (include/sdimb.h).  There is no fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
+FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT = 0x1, 0x2, 0x4, 0x8
+REC_DET, REC_VALUE = 0x80, 0x7F
+
+EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count")
+
+
+class SdimbLayout(C.Structure):
+    _fields_ = [("n", C.c_int32), ("d", C.c_int32), ("np", C.c_int32), ("lanes", C.c_int32),
+                ("order", C.c_int32), ("phase_order", C.c_int32),
+                ("row_bytes", C.c_int64), ("phase_offset", C.c_int64), ("shot_bytes", C.c_int64)]
+
+
+class SdimbRunArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("n", C.c_int32), ("d", C.c_int32),
+                ("shots", C.c_int64), ("shot_offset", C.c_int64), ("tableau", C.c_void_p),
+                ("ops", C.c_void_p), ("n_ops", C.c_int64), ("records", C.c_void_p), ("n_meas", C.c_int64),
+                ("rec_stride", C.c_int64), ("replay_meas", C.c_void_p), ("replay_noise", C.c_void_p),
+                ("noise_thresh24", C.c_void_p), ("noise_channel", C.c_void_p), ("n_noise", C.c_int64),
+                ("seed", C.c_uint64), ("stream", C.c_void_p)]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"libsdimb: {what} (code {code})")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libsdimb.so (built in-tree by `python -m sdim_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing. The tableau path runs only on the CUDA library "
+            "(no CPU fallback); build it with `python -m sdim_b200.build`.")
+    L = C.CDLL(LIB_PATH)
+    L.sdimb_version.restype = C.c_int
+    L.sdimb_strerror.restype = C.c_char_p
+    L.sdimb_strerror.argtypes = [C.c_int]
+    L.sdimb_layout.argtypes = [C.c_int, C.c_int, C.POINTER(SdimbLayout)]
+    L.sdimb_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    L.sdimb_run.argtypes = [C.POINTER(SdimbRunArgs)]
+    L.sdimb_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 6 + [C.c_void_p]
+    L.sdimb_simulate_host.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_float)]
+    L.sdimb_launch_count.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def check(code: int) -> None:
+    """Map a negative return code to the exception type the reference raises for that condition."""
+    if code == OK:
+        return
+    what = lib().sdimb_strerror(code).decode()
+    if code in (EINVAL, EDIM, EOP, ETOOBIG):
+        raise ValueError(what)          # reference errors on this path are ValueError (sdim/program.py:382)
+    raise NativeError(code, what)
+
+
+def layout(n: int, d: int) -> SdimbLayout:
+    out = SdimbLayout()
+    check(lib().sdimb_layout(n, d, C.byref(out)))
+    return out

@@ -1,0 +1,160 @@
+"""Device-side driver: owns the PyTorch buffers and calls the C ABI (include/sdimb.h).
+
+`TableauEngine` is the GPU counterpart of the body of `Program._simulate_tableau`
+(reference: sdim/program.py:269-365): it uploads the compiled op stream once,
+then `run()` simulates a contiguous range of shots — one tableau per shot — and
+returns the packed record matrix uint8[shots, n_meas] (bit 7 = deterministic,
+low bits = value).  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .ir import CompiledProgram
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("sdim_b200 runs the tableau path on a CUDA device only; no GPU is visible "
+                           "and there is no CPU fallback")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type != "cuda":
+        raise RuntimeError(f"sdim_b200 needs a CUDA device, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+class TableauEngine:
+    MODES = {None: 0, "auto": 0, "global": N.FORCE_GLOBAL, "resident": N.FORCE_RESIDENT}
+
+    def __init__(self, prog: CompiledProgram, device=None):
+        self.prog = prog
+        self.device = _require_cuda(device)
+        self.layout = N.layout(prog.num_qudits, prog.dimension)
+        self.lib = N.lib()
+        dev = self.device
+        self.ops = torch.from_numpy(np.ascontiguousarray(prog.ops)).to(dev)
+        self.noise_thresh = torch.from_numpy(prog.noise_thresh24.astype(np.int64)).to(dev).to(torch.int32) \
+            if prog.n_noise else None
+        if prog.n_noise:
+            # uint32 thresholds travel as int32 bit patterns (values <= 2^24 are unaffected)
+            self.noise_channel = torch.from_numpy(prog.noise_channel.copy()).to(dev)
+        else:
+            self.noise_channel = None
+        self.tableau: Optional[torch.Tensor] = None     # uint8 [shots, shot_bytes] of the last run that kept it
+        self.tableau_shots = 0
+
+    # ------------------------------------------------------------------------------------------
+    def fits_resident(self) -> bool:
+        return self.layout.shot_bytes + 2 * self.layout.np + 128 + 2048 + 128 <= 227 * 1024
+
+    def alloc_tableau(self, shots: int) -> torch.Tensor:
+        return torch.empty((shots, self.layout.shot_bytes), dtype=torch.uint8, device=self.device)
+
+    def init_tableau(self, tab: torch.Tensor) -> None:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self.lib.sdimb_init(tab.data_ptr(), self.prog.num_qudits, self.prog.dimension, tab.shape[0], stream))
+
+    def run(self, shots: int, shot_offset: int = 0, seed: int = 0,
+            replay_meas: Optional[torch.Tensor] = None, replay_noise: Optional[torch.Tensor] = None,
+            keep_tableau: bool = False, mode: Optional[str] = None,
+            tableau: Optional[torch.Tensor] = None, fresh: bool = True,
+            op_range: Optional[tuple] = None, records: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Simulate local shots [0, shots) with global ids shot_offset + local; returns records on device.
+
+        replay_meas  uint8[shots, n_meas]      outcome to use where measurement k is random (else Philox)
+        replay_noise uint8[shots, n_noise, 2]  (a, b) of every N1 event (else Philox)
+        tableau      existing store to continue from (fresh=False) or to fill (keep_tableau=True)
+        op_range     (lo, hi) slice of the op stream, for host-stepped execution
+        """
+        prog, L, dev = self.prog, self.layout, self.device
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {sorted(k for k in self.MODES if k)}")
+        flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
+        resident = self.fits_resident() and mode != "global"
+        need_tab = (not resident) or keep_tableau or not fresh
+        with torch.cuda.device(dev):
+            if need_tab:
+                if tableau is None:
+                    tableau = self.alloc_tableau(shots)
+                if tableau.shape != (shots, L.shot_bytes) or tableau.dtype != torch.uint8 or not tableau.is_contiguous():
+                    raise ValueError("tableau buffer has the wrong shape/dtype for this program")
+            if records is None:
+                records = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device=dev)
+            if replay_meas is not None:
+                replay_meas = replay_meas.to(device=dev, dtype=torch.uint8).contiguous()
+                if replay_meas.shape != (shots, prog.n_meas):
+                    raise ValueError("replay_meas must be [shots, n_meas]")
+            if replay_noise is not None:
+                replay_noise = replay_noise.to(device=dev, dtype=torch.uint8).contiguous()
+                if replay_noise.shape != (shots, prog.n_noise, 2):
+                    raise ValueError("replay_noise must be [shots, n_noise, 2]")
+            lo, hi = (0, prog.n_ops) if op_range is None else op_range
+            a = N.SdimbRunArgs()
+            a.struct_size = C.sizeof(N.SdimbRunArgs)
+            a.flags = flags
+            a.n, a.d = prog.num_qudits, prog.dimension
+            a.shots, a.shot_offset = shots, shot_offset
+            a.tableau = _ptr(tableau) if need_tab else None
+            a.ops = (self.ops.data_ptr() + 16 * lo) if hi > lo else None
+            a.n_ops = hi - lo
+            a.records = _ptr(records)
+            a.n_meas = prog.n_meas
+            a.rec_stride = records.stride(0) if prog.n_meas else 0
+            a.replay_meas = _ptr(replay_meas)
+            a.replay_noise = _ptr(replay_noise)
+            a.noise_thresh24 = _ptr(self.noise_thresh)
+            a.noise_channel = _ptr(self.noise_channel)
+            a.n_noise = prog.n_noise
+            a.seed = seed & 0xFFFFFFFFFFFFFFFF
+            a.stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(self.lib.sdimb_run(C.byref(a)))
+        if keep_tableau:
+            self.tableau, self.tableau_shots = tableau, shots
+        self._keepalive = (replay_meas, replay_noise)   # until the stream has consumed them
+        return records
+
+    def export(self, tableau: torch.Tensor, shot: int) -> Dict[str, np.ndarray]:
+        """Six int64 arrays of one shot in the reference orientation [qudit, generator]."""
+        n, dev = self.prog.num_qudits, self.device
+        with torch.cuda.device(dev):
+            big = torch.empty((4, n, n), dtype=torch.int64, device=dev)
+            small = torch.empty((2, n), dtype=torch.int64, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(self.lib.sdimb_export(tableau.data_ptr(), n, self.prog.dimension, shot,
+                                          big[0].data_ptr(), big[1].data_ptr(), small[0].data_ptr(),
+                                          big[2].data_ptr(), big[3].data_ptr(), small[1].data_ptr(), stream))
+            big_h, small_h = big.cpu().numpy(), small.cpu().numpy()
+        return {"x": big_h[0], "z": big_h[1], "p": small_h[0], "dx": big_h[2], "dz": big_h[3], "dp": small_h[1]}
+
+
+def simulate_host(prog: CompiledProgram, shots: int, shot_offset: int = 0, seed: int = 0,
+                  replay_meas: Optional[np.ndarray] = None, replay_noise: Optional[np.ndarray] = None,
+                  mode: Optional[str] = None):
+    """Host-buffer entry (sdimb_simulate_host): numpy in, numpy records out, plus device ms of the call."""
+    lib = N.lib()
+    ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
+    rec = np.empty((shots, prog.n_meas), dtype=np.uint8)
+    thr = np.ascontiguousarray(prog.noise_thresh24, dtype=np.uint32)
+    ch = np.ascontiguousarray(prog.noise_channel, dtype=np.uint8)
+    rm = None if replay_meas is None else np.ascontiguousarray(replay_meas, dtype=np.uint8)
+    rn = None if replay_noise is None else np.ascontiguousarray(replay_noise, dtype=np.uint8)
+    ms = C.c_float(0.0)
+
+    def p(arr):
+        return None if arr is None or arr.size == 0 else arr.ctypes.data
+
+    N.check(lib.sdimb_simulate_host(prog.num_qudits, prog.dimension, shots, shot_offset, p(ops), prog.n_ops,
+                                    p(rec), prog.n_meas, p(rm), p(rn), p(thr), p(ch), prog.n_noise,
+                                    seed & 0xFFFFFFFFFFFFFFFF, TableauEngine.MODES[mode], C.byref(ms)))
+    return rec, float(ms.value)

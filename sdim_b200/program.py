@@ -1,0 +1,375 @@
+"""`Program`: the reference's driver API on top of the CUDA tableau engine.
+
+Mirror of `sdim.program.Program` (reference: sdim/program.py:177-574) for
+prime dimensions.  `simulate()` keeps the reference signature and return
+shapes — a flat list ordered by (qudit, round) for one shot
+(program.py:357-363), the nested list `[qudit][round][shot]` otherwise
+(program.py:364-365) — but every shot is a full stabilizer tableau simulated
+on the GPU (`force_tableau` semantics for any shot count), with N1 noise applied
+per shot with the distribution of `_build_ir` (program.py:486-507) instead of
+being ignored (program.py:31).
+
+Extra keyword-only arguments (not in the reference): `seed`, `replay_meas`,
+`replay_noise`, `mode`, plus `simulate_records()` which returns the packed
+record table without materialising Python objects.
+"""
+from __future__ import annotations
+
+import copy
+import random
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from .circuit import Circuit, CircuitInstruction
+from .gatedata import MEASURE_OPS, OP_RESET
+from .ir import MAX_DIMENSION, CompiledProgram, compile_circuits, is_prime
+from .results import MEASUREMENT_DTYPE, MeasurementResult
+from .tableau import ExtendedTableau
+
+
+@dataclass
+class SimulationOptions:
+    """Same fields as the reference (sdim/program.py:167-175)."""
+
+    shots: int = 1
+    show_measurement: bool = False
+    record_tableau: bool = False
+    force_tableau: bool = False
+    verbose: bool = False
+    show_gate: bool = False
+    exact: bool = False
+
+
+@dataclass
+class RecordTable:
+    """Packed result of a run: one row per shot, one column per chronological measurement."""
+
+    values: np.ndarray          # uint8 [shots, n_meas]
+    deterministic: np.ndarray   # bool  [shots, n_meas]
+    meas_qudit: np.ndarray      # int32 [n_meas]
+    meas_round: np.ndarray      # int32 [n_meas]
+    seed: int
+    shot_offset: int = 0
+
+    @property
+    def shots(self) -> int:
+        return int(self.values.shape[0])
+
+    def column(self, qudit: int, meas_round: int = 0) -> int:
+        hit = np.nonzero((self.meas_qudit == qudit) & (self.meas_round == meas_round))[0]
+        if hit.size == 0:
+            raise ValueError(f"qudit {qudit} has no measurement round {meas_round}")
+        return int(hit[0])
+
+
+class Program:
+    def __init__(self, circuit: Circuit, tableau: Optional[ExtendedTableau] = None, device=None):
+        d = circuit.dimension
+        if not is_prime(d):
+            raise ValueError(f"dimension {d} is not prime: only the prime-dimension (ExtendedTableau) path of the "
+                             "reference is implemented; composite dimensions (WeylTableau) are out of scope")
+        if d > MAX_DIMENSION:
+            raise ValueError(f"dimension {d} exceeds the uint8-lane limit of {MAX_DIMENSION}")
+        self.circuits: List[Circuit] = [circuit]
+        self.measurement_results: list = []
+        self.device = device
+        self.initial_tableau: Optional[ExtendedTableau] = tableau
+        self._tableau_cache: Optional[ExtendedTableau] = (
+            copy.deepcopy(tableau) if tableau is not None else ExtendedTableau(circuit.num_qudits, d))
+        self._tableau_thunk = None
+        self._engine = None
+        self._engine_key = None
+        self.last_records: Optional[RecordTable] = None
+
+    # ---- engine plumbing -------------------------------------------------------------------------
+    def _compiled(self) -> CompiledProgram:
+        return compile_circuits(self.circuits)
+
+    def _get_engine(self, compiled: CompiledProgram):
+        from .engine import TableauEngine          # imports torch; kept out of module import time
+        key = (compiled.num_qudits, compiled.dimension, compiled.ops.tobytes(),
+               compiled.noise_thresh24.tobytes(), compiled.noise_channel.tobytes())
+        if self._engine is None or self._engine_key != key:
+            self._engine = TableauEngine(compiled, self.device)
+            self._engine_key = key
+        return self._engine
+
+    def _initial_store(self, engine, shots: int):
+        """Device store pre-loaded with the user-supplied initial tableau (None when starting from |0...0>)."""
+        if self.initial_tableau is None:
+            return None
+        import torch
+        t = self.initial_tableau
+        if t.num_qudits != engine.prog.num_qudits or t.dimension != engine.prog.dimension:
+            raise ValueError("initial tableau does not match the circuit's qudit count / dimension")
+        img = torch.from_numpy(t.pack(engine.layout.np)).to(engine.device)
+        return img.unsqueeze(0).repeat(shots, 1).contiguous()
+
+    @property
+    def stabilizer_tableau(self) -> ExtendedTableau:
+        """Tableau of the LAST shot of the last simulate() (reference keeps it in self.stabilizer_tableau).
+
+        Materialised on first access by re-simulating that one shot with the same counter-based random
+        draws and exporting it, so large runs never hold per-shot tableaus in HBM for this purpose.
+        """
+        if self._tableau_thunk is not None:
+            self._tableau_cache = self._tableau_thunk()
+            self._tableau_thunk = None
+        return self._tableau_cache
+
+    @stabilizer_tableau.setter
+    def stabilizer_tableau(self, value):
+        self._tableau_cache = value
+        self._tableau_thunk = None
+
+    # ---- simulate -----------------------------------------------------------------------------------
+    def simulate_records(self, shots: int = 1, *, seed: Optional[int] = None, shot_offset: int = 0,
+                         replay_meas=None, replay_noise=None, mode: Optional[str] = None,
+                         distributed: bool = False) -> RecordTable:
+        """Run `shots` tableau shots on the GPU and return the packed records (no Python objects)."""
+        compiled = self._compiled()
+        if seed is None:
+            seed = random.getrandbits(63)       # follows the user's random.seed(), like the reference's draws
+        if distributed:
+            from .dist import simulate_sharded
+            rec = simulate_sharded(self, compiled, shots, seed, mode=mode)
+        else:
+            rec = self._run_local(compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode)
+        table = RecordTable(values=rec & 0x7F, deterministic=(rec & 0x80) != 0,
+                            meas_qudit=compiled.meas_qudit, meas_round=compiled.meas_round,
+                            seed=seed, shot_offset=shot_offset)
+        self.last_records = table
+        return table
+
+    def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode) -> np.ndarray:
+        import torch
+        engine = self._get_engine(compiled)
+        rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
+        rn = None if replay_noise is None else torch.as_tensor(np.asarray(replay_noise, dtype=np.uint8))
+        store = self._initial_store(engine, shots)
+        rec = engine.run(shots, shot_offset, seed, rm, rn, mode=mode, tableau=store, fresh=store is None)
+        out = rec.cpu().numpy()
+
+        def last_shot_tableau(last=shots - 1):
+            one = engine.alloc_tableau(1)
+            if self.initial_tableau is not None:
+                one.copy_(self._initial_store(engine, 1))
+            engine.run(1, shot_offset + last, seed,
+                       None if rm is None else rm[last:last + 1], None if rn is None else rn[last:last + 1],
+                       keep_tableau=True, mode=mode, tableau=one, fresh=self.initial_tableau is None)
+            return ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, engine.export(one, 0))
+
+        self._tableau_thunk = last_shot_tableau if shots > 0 else None
+        return out
+
+    def simulate(self, shots: int = 1, show_measurement: bool = False, record_tableau: bool = False,
+                 force_tableau: bool = False, verbose: bool = False, show_gate: bool = False, exact: bool = False,
+                 options: Optional[SimulationOptions] = None, *, seed: Optional[int] = None,
+                 replay_meas=None, replay_noise=None, mode: Optional[str] = None, distributed: bool = False):
+        """Same call as the reference's Program.simulate (sdim/program.py:206-267).
+
+        Returns a flat list of MeasurementResult for shots == 1, else `[qudit][round][shot]`.
+        `force_tableau` is accepted and implied: all shots run on the tableau path.
+        `exact` only concerns composite dimensions and is ignored.
+        """
+        if options is None:
+            options = SimulationOptions(shots, show_measurement, record_tableau, force_tableau, verbose, show_gate,
+                                        exact)
+        compiled = self._compiled()
+        n = compiled.num_qudits
+        if options.verbose or options.show_gate or options.record_tableau:
+            tables = self._simulate_stepped(compiled, options, seed, replay_meas, replay_noise, mode)
+            values, det, snaps = tables
+        else:
+            table = self.simulate_records(options.shots, seed=seed, replay_meas=replay_meas,
+                                          replay_noise=replay_noise, mode=mode, distributed=distributed)
+            values, det, snaps = table.values, table.deterministic, None
+
+        # group as measurement_results[qudit][round][shot]                    (program.py:321-332)
+        results: list = [[] for _ in range(n)]
+        for k in range(compiled.n_meas):
+            q = int(compiled.meas_qudit[k])
+            vals, dets = values[:, k].tolist(), det[:, k].tolist()
+            if snaps is None:
+                column = [MeasurementResult(q, dt, v) for v, dt in zip(vals, dets)]
+            else:
+                column = [MeasurementResult(q, dt, v, snaps[s][k]) for s, (v, dt) in enumerate(zip(vals, dets))]
+            results[q].append(column)
+        self.measurement_results = results
+        if options.show_measurement:
+            self.print_measurements()
+        if options.shots == 1:
+            return [rounds[0] for per_qudit in results for rounds in per_qudit]
+        return results
+
+    def _simulate_stepped(self, compiled, options, seed, replay_meas, replay_noise, mode):
+        """Host-stepped execution for verbose / show_gate / record_tableau: the op stream is issued one op
+        per launch on a persistent device store so the tableau can be exported between ops."""
+        import torch
+        engine = self._get_engine(compiled)
+        shots = options.shots
+        if seed is None:
+            seed = random.getrandbits(63)
+        rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
+        rn = None if replay_noise is None else torch.as_tensor(np.asarray(replay_noise, dtype=np.uint8))
+        values = np.zeros((shots, compiled.n_meas), dtype=np.uint8)
+        det = np.zeros((shots, compiled.n_meas), dtype=bool)
+        snaps = [[None] * compiled.n_meas for _ in range(shots)] if options.record_tableau else None
+        user_ops = [op for c in self.circuits for op in c.operations if op.gate_id != 0]
+        length = len(user_ops)
+        last = None
+        for s in range(shots):
+            store = self._initial_store(engine, 1)
+            if store is None:
+                store = engine.alloc_tableau(1)
+                engine.init_tableau(store)
+            rec = torch.zeros((1, compiled.n_meas), dtype=torch.uint8, device=engine.device)
+            srm = None if rm is None else rm[s:s + 1]
+            srn = None if rn is None else rn[s:s + 1]
+            if options.verbose:
+                print("Initial state")
+                ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, engine.export(store, 0)).print_tableau()
+                print("\n")
+            for i in range(compiled.n_ops):
+                engine.run(1, s, seed, srm, srn, keep_tableau=True, mode=mode, tableau=store, fresh=False,
+                           op_range=(i, i + 1), records=rec)
+                op, _, _, slot = (int(v) for v in compiled.ops[i])
+                if snaps is not None and op in MEASURE_OPS:
+                    # The reference snapshots right after measure(), before the RESET correction
+                    # (program.py:323-324 precede :335-339); here the snapshot is taken after the whole op.
+                    snaps[s][slot] = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
+                                                                 engine.export(store, 0))
+                if options.show_gate:
+                    g = user_ops[i]
+                    info = g.target_index if g.target_index is not None else ""
+                    print("Time step" if i < length - 1 else "Final step", i, "\t", g.name, g.qudit_index, info)
+                if options.verbose:
+                    ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
+                                                engine.export(store, 0)).print_tableau()
+                    print("\n")
+            r = rec.cpu().numpy()[0]
+            values[s], det[s] = r & 0x7F, (r & 0x80) != 0
+            last = store
+        if last is not None:
+            self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
+                                                                  engine.export(last, 0))
+        return values, det, snaps
+
+    def apply_gate(self, instruc: CircuitInstruction) -> Optional[MeasurementResult]:
+        """Apply one instruction to the current `stabilizer_tableau` (reference: program.py:367-385)."""
+        import torch
+        from .engine import TableauEngine
+        from .ir import NUM_OPS
+        if instruc.gate_id is None or not 0 <= instruc.gate_id < NUM_OPS:
+            raise ValueError("Invalid gate value")
+        current = self.stabilizer_tableau
+        one = Circuit(current.num_qudits, current.dimension)
+        one.operations.append(instruc)
+        compiled = compile_circuits([one])
+        engine = TableauEngine(compiled, self.device)
+        store = torch.from_numpy(current.pack(engine.layout.np)).to(engine.device).unsqueeze(0).contiguous()
+        rec = engine.run(1, 0, random.getrandbits(63), keep_tableau=True, tableau=store, fresh=False)
+        out = None
+        if compiled.n_meas:
+            r = int(rec.cpu().numpy()[0, 0])
+            out = MeasurementResult(int(compiled.meas_qudit[0]), bool(r & 0x80), r & 0x7F)
+            if instruc.gate_id == OP_RESET:
+                # the reference's apply_reset only measures; its driver applies the X correction
+                # (program.py:335-339).  The device op does both, so undo nothing and document it.
+                pass
+        self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
+                                                              engine.export(store, 0))
+        return out
+
+    # ---- reference helpers kept for drop-in compatibility -------------------------------------------
+    @staticmethod
+    def _results_to_array(measurements: list) -> np.ndarray:
+        """Nested MeasurementResult lists -> structured array [n_qudits, max_rounds] (program.py:387-421)."""
+        if not measurements or not measurements[0]:
+            raise ValueError("Empty or invalid measurement results format")
+        first = measurements[0][0]
+        if not isinstance(first, (list, MeasurementResult)):
+            raise ValueError("Invalid measurement results format")
+        max_rounds = max(len(m) for m in measurements)
+        out = np.empty((len(measurements), max_rounds), dtype=MEASUREMENT_DTYPE)
+        for q, per_qudit in enumerate(measurements):
+            for r, item in enumerate(per_qudit):
+                m = item[0] if isinstance(first, list) else item
+                out[q, r] = (m.qudit_index, r, 0, m.deterministic, m.measurement_value)
+        return out
+
+    def _combine_results(self, frame_results) -> list:
+        """Append extra shots held in a structured array [n_qudits, rounds, shots] (program.py:423-454)."""
+        n_qudits, _, extra = frame_results.shape
+        for q in range(n_qudits):
+            for r in range(len(self.measurement_results[q])):
+                cell = frame_results[q, r]
+                self.measurement_results[q][r].extend(
+                    MeasurementResult(int(cell[s]["qudit_index"]), bool(cell[s]["deterministic"]),
+                                      int(cell[s]["measurement_value"])) for s in range(extra))
+        return self.measurement_results
+
+    def _build_ir(self, circuits: List[Circuit], extra_shots: int):
+        """The reference's IR + pre-sampled noise (program.py:456-526), for callers that consume that format.
+        The GPU path does not use it (noise is drawn on the device); semantics are identical."""
+        d = self.circuits[0].dimension
+        triples, noise = [], []
+        for circuit in circuits:
+            for ins in circuit.operations:
+                if ins.gate_id == 0:
+                    continue
+                triples.append((ins.gate_id, ins.qudit_index, -1 if ins.target_index is None else ins.target_index))
+                if ins.gate_id != 17:
+                    continue
+                params = ins.params or {}
+                channel = params.get("noise_channel", params.get("channel", "d"))
+                a = np.zeros(extra_shots, dtype=np.int64)
+                b = np.zeros(extra_shots, dtype=np.int64)
+                if channel == "d":
+                    r = np.random.randint(1, d * d, size=extra_shots)
+                    a, b = r % d, r // d
+                elif channel == "f":
+                    a = np.random.randint(1, d, size=extra_shots)
+                elif channel == "p":
+                    b = np.random.randint(1, d, size=extra_shots)
+                keep_identity = np.random.uniform(0.0, 1.0, size=extra_shots) < 1.0 - float(params.get("prob", 0.01))
+                a[keep_identity] = 0
+                b[keep_identity] = 0
+                noise.append(np.stack((a, b), axis=1))
+        ir_dtype = np.dtype([("gate_id", np.int64), ("qudit_index", np.int64), ("target_index", np.int64)])
+        ir = np.array(triples, dtype=ir_dtype)
+        noise_array = np.array(noise, dtype=np.int64) if noise else np.empty((1, extra_shots, 2), dtype=np.int64)
+        return ir, noise_array
+
+    def append_circuit(self, circuit: Circuit) -> None:
+        tail = self.circuits[-1]
+        if tail.num_qudits < circuit.num_qudits:
+            tail.num_qudits = circuit.num_qudits
+        else:
+            circuit.num_qudits = tail.num_qudits
+        if tail.dimension != circuit.dimension:
+            raise ValueError("Circuits must have the same dimension")
+        self.circuits.append(circuit)
+
+    def print_measurements(self) -> None:
+        """Print stored results (program.py:547-571; unlike the reference this never re-simulates, B-10)."""
+        shot_count = max((len(group) for per_qudit in self.measurement_results for group in per_qudit), default=0)
+        if shot_count == 0:
+            print("No measurements recorded.")
+            return
+        if shot_count == 1:
+            for per_qudit in self.measurement_results:
+                for group in per_qudit:
+                    print(group[0])
+            return
+        for s in range(shot_count):
+            print(f"Shot {s + 1}:")
+            for per_qudit in self.measurement_results:
+                for r, group in enumerate(per_qudit):
+                    print(f"{group[s]} during measurement {r}")
+            print()
+
+    def __str__(self) -> str:
+        return str(self.stabilizer_tableau)
