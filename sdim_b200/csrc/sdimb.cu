@@ -88,11 +88,16 @@ struct KParams {
 
 // Shared scratch common to both modes (carved from dynamic shared memory after the resident tableau).
 struct Scratch {
-  uint8_t* xs;         // [np] pivot column X (random branch) / destabilizer factors f (deterministic branch)
-  uint8_t* zs;         // [np] pivot column Z
-  uint8_t* inv;        // [128] multiplicative inverses mod d
+  uint32_t* dot;       // [W]    per-lane accumulator of Z[:,i] . x_p          (random branch)
+  uint32_t* fw;        // [W/4]  packed factors f = -X[q,i] mod d, 4 lanes/word (random branch)
+  uint32_t* red;       // [32]   cross-warp reduction scratch
+  uint32_t* cnt;       // [4]    list lengths
   uint16_t* noise;     // [kNoiseChunk] decoded (a | b << 8) of N1 events [noise_lo, noise_lo + kNoiseChunk)
-  uint32_t* red;       // [32] cross-warp reduction scratch
+  uint16_t* ar;        // [np]   active rows: qudits on which the pivot acts / active generators (det branch)
+  uint16_t* aw;        // [W/4]  active words: lane quads holding a non-zero factor
+  uint8_t* xs;         // [np]   pivot column X (random branch) / factors of the active generators (det branch)
+  uint8_t* zs;         // [np]   pivot column Z
+  uint8_t* inv;        // [128]  multiplicative inverses mod d
   int64_t noise_lo;    // first event held in `noise` (-1 = empty); uniform across the CTA, kept in registers
 };
 
@@ -297,13 +302,23 @@ __device__ void fill_noise(const KParams& p, Scratch& S, int64_t lo, int64_t sho
 
 // ---------------------------------------------------------------------------------------------
 // Measurement of qudit q in the Z basis (tableau_prime.py:262-363).  Returns the outcome to every thread.
+//
+// The reference skips generators whose factor is zero (tableau_prime.py:308,315,351) and its column
+// updates are no-ops on qudits where the pivot is the identity.  Both sparsities are exploited here:
+// the update runs over (active row) x (active lane-quad) pairs spread across the whole CTA, with kBatch
+// independent loads in flight per thread, so a sparse measurement costs a handful of memory round trips
+// and a dense one streams the tableau with full memory-level parallelism.
 // ---------------------------------------------------------------------------------------------
+constexpr int kBatch = 4;
+
 __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int64_t slot, int64_t shot_local) {
   const Arith& A = p.A;
   const int n = p.n, W = p.W, npad = p.np, nt = blockDim.x, tid = threadIdx.x;
+  const int wz = W / 4;
   uint8_t* rowq = T + (int64_t)q * p.row_bytes;
   uint8_t* P8 = T + p.phase_off;
-  __syncthreads();   // gate writes of other threads' lanes become visible
+  if (tid < 4) S.cnt[tid] = 0;
+  __syncthreads();   // gate writes of other threads' lanes become visible; counters reset
 
   // -- pivot: FIRST stabilizer with an X component on q (tableau_prime.py:273-283) ------------------
   uint32_t best = kNoPivot;
@@ -334,68 +349,122 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
     const uint32_t e = S.inv[v];
     const uint32_t ps_old = P8[piv];
     uint32_t sd_raw = 0;
-    for (int r = tid; r < n; r += nt) {
+    for (int r = tid; r < n; r += nt) {                       // pivot column -> xs/zs, active-row list
       const uint8_t* row = T + (int64_t)r * p.row_bytes;
       const uint32_t xr = row[piv], zr = row[W + piv];
       S.xs[r] = (uint8_t)mod_d(A, xr * e);
       S.zs[r] = (uint8_t)mod_d(A, zr * e);
       sd_raw += mod_d(A, xr * zr);
+      if (xr | zr) S.ar[atomicAdd(&S.cnt[0], 1u)] = (uint16_t)r;
     }
-    sd_raw = mod_d(A, block_sum(sd_raw, S.red));                       // also publishes xs/zs
-    const uint32_t ps = mod_o(A, ps_old * e + A.po * mod_d(A, sd_raw * mod_d(A, (e * (e - 1u)) >> 1)));
-    const uint32_t sd = mod_d(A, mod_d(A, sd_raw * e) * e);            // x_p . z_p after exponentiation
-
-    for (int w = tid; w < W / 4; w += nt) {
+    for (int w = tid; w < wz; w += nt) {                      // factors f = -X[q,i] mod d, active-word list
       const uint32_t xq_w = reinterpret_cast<const uint32_t*>(rowq)[w];
-      uint32_t f[4], any = 0;
+      uint32_t fw = 0;
+      if (xq_w) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        f[k] = (4u * w + k == piv) ? 0u : neg_d(A, byte_of(xq_w, k));  // f = -X[q,i] mod d; pivot itself skipped
-        any |= f[k];
+        for (int k = 0; k < 4; ++k)
+          if (4u * w + k != piv) fw |= neg_d(A, byte_of(xq_w, k)) << (8 * k);   // the pivot itself is skipped
       }
-      if (!any) continue;
-      uint32_t dot[4] = {0, 0, 0, 0};
-      for (int r = 0; r < n; ++r) {
-        const uint32_t s = S.xs[r], t = S.zs[r];
-        if ((s | t) == 0) continue;
-        uint32_t* xp = reinterpret_cast<uint32_t*>(T + (int64_t)r * p.row_bytes) + w;
-        uint32_t* zp = xp + W / 4;
-        const uint32_t xw = *xp, zw = *zp;
-        uint32_t nx = 0, nz = 0;
+      S.fw[w] = fw;
+      if (fw) {
+        S.aw[atomicAdd(&S.cnt[1], 1u)] = (uint16_t)w;
+        *reinterpret_cast<uint4*>(S.dot + 4 * w) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    sd_raw = mod_d(A, block_sum(sd_raw, S.red));              // barrier: publishes xs/zs/ar/fw/aw/dot/cnt
+    const uint32_t ps = mod_o(A, ps_old * e + A.po * mod_d(A, sd_raw * mod_d(A, (e * (e - 1u)) >> 1)));
+    const uint32_t sd = mod_d(A, mod_d(A, sd_raw * e) * e);   // x_p . z_p after exponentiation
+    const int nr_a = (int)S.cnt[0], nw_a = (int)S.cnt[1];
+
+    // col_i += f_i * col_p over all (active row, active word) pairs; pair id = ri * nw_a + wi
+    if (nw_a > 0) {
+      const int npairs = nr_a * nw_a;
+      const int dw = nt % nw_a, dr = nt / nw_a;
+      int wi = tid % nw_a, ri = tid / nw_a;
+      int cur_w = -1;
+      uint32_t dot0 = 0, dot1 = 0, dot2 = 0, dot3 = 0;
+      for (int base = tid; base < npairs; base += nt * kBatch) {
+        uint32_t xw[kBatch], zw[kBatch];
+        int rr[kBatch], ww[kBatch];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t zb = byte_of(zw, k);
-          dot[k] += zb * s;                                            // Z[:,i] . x_p
-          nx |= mod_d(A, byte_of(xw, k) + f[k] * s) << (8 * k);        // col_i += f * col_p
-          nz |= mod_d(A, zb + f[k] * t) << (8 * k);
+        for (int u = 0; u < kBatch; ++u) {
+          rr[u] = -1;
+          if (base + u * nt < npairs) {
+            rr[u] = S.ar[ri];
+            ww[u] = S.aw[wi];
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(T + (int64_t)rr[u] * p.row_bytes) + ww[u];
+            xw[u] = src[0];
+            zw[u] = src[wz];
+            wi += dw; ri += dr;
+            if (wi >= nw_a) { wi -= nw_a; ++ri; }
+          }
         }
-        *xp = nx; *zp = nz;
-        if ((r & 63) == 63) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dot[k] = mod_d(A, dot[k]);
+        for (int u = 0; u < kBatch; ++u) {
+          if (rr[u] < 0) continue;
+          if (ww[u] != cur_w) {
+            if (cur_w >= 0) {
+              atomicAdd(&S.dot[4 * cur_w + 0], dot0); atomicAdd(&S.dot[4 * cur_w + 1], dot1);
+              atomicAdd(&S.dot[4 * cur_w + 2], dot2); atomicAdd(&S.dot[4 * cur_w + 3], dot3);
+            }
+            cur_w = ww[u]; dot0 = dot1 = dot2 = dot3 = 0;
+          }
+          const uint32_t s = S.xs[rr[u]], t = S.zs[rr[u]], fw = S.fw[ww[u]];
+          const uint32_t z0 = byte_of(zw[u], 0), z1 = byte_of(zw[u], 1), z2 = byte_of(zw[u], 2), z3 = byte_of(zw[u], 3);
+          dot0 = mod_d(A, dot0 + z0 * s); dot1 = mod_d(A, dot1 + z1 * s);    // Z[:,i] . x_p (old Z)
+          dot2 = mod_d(A, dot2 + z2 * s); dot3 = mod_d(A, dot3 + z3 * s);
+          uint32_t nx = 0, nz = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t fk = byte_of(fw, k);
+            nx |= mod_d(A, byte_of(xw[u], k) + fk * s) << (8 * k);
+            nz |= mod_d(A, byte_of(zw[u], k) + fk * t) << (8 * k);
+          }
+          uint32_t* dst = reinterpret_cast<uint32_t*>(T + (int64_t)rr[u] * p.row_bytes) + ww[u];
+          dst[0] = nx;
+          dst[wz] = nz;
         }
       }
+      if (cur_w >= 0) {
+        atomicAdd(&S.dot[4 * cur_w + 0], dot0); atomicAdd(&S.dot[4 * cur_w + 1], dot1);
+        atomicAdd(&S.dot[4 * cur_w + 2], dot2); atomicAdd(&S.dot[4 * cur_w + 3], dot3);
+      }
+    }
+    __syncthreads();
+    // phase_i += f_i * phase_p + po * (f_i * (Z_i . x_p) + (x_p . z_p) * f_i(f_i-1)/2 * po)     (:310-312,317-319)
+    for (int i = tid; i < nw_a; i += nt) {
+      const int w = S.aw[i];
+      const uint32_t fw = S.fw[w];
       uint32_t* Pw = reinterpret_cast<uint32_t*>(P8) + w;
       const uint32_t ph = *Pw;
       uint32_t nph = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t fk = f[k];
+        const uint32_t fk = byte_of(fw, k);
         const uint32_t g = mod_d(A, (fk * (fk - 1u)) >> 1);
-        const uint32_t cp = mod_d(A, mod_d(A, dot[k]) * fk + sd * g * A.po);
+        const uint32_t cp = mod_d(A, mod_d(A, S.dot[4 * w + k]) * fk + sd * g * A.po);
         nph |= mod_o(A, byte_of(ph, k) + fk * ps + A.po * cp) << (8 * k);
       }
       *Pw = nph;
     }
     __syncthreads();
-    // destabilizer p <- old pivot, stabilizer p <- Z_q with phase -m*po (tableau_prime.py:323-333)
+    // destabilizer p <- old pivot, stabilizer p <- Z_q with phase -m*po (tableau_prime.py:323-333).
+    // Column accesses cost one DRAM sector per byte, so only entries that change are written: the
+    // stabilizer lane is non-zero exactly on the pivot's support (the active rows), the destabilizer
+    // lane is read back and rewritten where it differs.
+    for (int i = tid; i < nr_a; i += nt) {
+      uint8_t* row = T + (int64_t)S.ar[i] * p.row_bytes;
+      row[piv] = 0;
+      row[W + piv] = 0;
+    }
     for (int r = tid; r < n; r += nt) {
       uint8_t* row = T + (int64_t)r * p.row_bytes;
-      row[npad + piv] = S.xs[r];
-      row[W + npad + piv] = S.zs[r];
-      row[piv] = 0;
-      row[W + piv] = (r == q) ? 1 : 0;
+      const uint8_t xs = S.xs[r], zs = S.zs[r];
+      if (row[npad + piv] != xs) row[npad + piv] = xs;
+      if (row[W + npad + piv] != zs) row[W + npad + piv] = zs;
     }
+    __syncthreads();
+    if (tid == 0) rowq[W + piv] = 1;
     outcome = draw;
     if (tid == 0) {
       P8[npad + piv] = (uint8_t)ps;
@@ -404,30 +473,56 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
     rec = outcome;
   } else {
     // -- deterministic branch (tableau_prime.py:336-363): ordered accumulation over generators ----------
+    // Ordered compaction of the generators with a non-zero factor f_i = destab X[q,i] (order matters: the
+    // cross term uses the running ancilla, :354-357).
     uint32_t a1 = 0;
-    for (int i = tid; i < n; i += nt) {
-      const uint32_t f = rowq[npad + i];
-      S.xs[i] = (uint8_t)f;
-      a1 += f * P8[i];
+    int total = 0;
+    __syncthreads();   // every warp has finished reading S.red in block_min before it is reused below
+    for (int base = 0; base < n; base += nt) {
+      const int i = base + tid;
+      const uint32_t f = (i < n) ? rowq[npad + i] : 0u;
+      const uint32_t mask = __ballot_sync(0xFFFFFFFFu, f != 0);
+      if ((tid & 31) == 0) S.red[tid >> 5] = __popc(mask);
+      __syncthreads();
+      int off = total, all = total;
+      for (int wv = 0; wv < (nt >> 5); ++wv) {
+        const int c = (int)S.red[wv];
+        if (wv < (tid >> 5)) off += c;
+        all += c;
+      }
+      if (f) {
+        const int pos = off + __popc(mask & ((1u << (tid & 31)) - 1u));
+        S.ar[pos] = (uint16_t)i;
+        S.xs[pos] = (uint8_t)f;
+        a1 += f * P8[i];
+      }
+      total = all;
+      __syncthreads();
     }
-    a1 = mod_o(A, block_sum(mod_o(A, a1), S.red));                      // sum_i f_i * phase_i; publishes f
-    uint32_t cross = 0, sdg = 0;
+    a1 = mod_o(A, block_sum(mod_o(A, a1), S.red));            // sum_i f_i * phase_i; publishes the lists
+    uint32_t part = 0;
     for (int r = tid; r < n; r += nt) {
       const uint8_t* xr = T + (int64_t)r * p.row_bytes;
       const uint8_t* zr = xr + W;
-      uint32_t az = 0;
-      for (int i = 0; i < n; ++i) {
-        const uint32_t f = S.xs[i];
-        if (!f) continue;
-        const uint32_t xi = xr[i], zi = zr[i];
-        cross = mod_d(A, cross + mod_d(A, f * xi) * az);                // ancilla_z . (f * x_i), running ancilla
-        az = mod_d(A, az + f * zi);
-        sdg = mod_d(A, sdg + mod_d(A, xi * zi) * mod_d(A, (f * (f - 1u)) >> 1));
+      uint32_t az = 0, cross = 0, sdg = 0;
+      for (int base = 0; base < total; base += kBatch) {
+        uint32_t xi[kBatch], zi[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          if (base + u < total) { const int g = S.ar[base + u]; xi[u] = xr[g]; zi[u] = zr[g]; }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          if (base + u >= total) break;
+          const uint32_t f = S.xs[base + u];
+          cross = mod_d(A, cross + mod_d(A, f * xi[u]) * az);  // ancilla_z . (f * x_i), running ancilla
+          az = mod_d(A, az + f * zi[u]);
+          sdg = mod_d(A, sdg + mod_d(A, xi[u] * zi[u]) * mod_d(A, (f * (f - 1u)) >> 1));
+        }
       }
+      part += mod_d(A, cross + A.po * sdg);
     }
-    cross = mod_d(A, block_sum(cross, S.red));
-    sdg = mod_d(A, block_sum(sdg, S.red));
-    const uint32_t ap = mod_o(A, a1 + A.po * mod_d(A, cross + A.po * sdg));
+    part = mod_d(A, block_sum(part, S.red));
+    const uint32_t ap = mod_o(A, a1 + A.po * part);
     // (-ap // po) % d with Python floor semantics (tableau_prime.py:362)
     outcome = (A.po == 1) ? neg_d(A, ap) : (((ap + 1u) >> 1) & 1u);
     rec = outcome | SDIMB_REC_DET;
@@ -444,11 +539,16 @@ __global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_consta
   extern __shared__ __align__(16) uint8_t smem[];
   const int64_t tab_smem = p.resident ? p.shot_bytes : 0;
   Scratch S;
-  S.xs = smem + tab_smem;
+  S.dot = reinterpret_cast<uint32_t*>(smem + tab_smem);
+  S.fw = S.dot + p.W;
+  S.red = S.fw + p.W / 4;
+  S.cnt = S.red + 32;
+  S.noise = reinterpret_cast<uint16_t*>(S.cnt + 4);
+  S.ar = S.noise + kNoiseChunk;
+  S.aw = S.ar + p.np;
+  S.xs = reinterpret_cast<uint8_t*>(S.aw + p.W / 4);
   S.zs = S.xs + p.np;
   S.inv = S.zs + p.np;
-  S.noise = reinterpret_cast<uint16_t*>(S.inv + 128);
-  S.red = reinterpret_cast<uint32_t*>(S.noise + kNoiseChunk);
   const Arith& A = p.A;
 
   for (uint32_t v = threadIdx.x; v < A.d; v += blockDim.x) {   // inverse table; inv[0] unused
@@ -569,7 +669,10 @@ int block_threads(int W) {
   return t;
 }
 
-size_t scratch_bytes(int np) { return (size_t)2 * np + 128 + kNoiseChunk * sizeof(uint16_t) + 32 * sizeof(uint32_t); }
+size_t scratch_bytes(int np) {
+  const size_t W = 2 * (size_t)np;
+  return 4 * W + W + 32 * 4 + 4 * 4 + kNoiseChunk * 2 + 2 * (size_t)np + 2 * (W / 4) + 2 * (size_t)np + 128;
+}
 
 }  // namespace
 
@@ -625,11 +728,11 @@ int sdimb_run(const SdimbRunArgs* a) {
   const int rc = sdimb_layout(a->n, a->d, &L);
   if (rc) return rc;
   if (a->shots < 0 || a->n_ops < 0 || a->n_meas < 0 || a->n_noise < 0) return SDIMB_EINVAL;
+  if ((a->flags & SDIMB_FORCE_GLOBAL) && (a->flags & SDIMB_FORCE_RESIDENT)) return SDIMB_EINVAL;
+  if (a->shots == 0) return SDIMB_OK;
   if (a->n_ops > 0 && !a->ops) return SDIMB_EINVAL;
   if (a->n_meas > 0 && (!a->records || a->rec_stride < a->n_meas)) return SDIMB_EINVAL;
   if (a->n_noise > 0 && !a->replay_noise && (!a->noise_thresh24 || !a->noise_channel)) return SDIMB_EINVAL;
-  if ((a->flags & SDIMB_FORCE_GLOBAL) && (a->flags & SDIMB_FORCE_RESIDENT)) return SDIMB_EINVAL;
-  if (a->shots == 0) return SDIMB_OK;
 
   const size_t scratch = scratch_bytes(L.np);
   const bool fits = (size_t)L.shot_bytes + scratch <= (size_t)kSmemLimit;

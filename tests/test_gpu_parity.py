@@ -39,3 +39,149 @@ def test_golden_random_circuits_replay(golden_random, mode):
                     f"final {key} differs: seed {case['seed']} n={n} d={d}"
         checked += 1
     assert checked == len(golden_random) >= 100
+
+
+# ---------------------------------------------------------------------------------------------------
+# Free-running (Philox) mode against the C oracle: same counters on both sides -> bit-exact records
+# ---------------------------------------------------------------------------------------------------
+def _run_gpu(prog, shots, seed, mode=None, shot_offset=0, keep=False):
+    from sdim_b200.engine import TableauEngine
+    eng = TableauEngine(prog)
+    rec = eng.run(shots, shot_offset, seed, mode=mode, keep_tableau=keep)
+    return eng, rec.cpu().numpy()
+
+
+@pytest.mark.parametrize("d,n,depth", [(2, 5, 120), (2, 40, 900), (3, 1, 30), (3, 17, 500), (3, 64, 1500),
+                                        (5, 33, 800), (7, 16, 400), (11, 9, 300), (13, 21, 500), (127, 6, 200)])
+@pytest.mark.parametrize("mode", ["resident", "global"])
+def test_philox_mode_matches_c_oracle(d, n, depth, mode):
+    """Every opcode incl. M_X, RESET, SWAP and all three noise channels; ragged n (not a multiple of 16)."""
+    from make_cases import random_program
+    from oracle import c_oracle
+    prog = random_program(seed=1000 * d + n, n=n, d=d, depth=depth)
+    shots, seed = 96, 2026 + d
+    eng, got = _run_gpu(prog, shots, seed, mode, keep=True)
+    want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
+                             channel=prog.noise_channel, want_final=True)
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, shots - 1)       # final tableau of the last shot, all six arrays
+    for key in ("x", "z", "p", "dx", "dz", "dp"):
+        assert np.array_equal(arrs[key], fin[key]), key
+    if prog.n_noise:
+        assert len({got[s].tobytes() for s in range(shots)}) > 1    # noise/draws really differ between shots
+
+
+def test_noise_cache_refill_many_events():
+    """More N1 events than one shared-memory noise chunk (1024), interleaved with measurements."""
+    from make_cases import random_program
+    from oracle import c_oracle
+    prog = random_program(seed=77, n=8, d=3, depth=9000, p_meas=0.05, p_noise=0.4, noise_prob=0.2)
+    assert prog.n_noise > 3000
+    _, got = _run_gpu(prog, 40, 5)
+    want = c_oracle.run_philox(prog, 40, 0, 5)
+    assert np.array_equal(got, want)
+
+
+def test_headline_size_matches_c_oracle():
+    """BASELINE headline shape (d=3, n=256, 2000 gates + N1 after each + 256 M) at a shot count the C oracle
+    finishes in seconds; global-memory mode (one tableau = 262,656 B does not fit in shared memory)."""
+    from oracle import c_oracle
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.workloads import noisy_random_clifford
+    prog = compile_circuits([noisy_random_clifford(256, 2000, 3, prob=0.02)])
+    shots, seed = 128, 2026
+    eng, got = _run_gpu(prog, shots, seed, keep=True)
+    want, fin = c_oracle.run(256, 3, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
+                             channel=prog.noise_channel, want_final=True)
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, shots - 1)
+    for key in ("x", "z", "p", "dx", "dz", "dp"):
+        assert np.array_equal(arrs[key], fin[key]), key
+    assert len({got[s].tobytes() for s in range(shots)}) > 8
+
+
+def test_config2_random_clifford_n64_replay_first_shots():
+    """BASELINE config 2: generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1)."""
+    from oracle import c_oracle
+    from sdim_b200 import generate_random_clifford_circuit
+    from sdim_b200.ir import compile_circuits
+    prog = compile_circuits([generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1)])
+    assert prog.n_ops == 2064
+    _, got = _run_gpu(prog, 64, 1)
+    assert np.array_equal(got, c_oracle.run_philox(prog, 64, 0, 1))
+
+
+def test_sharding_invariance_and_shot_offset():
+    """Records depend on the GLOBAL shot id only: one call over [0,200) == calls over [0,77) + [77,200)."""
+    from make_cases import random_program
+    prog = random_program(seed=5, n=12, d=3, depth=300)
+    _, whole = _run_gpu(prog, 200, 9)
+    _, a = _run_gpu(prog, 77, 9, shot_offset=0)
+    _, b = _run_gpu(prog, 123, 9, shot_offset=77)
+    assert np.array_equal(whole, np.concatenate([a, b]))
+    _, far = _run_gpu(prog, 4, 9, shot_offset=2 ** 33)       # 64-bit shot ids reach the counter's high word
+    from oracle import c_oracle
+    assert np.array_equal(far, c_oracle.run_philox(prog, 4, 2 ** 33, 9))
+
+
+def test_host_buffer_entry_matches_device_path():
+    from make_cases import random_program
+    from sdim_b200.engine import simulate_host
+    prog = random_program(seed=8, n=20, d=5, depth=400)
+    _, dev = _run_gpu(prog, 300, 31)
+    host, ms = simulate_host(prog, 300, 0, 31)
+    assert np.array_equal(dev, host) and ms > 0
+    host_g, _ = simulate_host(prog, 300, 0, 31, mode="global")
+    assert np.array_equal(dev, host_g)
+
+
+def test_edge_cases_empty_and_tiny():
+    from sdim_b200.circuit import Circuit
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.engine import TableauEngine
+    # no ops at all: fresh tableau comes back as |0...0>
+    prog = compile_circuits([Circuit(3, 5)])
+    eng = TableauEngine(prog)
+    rec = eng.run(4, keep_tableau=True)
+    assert rec.shape == (4, 0)
+    arrs = eng.export(eng.tableau, 3)
+    assert np.array_equal(arrs["z"], np.eye(3, dtype=np.int64)) and np.array_equal(arrs["dx"], np.eye(3, dtype=np.int64))
+    assert not arrs["x"].any() and not arrs["dz"].any() and not arrs["p"].any() and not arrs["dp"].any()
+    # zero shots
+    c = Circuit(1, 2); c.add_gate("H", 0); c.add_gate("M", 0)
+    prog = compile_circuits([c])
+    assert TableauEngine(prog).run(0).shape == (0, 1)
+    # single qubit H, M: random 0/1
+    rec = TableauEngine(prog).run(4000, 0, 3).cpu().numpy()
+    assert set(np.unique(rec)) == {0, 1} and abs((rec == 1).mean() - 0.5) < 0.05
+    with pytest.raises(ValueError):
+        TableauEngine(prog).run(4, mode="bogus")
+
+
+def test_large_tableau_forced_resident_is_rejected():
+    from sdim_b200.circuit import Circuit
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    c = Circuit(400, 3); c.add_gate("H", 0); c.add_gate("M", 0)
+    with pytest.raises(ValueError, match="does not fit"):
+        TableauEngine(compile_circuits([c])).run(2, mode="resident")
+    rec = TableauEngine(compile_circuits([c])).run(2, mode="global").cpu().numpy()
+    assert rec.shape == (2, 1) and not (rec & 0x80).any()
+
+
+def test_many_shots_multiple_waves_are_race_free():
+    """4096 headline-shaped shots (several shots per CTA, every SM busy) twice, bit-exact vs the C oracle:
+    guards the shared-memory scratch reuse inside the measurement code against rare races."""
+    from oracle import c_oracle
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.workloads import noisy_random_clifford
+    prog = compile_circuits([noisy_random_clifford(256, 2000, 3)])
+    want = c_oracle.run_philox(prog, 4096, 0, 2026)
+    for _ in range(2):
+        _, got = _run_gpu(prog, 4096, 2026)
+        assert np.array_equal(got, want)
+    from make_cases import random_program
+    prog = random_program(seed=3, n=40, d=3, depth=1200)
+    want = c_oracle.run_philox(prog, 20000, 0, 1)
+    _, got = _run_gpu(prog, 20000, 1, "resident")
+    assert np.array_equal(got, want)

@@ -1,0 +1,119 @@
+"""CPU: both oracles (numpy restatement and C restatement) against the reference's golden vectors.
+
+The golden files were produced by the unmodified reference (oracle/make_golden.py); these tests are what
+pins the oracle.  When /root/reference is mounted the oracle is additionally cross-checked live.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, ref_harness
+from oracle.tableau_oracle import run_shot, run_shots
+
+KEYS = ("x", "z", "p", "dx", "dz", "dp")
+
+
+def _want(case):
+    return np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+
+
+def test_golden_file_is_substantial(golden_random):
+    assert len(golden_random) >= 100
+    dims = {c["d"] for c in golden_random}
+    assert {2, 3, 5, 7, 11, 13} <= dims
+    n_rand = sum(1 for c in golden_random for r in c["records"] if not r[1])
+    n_det = sum(1 for c in golden_random for r in c["records"] if r[1])
+    assert n_rand > 500 and n_det > 500
+    kinds = {op[0] for c in golden_random for op in c["ops"]}
+    assert kinds == set(range(18)), "every opcode (I..N1) must appear in the goldens"
+
+
+def test_numpy_oracle_matches_reference_goldens(golden_random):
+    for case in golden_random:
+        draws = [r[2] for r in case["records"]]
+        noise = np.array(case["noise_ab"], dtype=np.int64).reshape(-1, 2)
+        recs, t = run_shot(case["n"], case["d"], case["ops"], lambda k: draws[k], noise)
+        assert recs == [(q, bool(det), m) for q, det, m in case["records"]], case["seed"]
+        for key, arr in zip(KEYS, t.arrays()):
+            assert np.array_equal(arr, np.array(case["final"][key])), (case["seed"], key)
+
+
+@pytest.mark.skipif(not c_oracle.available(), reason="oracle/liboracle.so not built (run `make -C oracle`)")
+def test_c_oracle_matches_reference_goldens(golden_random):
+    for case in golden_random:
+        want = _want(case)
+        noise = np.array(case["noise_ab"], dtype=np.uint8).reshape(1, -1, 2)
+        rec, fin = c_oracle.run(case["n"], case["d"], case["ops"], 1, replay_meas=(want & 0x7F)[None, :],
+                                replay_noise=noise, want_final=True)
+        assert np.array_equal(rec[0], want), case["seed"]
+        for key in KEYS:
+            assert np.array_equal(fin[key], np.array(case["final"][key])), (case["seed"], key)
+
+
+def test_shipped_circuit_goldens(golden_shipped):
+    """circuits/css_steane_final.chp -> 1,1,0,1,1,0 all deterministic; circuits/epr.chp -> qudit 1 random."""
+    st = golden_shipped["circuits/css_steane_final.chp"]
+    assert st["num_qudits"] == 13 and st["dimension"] == 2
+    assert [r[2] for r in st["flat_results"]] == [1, 1, 0, 1, 1, 0]
+    assert all(r[1] == 1 for r in st["flat_results"])
+    for name, g in golden_shipped.items():
+        ops, k = [], 0
+        for op, a, b in g["ops"]:
+            slot = -1
+            if op in (14, 15, 16):
+                slot, k = k, k + 1
+            ops.append([op, a, b, slot])
+        draws = {}
+        # flat results are ordered by (qudit, round); every qudit is measured at most once in these files
+        for q, det, m in g["flat_results"]:
+            draws[q] = m
+        meas_q = [o[1] for o in ops if o[0] in (14, 15, 16)]
+        recs, t = run_shot(g["num_qudits"], g["dimension"], ops, lambda kk: draws[meas_q[kk]])
+        got = sorted((q, int(det), m) for q, det, m in recs)
+        assert got == sorted(tuple(r) for r in g["flat_results"]), name
+        for key, arr in zip(KEYS, t.arrays()):
+            assert np.array_equal(arr, np.array(g["final"][key])), (name, key)
+
+
+@pytest.mark.skipif(not c_oracle.available(), reason="liboracle.so not built")
+@pytest.mark.parametrize("d,n", [(2, 20), (3, 33), (5, 17), (7, 12), (13, 9)])
+def test_numpy_and_c_oracle_agree_free_running(d, n):
+    """Independent implementations, Philox draws: records of several shots must coincide."""
+    from make_cases import random_program
+    prog = random_program(seed=100 + d, n=n, d=d, depth=30 * n)
+    from sdim_b200.rng import measurement_draws, noise_draws
+    shots = 4
+    ids = np.arange(shots)
+    md = measurement_draws(77, d, ids, prog.n_meas)
+    nd = noise_draws(77, d, ids, prog.noise_thresh24, prog.noise_channel)
+    a, _ = run_shots(n, d, prog.ops, shots, md, nd)
+    b = c_oracle.run_philox(prog, shots, 0, 77)
+    assert np.array_equal(a, b)
+    assert ((a & 0x80) == 0).any() and ((a & 0x80) != 0).any()
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not mounted")
+def test_oracle_against_live_reference():
+    """Fresh random circuits through the real reference, beyond the committed goldens."""
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle.make_golden import random_ops, final_measure_all
+    rng = random.Random(424242)
+    checked = 0
+    for d in (2, 3, 5, 7):
+        for n in (2, 4, 6):
+            ops, k, j = random_ops(rng, n, 25 * n, d)
+            k = final_measure_all(ops, n, k)
+            noise = np.array([[rng.randrange(d), rng.randrange(d)] for _ in range(j)], dtype=np.int64).reshape(-1, 2)
+            recs, arrs = ref_harness.ref_run(n, d, ops, noise, draw_seed=d * 100 + n)
+            recs2, arrs2 = ref_harness.ref_run_eager_modulo(n, d, ops, noise, draw_seed=d * 100 + n)
+            if recs != recs2 or any(not np.array_equal(arrs[key], arrs2[key]) for key in arrs):
+                continue    # reference int64 overflow
+            draws = [r[2] for r in recs]
+            got, t = run_shot(n, d, ops, lambda kk: draws[kk], noise)
+            assert got == recs
+            for key, arr in zip(KEYS, t.arrays()):
+                assert np.array_equal(arr, arrs[key])
+            checked += 1
+    assert checked >= 10
