@@ -44,9 +44,14 @@ def build_workload():
     return circ, compile_circuits([circ])
 
 
-def algorithmic_bytes_per_shot(prog, det_flags) -> float:
+def algorithmic_bytes_per_shot(prog, det_flags, meas_nnz=None) -> float:
     """SURVEY 8d per-op byte table (un-fused streaming model), N = 2n lanes, 1 byte per entry/phase for odd d,
-    1 bit / 2 bits for d = 2.  det_flags[k] says whether measurement k was deterministic (shot-invariant)."""
+    1 bit / 2 bits for d = 2.  det_flags[k]: measurement k was deterministic (shot-invariant).
+
+    meas_nnz[k] (from the oracle) = generators with a non-zero factor in measurement k.  With it, a measurement
+    counts only the columns the reference itself touches (it skips zero factors, tableau_prime.py:308,315,351):
+    random: row q (N) + pivot column (2n) + nnz * 4n (X,Z columns read+write) + nnz * 2 phases + column writes 4n;
+    deterministic: row q destab half (n) + nnz * (2n + 1).  Without it the dense 8d figure is used."""
     n, d = prog.num_qudits, prog.dimension
     we, wp = (1.0, 1.0) if d != 2 else (1.0 / 8, 2.0 / 8)
     N = 2 * n
@@ -57,8 +62,6 @@ def algorithmic_bytes_per_shot(prog, det_flags) -> float:
              9: 6 * N * we, 10: 6 * N * we,
              11: 6 * N * we + 2 * N * wp, 12: 6 * N * we + 2 * N * wp,
              13: 8 * N * we}
-    m_random = 4 * N * n * we + 2 * N * wp + 1
-    m_det = 2 * n * n * we + n * we + n * wp + 1
     total = 0.0
     for op, _a, _b, slot in prog.ops:
         op = int(op)
@@ -67,7 +70,13 @@ def algorithmic_bytes_per_shot(prog, det_flags) -> float:
         elif op in (14, 15, 16):
             if op == 15:
                 total += table[6]
-            total += m_det if det_flags[int(slot)] else m_random
+            k = int(slot)
+            if meas_nnz is None:
+                total += (2 * n * n * we + n * we + n * wp + 1) if det_flags[k] else (4 * N * n * we + 2 * N * wp + 1)
+            elif det_flags[k]:
+                total += n * we + meas_nnz[k] * (2 * n * we + wp) + 1
+            else:
+                total += N * we + 2 * n * we + meas_nnz[k] * (4 * n * we + 2 * wp) + 4 * n * we + 1
             if op == 16:
                 total += pauli * (d - 1) / d          # X^k correction, k != 0 with prob (d-1)/d on random outcomes
         elif op == 17:
@@ -148,13 +157,24 @@ def run_cpu_oracle(prog, shots: int, seed: int):
     return time.perf_counter() - t0, 1, "port", rec
 
 
+def cpu_sample_size(prog, seed: int, target_s: float, requested: int) -> int:
+    """Shots whose CPU simulation takes about `target_s` seconds on this box (calibrated on a short run)."""
+    if requested > 0:
+        return requested
+    probe = 64
+    dt, _, _, _ = run_cpu_oracle(prog, probe, seed)
+    dt2, _, _, _ = run_cpu_oracle(prog, probe, seed)
+    per_shot = max(min(dt, dt2), 1e-6) / probe
+    return int(min(max(probe, target_s / per_shot), 1 << 16))
+
+
 def bench_reference(args):
     """--impl reference: the CPU restatement of the reference algorithm on the host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     _, prog = build_workload()
     gates = prog.n_user_gates
-    sample = args.cpu_shots
+    sample = cpu_sample_size(prog, WORKLOAD["philox_seed"], 4.0, args.cpu_shots)    # ~4 s of CPU work per step
     for _ in range(args.warmup):
         run_cpu_oracle(prog, max(1, sample // 8), WORKLOAD["philox_seed"])
     times = []
@@ -204,7 +224,8 @@ def bench_ours(args):
     seed = WORKLOAD["philox_seed"]
     engine = TableauEngine(prog, dev)
     L = engine.layout
-    tab = None if (engine.fits_resident() and args.mode != "global") else engine.alloc_tableau(shots)
+    kernel_name, need_tab = engine.plan(args.mode)
+    tab = engine.alloc_tableau(shots) if need_tab else None
     records = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device=dev)
     lo = rank * shots                       # global shot ids of this rank
     stream = torch.cuda.current_stream(dev)
@@ -217,6 +238,11 @@ def bench_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -224,18 +250,16 @@ def bench_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
         barrier()
-        t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
-        t_all0.record(stream)
         for e0, e1 in ev:
+            flush_l2()                      # untimed: evict the previous step's lines from L2
             e0.record(stream)
             step()
             e1.record(stream)
-        t_all1.record(stream)
         barrier()
         time.sleep(0.25)
     launches = N.lib().sdimb_launch_count() - launches0
-    total_ms = t_all0.elapsed_time(t_all1)
     kernel_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    total_ms = float(sum(kernel_ms))        # exactly K timed steps, device time on the launch stream
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,7 +294,10 @@ def bench_ours(args):
 
     # ---- roofline of the dominant kernel (the interpreter launch = one step) -------------------------
     det_flags = (records[0].cpu().numpy() & 0x80) != 0
-    alg_bytes = algorithmic_bytes_per_shot(prog, det_flags) * shots
+    from oracle import c_oracle
+    meas_nnz = c_oracle.measurement_factor_counts(prog, seed) if c_oracle.available() else None
+    alg_bytes = algorithmic_bytes_per_shot(prog, det_flags, meas_nnz) * shots
+    alg_bytes_dense = algorithmic_bytes_per_shot(prog, det_flags, None) * shots
     launch_s = float(np.mean(kernel_ms)) * 1e-3
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -290,10 +317,12 @@ def bench_ours(args):
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        dt, cores, kind, cpu_rec = run_cpu_oracle(prog, args.cpu_shots, seed)
-        cpu_ok = bool(np.array_equal(cpu_rec, rec_host[: args.cpu_shots]))
-        cpu = {"value": args.cpu_shots * gates / dt, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"{args.cpu_shots} shots of the same circuit/seed ({dt:.1f} s)",
+        cpu_shots = min(cpu_sample_size(prog, seed, 15.0, args.cpu_shots), shots)     # ~15 s of CPU work
+        dt, cores, kind, cpu_rec = run_cpu_oracle(prog, cpu_shots, seed)
+        cpu_ok = bool(np.array_equal(cpu_rec, rec_host[:cpu_shots]))
+        cpu = {"value": cpu_shots * gates / dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"first {cpu_shots} shots of the same circuit/seed, C restatement of the reference "
+                         f"algorithm with OpenMP over shots ({dt:.1f} s)",
                "records_match_gpu": cpu_ok}
 
     line = {
@@ -302,15 +331,19 @@ def bench_ours(args):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload_name(), "shots_per_gpu_per_step": shots, "gates_per_shot": gates,
                    "ops_in_stream": prog.n_ops, "n_meas": prog.n_meas, "n_noise": prog.n_noise,
-                   "mode": args.mode or ("resident" if tab is None else "global"),
-                   "l2": f"tableau store {shots * L.shot_bytes / 2**20:.0f} MiB per step >> 126 MB L2 (no flush needed)",
+                   "mode": args.mode or "auto", "kernel": kernel_name,
+                   "l2": "L2 flushed (256 MiB fill) between timed steps, outside the timed region",
+                   "tableau_store_mib_per_step": (shots * L.shot_bytes / 2**20) if need_tab else 0.0,
                    "parallelism": f"shots sharded over {world} GPU(s), no data-path collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "records_match_device_path": same},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "interp_kernel", "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_s * 1e3},
+                     "traffic": traffic, "kernel": "interp_planes_kernel" if kernel_name.startswith("planes") else "interp_kernel", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_s * 1e3,
+                     "accounting": "SURVEY 8d per-op bytes; measurements count only generators with non-zero factor "
+                                   "(the reference's own skip rule), see DESIGN.md section 4",
+                     "achieved_dense": alg_bytes_dense / launch_s / 1e9},
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
     }
@@ -326,8 +359,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shots", type=int, default=8192, help="shots per GPU per step")
-    ap.add_argument("--cpu-shots", type=int, default=32, help="shots in the CPU baseline sample")
-    ap.add_argument("--mode", default=None, choices=[None, "global", "resident"])
+    ap.add_argument("--cpu-shots", type=int, default=0, help="shots in the CPU baseline sample (0 = calibrate)")
+    ap.add_argument("--mode", default=None, choices=[None, "auto", "global", "resident", "lanes", "planes"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

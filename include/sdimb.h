@@ -66,7 +66,9 @@ enum {
 #define SDIMB_FRESH 0x1u           /* start every shot from |0...0> (ignore/skip the contents of `tableau`) */
 #define SDIMB_WRITEBACK 0x2u       /* leave the final tableau of every shot in `tableau` */
 #define SDIMB_FORCE_GLOBAL 0x4u    /* never stage the tableau in shared memory */
-#define SDIMB_FORCE_RESIDENT 0x8u  /* require the shared-memory resident interpreter (else SDIMB_ETOOBIG) */
+#define SDIMB_FORCE_RESIDENT 0x8u  /* require the shared-memory resident uint8-lane interpreter (else SDIMB_ETOOBIG) */
+#define SDIMB_FORCE_LANES 0x10u    /* never use the bit-plane interpreter (d = 2, 3), keep uint8 lanes */
+#define SDIMB_FORCE_PLANES 0x20u   /* require the bit-plane resident interpreter (d = 2, 3; else SDIMB_ETOOBIG) */
 
 typedef struct SdimbLayout {
   int32_t n, d, np, lanes;   /* lanes = W = 2*np */
@@ -129,6 +131,11 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,
                         const uint8_t* replay_meas, const uint8_t* replay_noise,
                         const uint32_t* noise_thresh24, const uint8_t* noise_channel, int64_t n_noise,
                         uint64_t seed, uint32_t flags, float* elapsed_ms);
+
+/* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store,
+ * 1 uint8 lanes resident in shared memory, 2 bit-plane resident (d = 2, 3); *needs_tableau = whether
+ * SdimbRunArgs.tableau must be a valid store for these flags. */
+int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t sdimb_launch_count(void);

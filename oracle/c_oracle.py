@@ -20,7 +20,7 @@ def _load():
         L = C.CDLL(_PATH)
         L.oracle_run.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p,
-                                 C.c_int]
+                                 C.c_void_p, C.c_int]
         L.oracle_max_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -35,7 +35,7 @@ def _p(a):
 
 
 def run(n, d, ops, shots, shot_offset=0, seed=0, replay_meas=None, replay_noise=None, thresh24=None, channel=None,
-        want_final=False, nthreads=0):
+        want_final=False, nthreads=0, meas_nnz=None):
     """Returns (records uint8[shots, n_meas], final dict or None).  Replay arrays as in the CUDA path."""
     ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 4)
     n_meas = int(np.isin(ops[:, 0], (14, 15, 16)).sum())
@@ -49,7 +49,7 @@ def run(n, d, ops, shots, shot_offset=0, seed=0, replay_meas=None, replay_noise=
         raise ValueError("noise events need replay_noise or (thresh24, channel)")
     final = np.zeros(4 * n * n + 2 * n, dtype=np.int64) if want_final else None
     rc = _load().oracle_run(n, d, shots, shot_offset, _p(ops), ops.shape[0], _p(rec), n_meas, _p(rm), _p(rn),
-                            _p(th), _p(ch), n_noise, seed & 0xFFFFFFFFFFFFFFFF, _p(final), nthreads)
+                            _p(th), _p(ch), n_noise, seed & 0xFFFFFFFFFFFFFFFF, _p(final), _p(meas_nnz), nthreads)
     if rc != 0:
         raise RuntimeError(f"oracle_run failed ({rc})")
     out = None
@@ -66,3 +66,12 @@ def run_philox(prog, shots, shot_offset, seed, nthreads=0):
     rec, _ = run(prog.num_qudits, prog.dimension, prog.ops, shots, shot_offset, seed,
                  thresh24=prog.noise_thresh24, channel=prog.noise_channel, nthreads=nthreads)
     return rec
+
+
+def measurement_factor_counts(prog, seed=0):
+    """int32[n_meas]: generators with a non-zero factor in each measurement of one shot (shot-invariant: the
+    x/z blocks do not depend on outcomes or Pauli noise)."""
+    nnz = np.zeros(max(prog.n_meas, 1), dtype=np.int32)
+    run(prog.num_qudits, prog.dimension, prog.ops, 1, 0, seed, thresh24=prog.noise_thresh24,
+        channel=prog.noise_channel, meas_nnz=nnz)
+    return nnz[: prog.n_meas]

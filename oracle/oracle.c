@@ -131,7 +131,7 @@ static int inverse_mod(int v, int d) {
 }
 
 /* tableau_prime.py:262-363.  Returns value; *det = 1 for a deterministic outcome. */
-static int measure(Tab* t, int q, int draw, int* det) {
+static int measure(Tab* t, int q, int draw, int* det, int* nnz) {
   const int n = t->n, d = t->d, po = t->po, o = t->order;
   int piv = -1;
   for (int i = 0; i < n; ++i)
@@ -140,7 +140,7 @@ static int measure(Tab* t, int q, int draw, int* det) {
     /* _det_measurement (:336-363), restructured row-wise: running ancilla_z per qudit row */
     int64_t ap = 0, cross = 0, sdg = 0;
     const int32_t* f = t->dx + (size_t)q * n;
-    for (int i = 0; i < n; ++i) ap += (int64_t)f[i] * t->p[i];
+    for (int i = 0; i < n; ++i) { ap += (int64_t)f[i] * t->p[i]; *nnz += (f[i] != 0); }
     for (int r = 0; r < n; ++r) {
       const int32_t* xr = t->x + (size_t)r * n;
       const int32_t* zr = t->z + (size_t)r * n;
@@ -189,6 +189,7 @@ static int measure(Tab* t, int q, int draw, int* det) {
       t->dot[i] = 0;
     }
     if (h == 1) t->f[piv] = 0;
+    for (int i = 0; i < n; ++i) *nnz += (t->f[i] != 0);
     for (int r = 0; r < n; ++r) {
       const int s = t->xs[r], u = t->zs[r];
       if (!s && !u) continue;
@@ -230,7 +231,7 @@ static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
 
 static void run_one(Tab* t, int64_t local, int64_t gshot, const int32_t* ops, int64_t n_ops, uint8_t* records,
                     int64_t n_meas, const uint8_t* replay_meas, const uint8_t* replay_noise, const uint32_t* thresh,
-                    const uint8_t* chan, int64_t n_noise, uint64_t seed) {
+                    const uint8_t* chan, int64_t n_noise, uint64_t seed, int32_t* meas_nnz) {
   const int d = t->d;
   tab_reset(t);
   for (int64_t i = 0; i < n_ops; ++i) { /* program.py:311-351 */
@@ -259,8 +260,9 @@ static void run_one(Tab* t, int64_t local, int64_t gshot, const int32_t* ops, in
           philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
           draw = (int)(((uint64_t)c[0] * (uint64_t)d) >> 32);
         }
-        int det = 0;
-        const int m = measure(t, a, draw, &det);
+        int det = 0, nnz = 0;
+        const int m = measure(t, a, draw, &det, &nnz);
+        if (meas_nnz) meas_nnz[slot] = nnz;
         records[local * n_meas + slot] = (uint8_t)((m & 0x7F) | (det ? 0x80 : 0));
         if (op == 16 && m) pauli(t, a, (d - m) % d, 0); /* program.py:335-339 */
         break;
@@ -292,10 +294,12 @@ int oracle_max_threads(void) {
 #endif
 }
 
-/* final (nullable): the LAST shot's six arrays as int64, concatenated x,z,dx,dz (n*n each) then p,dp (n each). */
+/* final (nullable): the LAST shot's six arrays as int64, concatenated x,z,dx,dz (n*n each) then p,dp (n each).
+ * meas_nnz (nullable, [n_meas]): for the LAST shot, the number of generators with a non-zero factor in each
+ * measurement (the ones the reference does not skip, tableau_prime.py:308,315,351) - used for byte accounting. */
 int oracle_run(int n, int d, int64_t shots, int64_t shot_offset, const int32_t* ops, int64_t n_ops, uint8_t* records,
                int64_t n_meas, const uint8_t* replay_meas, const uint8_t* replay_noise, const uint32_t* thresh,
-               const uint8_t* chan, int64_t n_noise, uint64_t seed, int64_t* final, int threads) {
+               const uint8_t* chan, int64_t n_noise, uint64_t seed, int64_t* final, int32_t* meas_nnz, int threads) {
   if (n < 1 || d < 2 || shots < 0) return -1;
   int failed = 0;
 #ifdef _OPENMP
@@ -313,7 +317,7 @@ int oracle_run(int n, int d, int64_t shots, int64_t shot_offset, const int32_t* 
 #pragma omp for schedule(dynamic, 1)
       for (int64_t s = 0; s < shots; ++s) {
         run_one(&t, s, shot_offset + s, ops, n_ops, records, n_meas, replay_meas, replay_noise, thresh, chan, n_noise,
-                seed);
+                seed, (s == shots - 1) ? meas_nnz : 0);
         if (final && s == shots - 1) {
           const size_t nn = (size_t)n * n;
           const int32_t* src[4] = {t.x, t.z, t.dx, t.dz};

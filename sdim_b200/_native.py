@@ -7,11 +7,12 @@ import os
 from .build import LIB_PATH
 
 OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
-FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT = 0x1, 0x2, 0x4, 0x8
+FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT, FORCE_LANES, FORCE_PLANES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
-                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count")
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan")
 
 
 class SdimbLayout(C.Structure):
@@ -59,6 +60,7 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_float)]
     L.sdimb_launch_count.restype = C.c_int64
+    L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -77,3 +79,10 @@ def layout(n: int, d: int) -> SdimbLayout:
     out = SdimbLayout()
     check(lib().sdimb_layout(n, d, C.byref(out)))
     return out
+
+
+def plan(n: int, d: int, flags: int):
+    """(kernel id, needs_tableau) that sdimb_run would use for these flags."""
+    k, need = C.c_int(0), C.c_int(0)
+    check(lib().sdimb_plan(n, d, flags, C.byref(k), C.byref(need)))
+    return k.value, bool(need.value)

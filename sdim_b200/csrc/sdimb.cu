@@ -23,7 +23,6 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 
 constexpr int kMaxThreads = 256;
-constexpr int kNoiseChunk = 1024;       // N1 events decoded per refill of the shared-memory noise cache
 constexpr uint32_t kNoPivot = 0xFFFFFFFFu;
 constexpr int kSmemLimit = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
@@ -92,13 +91,12 @@ struct Scratch {
   uint32_t* fw;        // [W/4]  packed factors f = -X[q,i] mod d, 4 lanes/word (random branch)
   uint32_t* red;       // [32]   cross-warp reduction scratch
   uint32_t* cnt;       // [4]    list lengths
-  uint16_t* noise;     // [kNoiseChunk] decoded (a | b << 8) of N1 events [noise_lo, noise_lo + kNoiseChunk)
+  int4* ops;           // [32]   staged op batch (N1 rows carry the decoded event in .z)
   uint16_t* ar;        // [np]   active rows: qudits on which the pivot acts / active generators (det branch)
   uint16_t* aw;        // [W/4]  active words: lane quads holding a non-zero factor
   uint8_t* xs;         // [np]   pivot column X (random branch) / factors of the active generators (det branch)
   uint8_t* zs;         // [np]   pivot column Z
   uint8_t* inv;        // [128]  multiplicative inverses mod d
-  int64_t noise_lo;    // first event held in `noise` (-1 = empty); uniform across the CTA, kept in registers
 };
 
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* red) {
@@ -258,46 +256,43 @@ __device__ __forceinline__ void gate_cz(uint8_t* T, const KParams& p, int a, int
 __device__ __forceinline__ void gate_swap(uint8_t* T, const KParams& p, int a, int b) {
   uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
   uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
-  for (int w = threadIdx.x; w < p.W / 2; w += blockDim.x) {   // X and Z halves of the row pair
-    const uint32_t t = rowa[w];
-    rowa[w] = rowb[w];
-    rowb[w] = t;
+  const int wz = p.W / 4;
+  // each thread swaps the X and Z words of the lanes it owns (lane ownership must hold across gates: there is
+  // no barrier between consecutive gates)
+  for (int w = threadIdx.x; w < wz; w += blockDim.x) {
+    const uint32_t tx = rowa[w], tz = rowa[wz + w];
+    rowa[w] = rowb[w]; rowa[wz + w] = rowb[wz + w];
+    rowb[w] = tx; rowb[wz + w] = tz;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Noise: decode N1 events [lo, lo+kNoiseChunk) of this shot into shared memory, either from the replay
-// array or from Philox with the distribution of sdim/program.py:486-507.
+// Noise: N1 event j of this shot -> (a | b << 8), 0 if it does not fire.  Replayed, or Philox with the
+// distribution of sdim/program.py:486-507.  Evaluated by the thread that fetched the op, so events that do
+// not fire never reach the dispatch loop.
 // ---------------------------------------------------------------------------------------------
-__device__ void fill_noise(const KParams& p, Scratch& S, int64_t lo, int64_t shot_local) {
-  __syncthreads();
-  const uint64_t gshot = (uint64_t)(p.shot_offset + shot_local);
+__device__ __forceinline__ uint32_t noise_event(const KParams& p, int64_t j, int64_t shot_local) {
   const uint32_t d = p.A.d;
-  for (int t = threadIdx.x; t < kNoiseChunk; t += blockDim.x) {
-    const int64_t j = lo + t;
-    if (j >= p.n_noise) break;
-    uint32_t a = 0, b = 0;
-    if (p.replay_noise) {
-      const uint8_t* src = p.replay_noise + (shot_local * p.n_noise + j) * 2;
-      a = src[0]; b = src[1];
-    } else {
-      const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)j, 1u, (uint32_t)p.seed,
-                                 (uint32_t)(p.seed >> 32));
-      if ((r.x >> 8) >= p.thresh[j]) {
-        const uint32_t ch = p.chan[j];
-        if (ch == 0) {                                      // 'd': r ~ U{1..d^2-1}, a = r % d, b = r // d
-          const uint32_t v = 1u + __umulhi(r.y, d * d - 1u);
-          a = v % d; b = v / d;
-        } else {                                            // 'f': X^e, 'p': Z^e, e ~ U{1..d-1}
-          const uint32_t e = 1u + __umulhi(r.y, d - 1u);
-          if (ch == 1) a = e; else b = e;
-        }
+  uint32_t a = 0, b = 0;
+  if (p.replay_noise) {
+    const uint8_t* src = p.replay_noise + (shot_local * p.n_noise + j) * 2;
+    a = src[0]; b = src[1];
+  } else {
+    const uint64_t gshot = (uint64_t)(p.shot_offset + shot_local);
+    const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)j, 1u, (uint32_t)p.seed,
+                               (uint32_t)(p.seed >> 32));
+    if ((r.x >> 8) >= __ldg(p.thresh + j)) {
+      const uint32_t ch = __ldg(p.chan + j);
+      if (ch == 0) {                                        // 'd': r ~ U{1..d^2-1}, a = r % d, b = r // d
+        const uint32_t v = 1u + __umulhi(r.y, d * d - 1u);
+        a = v % d; b = v / d;
+      } else {                                              // 'f': X^e, 'p': Z^e, e ~ U{1..d-1}
+        const uint32_t e = 1u + __umulhi(r.y, d - 1u);
+        if (ch == 1) a = e; else b = e;
       }
     }
-    S.noise[t] = (uint16_t)(a | (b << 8));
   }
-  __syncthreads();
-  S.noise_lo = lo;
+  return a | (b << 8);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,7 +312,7 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
   const int wz = W / 4;
   uint8_t* rowq = T + (int64_t)q * p.row_bytes;
   uint8_t* P8 = T + p.phase_off;
-  if (tid < 4) S.cnt[tid] = 0;
+  if (tid < 2) S.cnt[tid] = 0;   // cnt[3] holds the live-op mask of the current batch
   __syncthreads();   // gate writes of other threads' lanes become visible; counters reset
 
   // -- pivot: FIRST stabilizer with an X component on q (tableau_prime.py:273-283) ------------------
@@ -532,6 +527,8 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
   return outcome;
 }
 
+#include "planes.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // The interpreter: one CTA per shot, grid-stride over shots.
 // ---------------------------------------------------------------------------------------------
@@ -543,8 +540,8 @@ __global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_consta
   S.fw = S.dot + p.W;
   S.red = S.fw + p.W / 4;
   S.cnt = S.red + 32;
-  S.noise = reinterpret_cast<uint16_t*>(S.cnt + 4);
-  S.ar = S.noise + kNoiseChunk;
+  S.ops = reinterpret_cast<int4*>(S.cnt + 4);
+  S.ar = reinterpret_cast<uint16_t*>(S.ops + 32);
   S.aw = S.ar + p.np;
   S.xs = reinterpret_cast<uint8_t*>(S.aw + p.W / 4);
   S.zs = S.xs + p.np;
@@ -570,42 +567,55 @@ __global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_consta
       for (int64_t i = threadIdx.x; i < p.shot_bytes / 16; i += blockDim.x) dst[i] = src[i];
       __syncthreads();
     }
-    S.noise_lo = -1;
 
-    for (int64_t i = 0; i < p.n_ops; ++i) {
-      const int4 op = __ldg(p.ops + i);
-      switch (op.x) {
-        case SDIMB_OP_I: break;
-        case SDIMB_OP_X: gate_pauli(T, p, op.y, 1u, 0u); break;
-        case SDIMB_OP_X_INV: gate_pauli(T, p, op.y, A.d - 1u, 0u); break;
-        case SDIMB_OP_Z: gate_pauli(T, p, op.y, 0u, 1u); break;
-        case SDIMB_OP_Z_INV: gate_pauli(T, p, op.y, 0u, A.d - 1u); break;
-        case SDIMB_OP_H: gate_h(T, p, op.y, false); break;
-        case SDIMB_OP_H_INV: gate_h(T, p, op.y, true); break;
-        case SDIMB_OP_P: gate_p(T, p, op.y, false); break;
-        case SDIMB_OP_P_INV: gate_p(T, p, op.y, true); break;
-        case SDIMB_OP_CNOT: gate_cnot(T, p, op.y, op.z, false); break;
-        case SDIMB_OP_CNOT_INV: gate_cnot(T, p, op.y, op.z, true); break;
-        case SDIMB_OP_CZ: gate_cz(T, p, op.y, op.z, false); break;
-        case SDIMB_OP_CZ_INV: gate_cz(T, p, op.y, op.z, true); break;
-        case SDIMB_OP_SWAP: gate_swap(T, p, op.y, op.z); break;
-        case SDIMB_OP_M_X:
-          gate_h(T, p, op.y, true);                          // tableau_gates.py:292-296: H^-1 then measure
-          // fallthrough
-        case SDIMB_OP_M:
-        case SDIMB_OP_RESET: {
-          const uint32_t m = measure(T, p, S, op.y, op.w, shot);
-          if (op.x == SDIMB_OP_RESET && m) gate_pauli(T, p, op.y, A.d - m, 0u);   // program.py:335-339
-          break;
+    for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
+      // warp 0 fetches 32 ops (one per lane) and resolves their N1 events; only live ops are dispatched
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
+        if (i0 + threadIdx.x < p.n_ops) mine = __ldg(p.ops + i0 + threadIdx.x);
+        bool live = mine.x != SDIMB_OP_I;
+        if (mine.x == SDIMB_OP_N1) {
+          mine.z = (int)noise_event(p, mine.w, shot);
+          live = mine.z != 0;
         }
-        case SDIMB_OP_N1: {
-          const int64_t j = op.w;
-          if (S.noise_lo < 0 || j < S.noise_lo || j >= S.noise_lo + kNoiseChunk) fill_noise(p, S, j, shot);
-          const uint32_t ab = S.noise[j - S.noise_lo];
-          if (ab) gate_pauli(T, p, op.y, ab & 0xFFu, ab >> 8);
-          break;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, live);
+        S.ops[threadIdx.x] = mine;
+        if (threadIdx.x == 0) S.cnt[3] = m;
+      }
+      __syncthreads();
+      uint32_t todo = S.cnt[3];
+#pragma unroll 1
+      while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int4 op = S.ops[k];
+        switch (op.x) {
+          case SDIMB_OP_X: gate_pauli(T, p, op.y, 1u, 0u); break;
+          case SDIMB_OP_X_INV: gate_pauli(T, p, op.y, A.d - 1u, 0u); break;
+          case SDIMB_OP_Z: gate_pauli(T, p, op.y, 0u, 1u); break;
+          case SDIMB_OP_Z_INV: gate_pauli(T, p, op.y, 0u, A.d - 1u); break;
+          case SDIMB_OP_H: gate_h(T, p, op.y, false); break;
+          case SDIMB_OP_H_INV: gate_h(T, p, op.y, true); break;
+          case SDIMB_OP_P: gate_p(T, p, op.y, false); break;
+          case SDIMB_OP_P_INV: gate_p(T, p, op.y, true); break;
+          case SDIMB_OP_CNOT: gate_cnot(T, p, op.y, op.z, false); break;
+          case SDIMB_OP_CNOT_INV: gate_cnot(T, p, op.y, op.z, true); break;
+          case SDIMB_OP_CZ: gate_cz(T, p, op.y, op.z, false); break;
+          case SDIMB_OP_CZ_INV: gate_cz(T, p, op.y, op.z, true); break;
+          case SDIMB_OP_SWAP: gate_swap(T, p, op.y, op.z); break;
+          case SDIMB_OP_M_X:
+            gate_h(T, p, op.y, true);                          // tableau_gates.py:292-296: H^-1 then measure
+            // fallthrough
+          case SDIMB_OP_M:
+          case SDIMB_OP_RESET: {
+            const uint32_t m = measure(T, p, S, op.y, op.w, shot);
+            if (op.x == SDIMB_OP_RESET && m) gate_pauli(T, p, op.y, A.d - m, 0u);   // program.py:335-339
+            break;
+          }
+          case SDIMB_OP_N1: gate_pauli(T, p, op.y, (uint32_t)op.z & 0xFFu, (uint32_t)op.z >> 8); break;
+          default: break;   // rejected on the host before launch
         }
-        default: break;   // rejected on the host before launch
       }
     }
     __syncthreads();
@@ -671,7 +681,23 @@ int block_threads(int W) {
 
 size_t scratch_bytes(int np) {
   const size_t W = 2 * (size_t)np;
-  return 4 * W + W + 32 * 4 + 4 * 4 + kNoiseChunk * 2 + 2 * (size_t)np + 2 * (W / 4) + 2 * (size_t)np + 128;
+  return 4 * W + W + 32 * 4 + 4 * 4 + 32 * 16 + 2 * (size_t)np + 2 * (W / 4) + 2 * (size_t)np + 128;
+}
+
+// Which interpreter a (n, d, flags) call runs: 0 = uint8 lanes in global memory, 1 = uint8 lanes resident in
+// shared memory, 2 = bit-plane resident (d = 2, 3).  Negative = error code.
+int plan_kernel(int n, int d, uint32_t flags, int np) {
+  if ((flags & SDIMB_FORCE_GLOBAL) && (flags & (SDIMB_FORCE_RESIDENT | SDIMB_FORCE_PLANES))) return SDIMB_EINVAL;
+  if ((flags & SDIMB_FORCE_LANES) && (flags & SDIMB_FORCE_PLANES)) return SDIMB_EINVAL;
+  SdimbLayout L;
+  const int rc = sdimb_layout(n, d, &L);
+  if (rc) return rc;
+  const bool fits = (size_t)L.shot_bytes + scratch_bytes(np) <= (size_t)kSmemLimit;
+  const bool planes_fit = (d == 2 || d == 3) && planes::planes_smem_bytes(n, d) <= (size_t)kSmemLimit;
+  if ((flags & SDIMB_FORCE_PLANES) && !planes_fit) return SDIMB_ETOOBIG;
+  if ((flags & SDIMB_FORCE_RESIDENT) && !fits) return SDIMB_ETOOBIG;
+  if (planes_fit && !(flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES))) return 2;
+  return (fits && !(flags & SDIMB_FORCE_GLOBAL)) ? 1 : 0;
 }
 
 }  // namespace
@@ -728,16 +754,16 @@ int sdimb_run(const SdimbRunArgs* a) {
   const int rc = sdimb_layout(a->n, a->d, &L);
   if (rc) return rc;
   if (a->shots < 0 || a->n_ops < 0 || a->n_meas < 0 || a->n_noise < 0) return SDIMB_EINVAL;
-  if ((a->flags & SDIMB_FORCE_GLOBAL) && (a->flags & SDIMB_FORCE_RESIDENT)) return SDIMB_EINVAL;
+  if (plan_kernel(a->n, a->d, a->flags, L.np) < 0) return plan_kernel(a->n, a->d, a->flags, L.np);
   if (a->shots == 0) return SDIMB_OK;
   if (a->n_ops > 0 && !a->ops) return SDIMB_EINVAL;
   if (a->n_meas > 0 && (!a->records || a->rec_stride < a->n_meas)) return SDIMB_EINVAL;
   if (a->n_noise > 0 && !a->replay_noise && (!a->noise_thresh24 || !a->noise_channel)) return SDIMB_EINVAL;
 
+  const int kernel = plan_kernel(a->n, a->d, a->flags, L.np);
+  if (kernel < 0) return kernel;
   const size_t scratch = scratch_bytes(L.np);
-  const bool fits = (size_t)L.shot_bytes + scratch <= (size_t)kSmemLimit;
-  bool resident = fits && !(a->flags & SDIMB_FORCE_GLOBAL);
-  if ((a->flags & SDIMB_FORCE_RESIDENT) && !fits) return SDIMB_ETOOBIG;
+  const bool use_planes = kernel == 2, resident = kernel >= 1;
   const bool need_tab = !resident || !(a->flags & SDIMB_FRESH) || (a->flags & SDIMB_WRITEBACK);
   if (need_tab && !a->tableau) return SDIMB_EINVAL;
 
@@ -761,15 +787,28 @@ int sdimb_run(const SdimbRunArgs* a) {
   p.row_bytes = L.row_bytes; p.phase_off = L.phase_offset; p.shot_bytes = L.shot_bytes;
   p.A = make_arith(a->d);
   p.flags = a->flags;
-  p.resident = resident ? 1 : 0;
+  p.resident = kernel == 1 ? 1 : 0;
 
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
+  if (use_planes) {
+    const size_t smem = planes::planes_smem_bytes(a->n, a->d);
+    auto kern = (a->d == 2) ? planes::interp_planes_kernel<2> : planes::interp_planes_kernel<3>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return SDIMB_ECUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
+      return SDIMB_ECUDA;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > a->shots) grid = a->shots;
+    kern<<<(unsigned)grid, 32, smem, (cudaStream_t)a->stream>>>(p);
+    g_launches++;
+    return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+  }
   const int threads = block_threads(L.lanes);
   const size_t smem = scratch + (resident ? (size_t)L.shot_bytes : 0);
   if (cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return SDIMB_ECUDA;
-  int dev = 0, sms = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
-  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel, threads, smem) != cudaSuccess || per_sm < 1)
     return SDIMB_ECUDA;
   int64_t grid = (int64_t)sms * per_sm;
@@ -818,9 +857,10 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   void *d_ops = nullptr, *d_rec = nullptr, *d_rm = nullptr, *d_rn = nullptr, *d_th = nullptr, *d_ch = nullptr,
        *d_tab = nullptr;
-  const size_t scratch = scratch_bytes(L.np);
-  const bool fits = (size_t)L.shot_bytes + scratch <= (size_t)kSmemLimit;
-  const bool resident = fits && !(flags & SDIMB_FORCE_GLOBAL);
+  const uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES | SDIMB_FORCE_PLANES);
+  const int kernel = plan_kernel(n, d, mode_flags, L.np);
+  if (kernel < 0) return kernel;
+  const bool resident = kernel >= 1;
   rc = SDIMB_ECUDA;
   do {
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
@@ -841,7 +881,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     SdimbRunArgs a;
     std::memset(&a, 0, sizeof(a));
     a.struct_size = sizeof(a);
-    a.flags = (flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT)) | SDIMB_FRESH;
+    a.flags = mode_flags | SDIMB_FRESH;
     a.n = n; a.d = d; a.shots = shots; a.shot_offset = shot_offset;
     a.tableau = d_tab;
     a.ops = (const int32_t*)d_ops; a.n_ops = n_ops;
@@ -867,5 +907,16 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
 }
 
 int64_t sdimb_launch_count(void) { return g_launches.load(); }
+
+int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau) {
+  SdimbLayout L;
+  const int rc = sdimb_layout(n, d, &L);
+  if (rc) return rc;
+  const int k = plan_kernel(n, d, flags, L.np);
+  if (k < 0) return k;
+  if (kernel) *kernel = k;
+  if (needs_tableau) *needs_tableau = (k == 0 || !(flags & SDIMB_FRESH) || (flags & SDIMB_WRITEBACK)) ? 1 : 0;
+  return SDIMB_OK;
+}
 
 }  // extern "C"

@@ -35,7 +35,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class TableauEngine:
-    MODES = {None: 0, "auto": 0, "global": N.FORCE_GLOBAL, "resident": N.FORCE_RESIDENT}
+    # auto: bit-plane resident for d in {2,3} when it fits, else uint8 lanes resident when they fit, else global
+    MODES = {None: 0, "auto": 0, "global": N.FORCE_GLOBAL, "resident": N.FORCE_RESIDENT, "lanes": N.FORCE_LANES,
+             "planes": N.FORCE_PLANES}
 
     def __init__(self, prog: CompiledProgram, device=None):
         self.prog = prog
@@ -55,8 +57,16 @@ class TableauEngine:
         self.tableau_shots = 0
 
     # ------------------------------------------------------------------------------------------
-    def fits_resident(self) -> bool:
-        return self.layout.shot_bytes + 2 * self.layout.np + 128 + 2048 + 128 <= 227 * 1024
+    def plan(self, mode: Optional[str] = None, fresh: bool = True, keep_tableau: bool = False):
+        """(kernel name, needs_tableau) for a run in `mode`."""
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {sorted(k for k in self.MODES if k)}")
+        flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
+        k, need = N.plan(self.prog.num_qudits, self.prog.dimension, flags)
+        return N.KERNEL_NAMES[k], need
+
+    def fits_resident(self, mode: Optional[str] = None) -> bool:
+        return not self.plan(mode)[1]
 
     def alloc_tableau(self, shots: int) -> torch.Tensor:
         return torch.empty((shots, self.layout.shot_bytes), dtype=torch.uint8, device=self.device)
@@ -78,11 +88,8 @@ class TableauEngine:
         op_range     (lo, hi) slice of the op stream, for host-stepped execution
         """
         prog, L, dev = self.prog, self.layout, self.device
-        if mode not in self.MODES:
-            raise ValueError(f"mode must be one of {sorted(k for k in self.MODES if k)}")
+        _, need_tab = self.plan(mode, fresh, keep_tableau)
         flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
-        resident = self.fits_resident() and mode != "global"
-        need_tab = (not resident) or keep_tableau or not fresh
         with torch.cuda.device(dev):
             if need_tab:
                 if tableau is None:

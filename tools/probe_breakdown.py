@@ -9,7 +9,7 @@ from sdim_b200.workloads import noisy_random_clifford
 
 def timeit(prog, shots, mode=None, reps=3):
     eng = TableauEngine(prog)
-    tab = None if (eng.fits_resident() and mode != "global") else eng.alloc_tableau(shots)
+    tab = eng.alloc_tableau(shots) if eng.plan(mode)[1] else None
     rec = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device="cuda")
     for _ in range(2):
         eng.run(shots, 0, 1, mode=mode, tableau=tab, records=rec)

@@ -15,7 +15,7 @@ c = {"headline": lambda: noisy_random_clifford(n, 2000, d),
      "gates+meas": lambda: generate_random_clifford_circuit(n, 2000, d, measurement_rounds=1, seed=1)}[kind]()
 prog = compile_circuits([c])
 eng = TableauEngine(prog)
-tab = None if (eng.fits_resident() and mode != "global") else eng.alloc_tableau(shots)
+tab = eng.alloc_tableau(shots) if eng.plan(mode)[1] else None
 rec = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device="cuda")
 for _ in range(reps):
     eng.run(shots, 0, 1, mode=mode, tableau=tab, records=rec)
