@@ -8,9 +8,12 @@
 //   d = 3  value v = 2*h + l, planes (l, h):  0 = (0,0), 1 = (1,0), 2 = (0,1);  negation swaps the planes
 //   d = 2  value v = l;  phases are mod 4 = 2*h + l                         
 //
-// Shared-memory image of one shot (uint32 words, Wb = W/32 words per plane, B = bits per exponent):
-//   row q:   X planes [B][Wb], Z planes [B][Wb]            at q * 2*B*Wb
-//   phases:  P_l [Wb], P_h [Wb]                            at n * 2*B*Wb
+// Shared-memory image of one shot.  Lane word j (32 generators) of a qudit row is ONE vector entry holding
+// all planes of X and Z, so a gate is one LDS.128 + one STS.128 per lane (LDS.64 for d = 2):
+//   d = 3: entry = uint4 (x_l, x_h, z_l, z_h)        d = 2: entry = uint2 (x, z)
+//   row q:   entry[0..Wb) at q * (Wb + 1) entries    (+1 entry of padding: column walks — one entry per row,
+//                                                     32 rows per instruction — then hit distinct banks)
+//   phases:  uint2 (p_l, p_h) [Wb]                   after the n rows
 // Lane numbering is that of the uint8 store (include/sdimb.h): stabilizer g -> lane g, destabilizer g -> lane
 // np + g, with np a multiple of 32 here so the two halves never share a word.
 //
@@ -21,6 +24,9 @@ namespace planes {
 
 struct E {   // 32 lanes of one exponent (or phase): l = low plane, h = high plane
   uint32_t l, h;
+};
+struct XZ {  // one lane word of a qudit row
+  E x, z;
 };
 
 // ---- GF(3), bit-sliced --------------------------------------------------------------------------
@@ -41,94 +47,76 @@ __device__ __forceinline__ E add4(E p, E a) {   // lane-wise p + a mod 4
   const uint32_t carry = p.l & a.l;
   return E{p.l ^ a.l, p.h ^ a.h ^ carry};
 }
+__device__ __forceinline__ uint32_t bit2(E v, int b) { return ((v.l >> b) & 1u) | (((v.h >> b) & 1u) << 1); }
+__device__ __forceinline__ E setbit2(E w, int b, uint32_t v) {
+  const uint32_t m = 1u << b;
+  return E{(w.l & ~m) | ((v & 1u) << b), (w.h & ~m) | (((v >> 1) & 1u) << b)};
+}
 
 template <int D>
 struct Geo {
-  static constexpr int B = (D == 2) ? 1 : 2;
-  uint32_t* tab;   // shared-memory image
-  int n, np, Wb, RW;
-  __device__ __forceinline__ uint32_t* row(int q) const { return tab + q * RW; }
-  __device__ __forceinline__ uint32_t* phase() const { return tab + n * RW; }
-  __device__ __forceinline__ E ldx(int q, int j) const {
-    const uint32_t* r = row(q);
-    return E{r[j], D == 3 ? r[Wb + j] : 0u};
+  static constexpr int EW = (D == 2) ? 2 : 4;   // words per entry
+  uint32_t* tab;                                // shared-memory image
+  int n, np, Wb, RS;                            // RS = row stride in words = EW * (Wb + 1)
+  __device__ __forceinline__ uint32_t* entry(int q, int j) const { return tab + q * RS + j * EW; }
+  __device__ __forceinline__ uint2* phase() const { return reinterpret_cast<uint2*>(tab + n * RS); }
+  __device__ __forceinline__ XZ ld(int q, int j) const {
+    if (D == 3) {
+      const uint4 v = *reinterpret_cast<const uint4*>(entry(q, j));
+      return XZ{E{v.x, v.y}, E{v.z, v.w}};
+    }
+    const uint2 v = *reinterpret_cast<const uint2*>(entry(q, j));
+    return XZ{E{v.x, 0u}, E{v.y, 0u}};
   }
-  __device__ __forceinline__ E ldz(int q, int j) const {
-    const uint32_t* r = row(q) + B * Wb;
-    return E{r[j], D == 3 ? r[Wb + j] : 0u};
+  __device__ __forceinline__ void st(int q, int j, XZ v) const {
+    if (D == 3) *reinterpret_cast<uint4*>(entry(q, j)) = make_uint4(v.x.l, v.x.h, v.z.l, v.z.h);
+    else *reinterpret_cast<uint2*>(entry(q, j)) = make_uint2(v.x.l, v.z.l);
   }
-  __device__ __forceinline__ void stx(int q, int j, E v) const {
-    uint32_t* r = row(q);
-    r[j] = v.l;
-    if (D == 3) r[Wb + j] = v.h;
+  __device__ __forceinline__ void stx(int q, int j, E x) const {
+    if (D == 3) *reinterpret_cast<uint2*>(entry(q, j)) = make_uint2(x.l, x.h);
+    else entry(q, j)[0] = x.l;
   }
-  __device__ __forceinline__ void stz(int q, int j, E v) const {
-    uint32_t* r = row(q) + B * Wb;
-    r[j] = v.l;
-    if (D == 3) r[Wb + j] = v.h;
+  __device__ __forceinline__ void stz(int q, int j, E z) const {
+    if (D == 3) *reinterpret_cast<uint2*>(entry(q, j) + 2) = make_uint2(z.l, z.h);
+    else entry(q, j)[1] = z.l;
   }
-  __device__ __forceinline__ E ldp(int j) const { return E{phase()[j], phase()[Wb + j]}; }
-  __device__ __forceinline__ void stp(int j, E v) const { phase()[j] = v.l; phase()[Wb + j] = v.h; }
-  // scalar accessors (column operations)
-  __device__ __forceinline__ uint32_t getx(int q, int lane) const {
-    const E v = ldx(q, lane >> 5);
-    return ((v.l >> (lane & 31)) & 1u) | (((v.h >> (lane & 31)) & 1u) << 1);
-  }
-  __device__ __forceinline__ uint32_t getz(int q, int lane) const {
-    const E v = ldz(q, lane >> 5);
-    return ((v.l >> (lane & 31)) & 1u) | (((v.h >> (lane & 31)) & 1u) << 1);
-  }
-  __device__ __forceinline__ uint32_t getp(int lane) const {
-    const E v = ldp(lane >> 5);
-    return ((v.l >> (lane & 31)) & 1u) | (((v.h >> (lane & 31)) & 1u) << 1);
-  }
+  __device__ __forceinline__ E ldp(int j) const { const uint2 v = phase()[j]; return E{v.x, v.y}; }
+  __device__ __forceinline__ void stp(int j, E v) const { phase()[j] = make_uint2(v.l, v.h); }
+  // scalar accessors
+  __device__ __forceinline__ uint32_t getx(int q, int lane) const { return bit2(ld(q, lane >> 5).x, lane & 31); }
+  __device__ __forceinline__ uint32_t getz(int q, int lane) const { return bit2(ld(q, lane >> 5).z, lane & 31); }
+  __device__ __forceinline__ uint32_t getp(int lane) const { return bit2(ldp(lane >> 5), lane & 31); }
   __device__ __forceinline__ void setx(int q, int lane, uint32_t v) const {
-    E w = ldx(q, lane >> 5);
-    const uint32_t bit = 1u << (lane & 31);
-    w.l = (w.l & ~bit) | ((v & 1u) ? bit : 0u);
-    w.h = (w.h & ~bit) | ((v & 2u) ? bit : 0u);
-    stx(q, lane >> 5, w);
+    stx(q, lane >> 5, setbit2(ld(q, lane >> 5).x, lane & 31, v));
   }
   __device__ __forceinline__ void setz(int q, int lane, uint32_t v) const {
-    E w = ldz(q, lane >> 5);
-    const uint32_t bit = 1u << (lane & 31);
-    w.l = (w.l & ~bit) | ((v & 1u) ? bit : 0u);
-    w.h = (w.h & ~bit) | ((v & 2u) ? bit : 0u);
-    stz(q, lane >> 5, w);
+    stz(q, lane >> 5, setbit2(ld(q, lane >> 5).z, lane & 31, v));
   }
   __device__ __forceinline__ void setp(int lane, uint32_t v) const {
-    E w = ldp(lane >> 5);
-    const uint32_t bit = 1u << (lane & 31);
-    w.l = (w.l & ~bit) | ((v & 1u) ? bit : 0u);
-    w.h = (w.h & ~bit) | ((v & 2u) ? bit : 0u);
-    stp(lane >> 5, w);
+    stp(lane >> 5, setbit2(ldp(lane >> 5), lane & 31, v));
   }
 };
 
 struct PScratch {
-  uint32_t* fl;      // [Wb] factor planes f = -X[q,i]
-  uint32_t* fh;      // [Wb]
   int4* ops;         // [32] staged op batch
-  uint16_t* ar;      // [np] active rows / active generators
-  uint8_t* xs;       // [np]
-  uint8_t* zs;       // [np]
+  uint2* f;          // [Wb] factor planes f = -X[q,i]
+  uint16_t* ar;      // [np] active rows (pivot support) / active generators (det branch)
+  uint16_t* br;      // [np] rows whose destabilizer-p entry must be cleared
+  uint8_t* xz;       // [np] pivot column: xs | zs << 2   (det branch: factor of active generator k)
 };
 
-// ---- gates: lane j of the warp owns word j of every plane -------------------------------------------
+// ---- gates: lane j of the warp owns lane word j of every row ------------------------------------------
 template <int D>
 __device__ __forceinline__ void g_h(const Geo<D>& G, int a, bool inverse) {
   for (int j = threadIdx.x; j < G.Wb; j += 32) {
-    const E x = G.ldx(a, j), z = G.ldz(a, j);
-    if ((x.l | x.h | z.l | z.h) == 0) continue;
+    const XZ v = G.ld(a, j);
     E p = G.ldp(j);
     if (D == 3) {
-      p = add3(p, neg3(mul3(x, z)));                       // phase -= x*z
-      G.stx(a, j, inverse ? z : neg3(z));                  // H: (x,z) <- (-z,x); H^-1: (x,z) <- (z,-x)
-      G.stz(a, j, inverse ? neg3(x) : x);
+      p = add3(p, neg3(mul3(v.x, v.z)));                                  // phase -= x*z
+      G.st(a, j, inverse ? XZ{v.z, neg3(v.x)} : XZ{neg3(v.z), v.x});     // H: (x,z)<-(-z,x); H^-1: (x,z)<-(z,-x)
     } else {
-      p.h ^= x.l & z.l;                                    // phase += 2*x*z (mod 4); H == H^-1 on qubits
-      G.stx(a, j, z);
-      G.stz(a, j, x);
+      p.h ^= v.x.l & v.z.l;                                               // phase += 2*x*z (mod 4); H == H^-1
+      G.st(a, j, XZ{v.z, v.x});
     }
     G.stp(j, p);
   }
@@ -137,19 +125,15 @@ __device__ __forceinline__ void g_h(const Geo<D>& G, int a, bool inverse) {
 template <int D>
 __device__ __forceinline__ void g_p(const Geo<D>& G, int a, bool inverse) {
   for (int j = threadIdx.x; j < G.Wb; j += 32) {
-    const E x = G.ldx(a, j);
-    if ((x.l | x.h) == 0) continue;
-    const E z = G.ldz(a, j);
+    const XZ v = G.ld(a, j);
     E p = G.ldp(j);
     if (D == 3) {
-      // phase +-= x(x-1)/2 = [x == 2];  z +-= x
-      p = add3(p, inverse ? E{0u, x.h} : E{x.h, 0u});
-      G.stz(a, j, add3(z, inverse ? neg3(x) : x));
+      p = add3(p, inverse ? E{0u, v.x.h} : E{v.x.h, 0u});                 // phase +-= x(x-1)/2 = [x == 2]
+      G.stz(a, j, add3(v.z, inverse ? neg3(v.x) : v.x));                  // z +-= x
     } else {
-      // phase +-= x^2 = x (mod 4);  z ^= x
-      if (inverse) { const uint32_t borrow = ~p.l & x.l; p.l ^= x.l; p.h ^= borrow; }
-      else { const uint32_t carry = p.l & x.l; p.l ^= x.l; p.h ^= carry; }
-      G.stz(a, j, E{z.l ^ x.l, 0u});
+      if (inverse) { const uint32_t borrow = ~p.l & v.x.l; p.l ^= v.x.l; p.h ^= borrow; }   // phase -= x (mod 4)
+      else { const uint32_t carry = p.l & v.x.l; p.l ^= v.x.l; p.h ^= carry; }              // phase += x^2 = x
+      G.stz(a, j, E{v.z.l ^ v.x.l, 0u});
     }
     G.stp(j, p);
   }
@@ -159,20 +143,10 @@ __device__ __forceinline__ void g_p(const Geo<D>& G, int a, bool inverse) {
 template <int D>
 __device__ __forceinline__ void g_pauli(const Geo<D>& G, int q, uint32_t a, uint32_t b) {
   for (int j = threadIdx.x; j < G.Wb; j += 32) {
+    const XZ v = G.ld(q, j);
     E p = G.ldp(j);
-    if (D == 3) {
-      E t{0u, 0u};
-      if (b) t = smul3(G.ldx(q, j), b);
-      if (a) t = add3(t, smul3(G.ldz(q, j), 3u - a));
-      if ((t.l | t.h) == 0) continue;
-      p = add3(p, t);
-    } else {
-      uint32_t t = 0;
-      if (b & 1u) t ^= G.ldx(q, j).l;
-      if (a & 1u) t ^= G.ldz(q, j).l;
-      if (!t) continue;
-      p.h ^= t;
-    }
+    if (D == 3) p = add3(p, add3(smul3(v.x, b), smul3(v.z, (3u - a) % 3u)));
+    else p.h ^= ((b & 1u) ? v.x.l : 0u) ^ ((a & 1u) ? v.z.l : 0u);
     G.stp(j, p);
   }
 }
@@ -180,15 +154,13 @@ __device__ __forceinline__ void g_pauli(const Geo<D>& G, int q, uint32_t a, uint
 template <int D>
 __device__ __forceinline__ void g_cnot(const Geo<D>& G, int a, int b, bool inverse) {
   for (int j = threadIdx.x; j < G.Wb; j += 32) {
-    const E xa = G.ldx(a, j), zb = G.ldz(b, j);
-    if ((xa.l | xa.h | zb.l | zb.h) == 0) continue;
-    const E xb = G.ldx(b, j), za = G.ldz(a, j);
+    const XZ va = G.ld(a, j), vb = G.ld(b, j);
     if (D == 3) {
-      G.stx(b, j, add3(xb, inverse ? neg3(xa) : xa));      // x[t] +-= x[c]
-      G.stz(a, j, add3(za, inverse ? zb : neg3(zb)));      // z[c] -+= z[t]
+      G.stx(b, j, add3(vb.x, inverse ? neg3(va.x) : va.x));               // x[t] +-= x[c]
+      G.stz(a, j, add3(va.z, inverse ? vb.z : neg3(vb.z)));               // z[c] -+= z[t]
     } else {
-      G.stx(b, j, E{xb.l ^ xa.l, 0u});
-      G.stz(a, j, E{za.l ^ zb.l, 0u});
+      G.stx(b, j, E{vb.x.l ^ va.x.l, 0u});
+      G.stz(a, j, E{va.z.l ^ vb.z.l, 0u});
     }
   }
 }
@@ -196,19 +168,17 @@ __device__ __forceinline__ void g_cnot(const Geo<D>& G, int a, int b, bool inver
 template <int D>
 __device__ __forceinline__ void g_cz(const Geo<D>& G, int a, int b, bool inverse) {
   for (int j = threadIdx.x; j < G.Wb; j += 32) {
-    const E xa = G.ldx(a, j), xb = G.ldx(b, j);
-    if ((xa.l | xa.h | xb.l | xb.h) == 0) continue;
-    const E za = G.ldz(a, j), zb = G.ldz(b, j);
+    const XZ va = G.ld(a, j), vb = G.ld(b, j);
     E p = G.ldp(j);
     if (D == 3) {
-      const E prod = mul3(xa, xb);
-      p = add3(p, inverse ? neg3(prod) : prod);            // phase +-= x[a]*x[b]
-      G.stz(a, j, add3(za, inverse ? neg3(xb) : xb));
-      G.stz(b, j, add3(zb, inverse ? neg3(xa) : xa));
+      const E prod = mul3(va.x, vb.x);
+      p = add3(p, inverse ? neg3(prod) : prod);                           // phase +-= x[a]*x[b]
+      G.stz(a, j, add3(va.z, inverse ? neg3(vb.x) : vb.x));
+      G.stz(b, j, add3(vb.z, inverse ? neg3(va.x) : va.x));
     } else {
-      p.h ^= xa.l & xb.l;
-      G.stz(a, j, E{za.l ^ xb.l, 0u});
-      G.stz(b, j, E{zb.l ^ xa.l, 0u});
+      p.h ^= va.x.l & vb.x.l;
+      G.stz(a, j, E{va.z.l ^ vb.x.l, 0u});
+      G.stz(b, j, E{vb.z.l ^ va.x.l, 0u});
     }
     G.stp(j, p);
   }
@@ -216,10 +186,10 @@ __device__ __forceinline__ void g_cz(const Geo<D>& G, int a, int b, bool inverse
 
 template <int D>
 __device__ __forceinline__ void g_swap(const Geo<D>& G, int a, int b) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {   // lane j swaps word j of every plane (lane ownership)
-    const E xa = G.ldx(a, j), za = G.ldz(a, j), xb = G.ldx(b, j), zb = G.ldz(b, j);
-    G.stx(a, j, xb); G.stz(a, j, zb);
-    G.stx(b, j, xa); G.stz(b, j, za);
+  for (int j = threadIdx.x; j < G.Wb; j += 32) {   // lane j swaps lane word j (lane ownership holds across gates)
+    const XZ va = G.ld(a, j), vb = G.ld(b, j);
+    G.st(a, j, vb);
+    G.st(b, j, va);
   }
 }
 
@@ -252,12 +222,13 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO;
   const int n = G.n, np = G.np, Wb = G.Wb, lane = threadIdx.x;
+  const uint32_t lt = (1u << lane) - 1u;
   __syncwarp();
 
   // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283)
   uint32_t best = kNoPivot;
   for (int j = lane; j < np / 32; j += 32) {
-    const E x = G.ldx(q, j);
+    const E x = G.ld(q, j).x;
     const uint32_t m = x.l | x.h;
     if (m) { best = 32u * j + (__ffs(m) - 1); break; }
   }
@@ -276,32 +247,38 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
   uint32_t outcome, rec;
   if (piv != kNoPivot) {
     // ---- random branch (tableau_prime.py:294-334, exponentiate :365-380 folded in) ----
-    const uint32_t e = (D == 3) ? G.getx(q, piv) : 1u;      // inverse of v mod 3 is v itself
+    const int jp = piv >> 5, bp = piv & 31, jd = np / 32 + jp;          // stab word / bit, destab word of lane p
+    const uint32_t e = (D == 3) ? G.getx(q, piv) : 1u;                  // inverse of v mod 3 is v itself
     const uint32_t ps_old = G.getp(piv);
+    // one pass down the pivot column AND the destabilizer-p column: support list, values, stale destab entries
     uint32_t sd_raw = 0;
-    int nr_a = 0;
+    int nr_a = 0, nr_b = 0;
     for (int base = 0; base < n; base += 32) {
       const int r = base + lane;
-      uint32_t xr = 0, zr = 0;
+      uint32_t xr = 0, zr = 0, od = 0;
       if (r < n) {
-        xr = G.getx(r, piv); zr = G.getz(r, piv);
-        S.xs[r] = (uint8_t)((xr * e) % D);
-        S.zs[r] = (uint8_t)((zr * e) % D);
+        const XZ s = G.ld(r, jp), dd = G.ld(r, jd);
+        xr = bit2(s.x, bp); zr = bit2(s.z, bp);
+        od = bit2(dd.x, bp) | bit2(dd.z, bp);
         sd_raw += xr * zr;
+        if (D == 3 && e == 2u) { xr = (xr >> 1) | ((xr & 1u) << 1); zr = (zr >> 1) | ((zr & 1u) << 1); }   // * 2 = negate
+        S.xz[r] = (uint8_t)(xr | (zr << 2));
       }
-      const uint32_t mask = __ballot_sync(FULL, (xr | zr) != 0);
-      if (xr | zr) S.ar[nr_a + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)r;
-      nr_a += __popc(mask);
+      const bool act = (xr | zr) != 0, stale = !act && od != 0;
+      const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, stale);
+      if (act) S.ar[nr_a + __popc(ma & lt)] = (uint16_t)r;
+      if (stale) S.br[nr_b + __popc(mb & lt)] = (uint16_t)r;
+      nr_a += __popc(ma);
+      nr_b += __popc(mb);
     }
     sd_raw = __reduce_add_sync(FULL, sd_raw) % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
     // factors f = -X[q,i] for every lane but the pivot itself
     for (int j = lane; j < Wb; j += 32) {
-      E x = G.ldx(q, j);
-      if (j == (int)(piv >> 5)) { x.l &= ~(1u << (piv & 31)); x.h &= ~(1u << (piv & 31)); }
-      S.fl[j] = (D == 3) ? x.h : x.l;
-      S.fh[j] = (D == 3) ? x.l : 0u;
+      E x = G.ld(q, j).x;
+      if (j == jp) { x.l &= ~(1u << bp); x.h &= ~(1u << bp); }
+      S.f[j] = (D == 3) ? make_uint2(x.h, x.l) : make_uint2(x.l, 0u);
     }
     __syncwarp();
     // col_i += f_i * col_p on the pivot's support; lanes split into 32/Wb row groups when Wb divides 32
@@ -309,20 +286,20 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
     const int jstep = groups > 1 ? Wb : 32;
     const int grp = groups > 1 ? lane / Wb : 0;
     for (int j = groups > 1 ? lane % Wb : lane; j < Wb; j += jstep) {
-      const E f{S.fl[j], S.fh[j]};
+      const uint2 fv = S.f[j];
+      const E f{fv.x, fv.y};
       E dot{0u, 0u};
       if (f.l | f.h) {
         for (int ri = grp; ri < nr_a; ri += groups) {
           const int r = S.ar[ri];
-          const uint32_t s = S.xs[r], t = S.zs[r];
-          const E x = G.ldx(r, j), z = G.ldz(r, j);
+          const uint32_t c = S.xz[r], s = c & 3u, t = c >> 2;
+          const XZ v = G.ld(r, j);
           if (D == 3) {
-            dot = add3(dot, smul3(z, s));                   // Z[:,i] . x_p  (old Z)
-            if (s) G.stx(r, j, add3(x, smul3(f, s)));
-            if (t) G.stz(r, j, add3(z, smul3(f, t)));
+            dot = add3(dot, smul3(v.z, s));                               // Z[:,i] . x_p  (old Z)
+            G.st(r, j, XZ{add3(v.x, smul3(f, s)), add3(v.z, smul3(f, t))});
           } else {
-            if (s) { dot.l ^= z.l; G.stx(r, j, E{x.l ^ f.l, 0u}); }
-            if (t) G.stz(r, j, E{z.l ^ f.l, 0u});
+            if (s) dot.l ^= v.z.l;
+            G.st(r, j, XZ{E{v.x.l ^ (s ? f.l : 0u), 0u}, E{v.z.l ^ (t ? f.l : 0u), 0u}});
           }
         }
       }
@@ -335,7 +312,7 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
         E ph = G.ldp(j);
         if (D == 3) {
           E t = add3(smul3(f, ps), mul3(dot, f));
-          t = add3(t, smul3(E{f.h, 0u}, sd));               // f(f-1)/2 = [f == 2]
+          t = add3(t, smul3(E{f.h, 0u}, sd));                             // f(f-1)/2 = [f == 2]
           ph = add3(ph, t);
         } else {
           ph = add4(ph, E{(ps & 1u) ? f.l : 0u, (ps & 2u) ? f.l : 0u});
@@ -345,39 +322,58 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
       }
     }
     __syncwarp();
-    // destabilizer p <- old pivot; stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333)
+    // destabilizer p <- old pivot; stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333).
+    // Only rows where something changes are touched: the support (list ar) and stale destabilizer rows (br).
     for (int i = lane; i < nr_a; i += 32) {
       const int r = S.ar[i];
-      G.setx(r, piv, 0u);
-      G.setz(r, piv, 0u);
+      const uint32_t c = S.xz[r];
+      XZ s = G.ld(r, jp);
+      s.x = setbit2(s.x, bp, 0u);
+      s.z = setbit2(s.z, bp, (r == q) ? 1u : 0u);
+      G.st(r, jp, s);
+      XZ dd = G.ld(r, jd);
+      dd.x = setbit2(dd.x, bp, c & 3u);
+      dd.z = setbit2(dd.z, bp, c >> 2);
+      G.st(r, jd, dd);
     }
-    for (int r = lane; r < n; r += 32) {
-      G.setx(r, np + piv, S.xs[r]);
-      G.setz(r, np + piv, S.zs[r]);
+    for (int i = lane; i < nr_b; i += 32) {
+      const int r = S.br[i];
+      XZ dd = G.ld(r, jd);
+      dd.x = setbit2(dd.x, bp, 0u);
+      dd.z = setbit2(dd.z, bp, 0u);
+      G.st(r, jd, dd);
     }
-    __syncwarp();
     outcome = draw;
-    if (lane == 0) {
-      G.setz(q, piv, 1u);
-      G.setp(np + piv, ps);
-      G.setp(piv, (ORDER - outcome * PO) % ORDER);
-    }
+    if (lane == 0) G.setp(np + piv, ps);
+    if (lane == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
     rec = outcome;
   } else {
     // ---- deterministic branch (tableau_prime.py:336-363) ----
+    // ordered list of the generators with factor f_i = destab X[q,i] != 0, straight from the plane words
     uint32_t a1 = 0;
     int total = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const uint32_t f = (i < n) ? G.getx(q, np + i) : 0u;
-      const uint32_t mask = __ballot_sync(FULL, f != 0);
-      if (f) {
-        const int pos = total + __popc(mask & ((1u << lane) - 1u));
-        S.ar[pos] = (uint16_t)i;
-        S.xs[pos] = (uint8_t)f;
-        a1 += f * G.getp(i);
+    for (int base = 0; base < np / 32; base += 32) {
+      const int j = base + lane;
+      E f{0u, 0u}, ph{0u, 0u};
+      if (j < np / 32) { f = G.ld(q, np / 32 + j).x; ph = G.ldp(j); }
+      uint32_t m = f.l | f.h;
+      const int cnt = __popc(m);
+      int off = cnt;                                                      // inclusive warp scan of the counts
+      for (int d2 = 1; d2 < 32; d2 <<= 1) {
+        const int o = __shfl_up_sync(FULL, off, d2);
+        if (lane >= d2) off += o;
       }
-      total += __popc(mask);
+      int pos = total + off - cnt;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t fv = bit2(f, b);
+        S.ar[pos] = (uint16_t)(32 * j + b);
+        S.xz[pos] = (uint8_t)fv;
+        a1 += fv * bit2(ph, b);
+        ++pos;
+      }
+      total += __shfl_sync(FULL, off, 31);
     }
     a1 = __reduce_add_sync(FULL, a1) % ORDER;
     __syncwarp();
@@ -386,9 +382,10 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
       uint32_t az = 0, cross = 0, sdg = 0;
       for (int k = 0; k < total; ++k) {
         const int g = S.ar[k];
-        const uint32_t f = S.xs[k];
-        const uint32_t xi = G.getx(r, g), zi = G.getz(r, g);
-        cross += (f * xi) * az;                              // ancilla_z . (f * x_i), running ancilla
+        const uint32_t f = S.xz[k];
+        const XZ v = G.ld(r, g >> 5);
+        const uint32_t xi = bit2(v.x, g & 31), zi = bit2(v.z, g & 31);
+        cross += (f * xi) * az;                                           // ancilla_z . (f * x_i), running ancilla
         az = (az + f * zi) % D;
         sdg += xi * zi * ((f * (f - 1u)) >> 1);
         if ((k & 15) == 15) { cross %= D; sdg %= D; }
@@ -397,7 +394,7 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
     }
     part = __reduce_add_sync(FULL, part) % D;
     const uint32_t ap = (a1 + PO * part) % ORDER;
-    outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);   // (-ap // po) % d  (tableau_prime.py:362)
+    outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);        // (-ap // po) % d  (tableau_prime.py:362)
     rec = outcome | SDIMB_REC_DET;
   }
   if (lane == 0) p.records[shot_local * p.rec_stride + slot] = (uint8_t)rec;
@@ -413,16 +410,15 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
   G.n = p.n;
   G.np = (p.n + 31) / 32 * 32;
   G.Wb = 2 * G.np / 32;
-  G.RW = 2 * Geo<D>::B * G.Wb;
+  G.RS = Geo<D>::EW * (G.Wb + 1);
   G.tab = reinterpret_cast<uint32_t*>(smem);
-  const int tab_words = p.n * G.RW + 2 * G.Wb;
+  const int tab_words = (p.n * G.RS + 2 * G.Wb + 3) & ~3;
   PScratch S;
-  S.fl = G.tab + tab_words;
-  S.fh = S.fl + G.Wb;
-  S.ops = reinterpret_cast<int4*>(S.fh + G.Wb + ((4 - ((tab_words + 2 * G.Wb) & 3)) & 3));
-  S.ar = reinterpret_cast<uint16_t*>(S.ops + 32);
-  S.xs = reinterpret_cast<uint8_t*>(S.ar + G.np);
-  S.zs = S.xs + G.np;
+  S.ops = reinterpret_cast<int4*>(G.tab + tab_words);
+  S.f = reinterpret_cast<uint2*>(S.ops + 32);
+  S.ar = reinterpret_cast<uint16_t*>(S.f + G.Wb);
+  S.br = S.ar + G.np;
+  S.xz = reinterpret_cast<uint8_t*>(S.br + G.np);
   const int lane = threadIdx.x;
 
   for (int64_t shot = blockIdx.x; shot < p.shots; shot += gridDim.x) {
@@ -439,16 +435,16 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
       for (int q = 0; q < p.n; ++q) {
         const uint8_t* row8 = T8 + (int64_t)q * p.row_bytes;
         for (int j = lane; j < G.Wb; j += 32) {
-          E x{0u, 0u}, z{0u, 0u};
+          XZ v{E{0u, 0u}, E{0u, 0u}};
           for (int b = 0; b < 32; ++b) {
             const int ln = 32 * j + b;
             const int half = ln >= G.np, g = half ? ln - G.np : ln;
             if (g >= p.n) continue;
             const uint32_t xv = row8[half * p.np + g], zv = row8[p.W + half * p.np + g];
-            x.l |= (xv & 1u) << b; x.h |= ((xv >> 1) & 1u) << b;
-            z.l |= (zv & 1u) << b; z.h |= ((zv >> 1) & 1u) << b;
+            v.x.l |= (xv & 1u) << b; v.x.h |= ((xv >> 1) & 1u) << b;
+            v.z.l |= (zv & 1u) << b; v.z.h |= ((zv >> 1) & 1u) << b;
           }
-          G.stx(q, j, x); G.stz(q, j, z);
+          G.st(q, j, v);
         }
       }
       for (int j = lane; j < G.Wb; j += 32) {
@@ -464,6 +460,7 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
       }
     }
     __syncwarp();
+
     for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
       // fetch 32 ops, one per lane; the fetching lane resolves N1 events, so only live ops are dispatched
       int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
@@ -531,10 +528,10 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
 }
 
 inline size_t planes_smem_bytes(int n, int d) {
-  const int B = (d == 2) ? 1 : 2;
-  const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32, RW = 2 * B * Wb;
-  const size_t tab_words = (size_t)n * RW + 2 * Wb;
-  return 4 * (tab_words + 2 * Wb + 4) + 32 * 16 + 2 * np + 2 * np + 16;
+  const size_t EW = (d == 2) ? 2 : 4;
+  const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32, RS = EW * (Wb + 1);
+  const size_t tab_words = ((size_t)n * RS + 2 * Wb + 3) & ~(size_t)3;
+  return 4 * tab_words + 32 * 16 + 8 * Wb + 2 * np + 2 * np + np + 16;
 }
 
 }  // namespace planes
