@@ -54,8 +54,14 @@ enum {
   SDIMB_OP_I = 0, SDIMB_OP_X = 1, SDIMB_OP_X_INV = 2, SDIMB_OP_Z = 3, SDIMB_OP_Z_INV = 4,
   SDIMB_OP_H = 5, SDIMB_OP_H_INV = 6, SDIMB_OP_P = 7, SDIMB_OP_P_INV = 8,
   SDIMB_OP_CNOT = 9, SDIMB_OP_CNOT_INV = 10, SDIMB_OP_CZ = 11, SDIMB_OP_CZ_INV = 12, SDIMB_OP_SWAP = 13,
-  SDIMB_OP_M = 14, SDIMB_OP_M_X = 15, SDIMB_OP_RESET = 16, SDIMB_OP_N1 = 17
+  SDIMB_OP_M = 14, SDIMB_OP_M_X = 15, SDIMB_OP_RESET = 16, SDIMB_OP_N1 = 17,
+  SDIMB_OP_BARRIER = 18   /* layer boundary emitted by sdimb_schedule; never written by users */
 };
+/* In a SCHEDULED stream (output of sdimb_schedule) bits 8..15 of the opcode field carry the warp that
+ * executes the op inside its layer; bits 0..7 are the opcode.  An unscheduled stream has those bits 0. */
+#define SDIMB_OP_MASK 0xFF
+#define SDIMB_OP_WARP_SHIFT 8
+#define SDIMB_SCHED_WARPS 4
 
 /* Record byte: low 7 bits = measured value, bit 7 = deterministic flag
  * (MeasurementResult.measurement_value / .deterministic, sdim/tableau/dataclasses.py:166-180). */
@@ -69,6 +75,8 @@ enum {
 #define SDIMB_FORCE_RESIDENT 0x8u  /* require the shared-memory resident uint8-lane interpreter (else SDIMB_ETOOBIG) */
 #define SDIMB_FORCE_LANES 0x10u    /* never use the bit-plane interpreter (d = 2, 3), keep uint8 lanes */
 #define SDIMB_FORCE_PLANES 0x20u   /* require the bit-plane resident interpreter (d = 2, 3; else SDIMB_ETOOBIG) */
+#define SDIMB_SCHEDULED 0x40u      /* `ops` is the output of sdimb_schedule: the bit-plane interpreter may run
+                                      SDIMB_SCHED_WARPS warps per shot, one commuting layer at a time */
 
 typedef struct SdimbLayout {
   int32_t n, d, np, lanes;   /* lanes = W = 2*np */
@@ -131,6 +139,15 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,
                         const uint8_t* replay_meas, const uint8_t* replay_noise,
                         const uint32_t* noise_thresh24, const uint8_t* noise_channel, int64_t n_noise,
                         uint64_t seed, uint32_t flags, float* elapsed_ms);
+
+/* Host-side op-stream scheduler (no GPU work).  Reorders the gates between two collective ops (M, M_X, RESET)
+ * into layers of ops on pairwise disjoint qudits (ASAP levels over row read/write dependencies), assigns the
+ * ops of a layer round-robin to SDIMB_SCHED_WARPS warps and separates layers with SDIMB_OP_BARRIER.  Ops on
+ * disjoint qudits commute exactly on the tableau (they touch disjoint rows and their phase increments add), so
+ * records and final tableaus are unchanged; event slots travel with their ops.  `out` needs room for
+ * 2*n_ops + 1 rows; *out_n receives the number written.  Replaces nothing in the reference (its loop is strictly
+ * sequential, sdim/program.py:311-312); SURVEY 8f rank 3. */
+int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap, int64_t* out_n);
 
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store,
  * 1 uint8 lanes resident in shared memory, 2 bit-plane resident (d = 2, 3); *needs_tableau = whether

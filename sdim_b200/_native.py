@@ -8,11 +8,13 @@ from .build import LIB_PATH
 
 OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
 FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT, FORCE_LANES, FORCE_PLANES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+SCHEDULED = 0x40
+OP_BARRIER = 18
 KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
-                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan")
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule")
 
 
 class SdimbLayout(C.Structure):
@@ -60,6 +62,7 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_float)]
     L.sdimb_launch_count.restype = C.c_int64
+    L.sdimb_schedule.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
@@ -86,3 +89,14 @@ def plan(n: int, d: int, flags: int):
     k, need = C.c_int(0), C.c_int(0)
     check(lib().sdimb_plan(n, d, flags, C.byref(k), C.byref(need)))
     return k.value, bool(need.value)
+
+
+def schedule(n: int, ops):
+    """Layered op stream (sdimb_schedule) of an int32[n_ops, 4] array; host-only, no GPU needed."""
+    import numpy as np
+    ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 4)
+    out = np.empty((2 * ops.shape[0] + 1, 4), dtype=np.int32)
+    count = C.c_int64(0)
+    check(lib().sdimb_schedule(n, ops.ctypes.data if ops.size else None, ops.shape[0], out.ctypes.data,
+                               out.shape[0], C.byref(count)))
+    return out[: count.value].copy()

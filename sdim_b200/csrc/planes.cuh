@@ -17,6 +17,13 @@
 // Lane numbering is that of the uint8 store (include/sdimb.h): stabilizer g -> lane g, destabilizer g -> lane
 // np + g, with np a multiple of 32 here so the two halves never share a word.
 //
+// One CTA owns one shot.  With an unscheduled op stream the CTA is a single warp.  With a SCHEDULED stream
+// (sdimb_schedule: layers of gates on pairwise disjoint qudits, separated by barriers) the CTA has
+// SDIMB_SCHED_WARPS warps: inside a layer each warp executes its share of the gates — every warp adds its phase
+// increments to a PRIVATE phase accumulator, so gates of one layer never touch the same word — and
+// measurements split their column walks and row updates over all warps.  The accumulators are folded into
+// accumulator 0 at the start of each measurement.
+//
 // Same reference behaviour as the uint8 interpreter in sdimb.cu (file:line citations there).
 #pragma once
 
@@ -57,9 +64,11 @@ template <int D>
 struct Geo {
   static constexpr int EW = (D == 2) ? 2 : 4;   // words per entry
   uint32_t* tab;                                // shared-memory image
+  uint2* pacc;                                  // phase accumulator used by ldp/stp (this warp's, or #0 in measure)
   int n, np, Wb, RS;                            // RS = row stride in words = EW * (Wb + 1)
   __device__ __forceinline__ uint32_t* entry(int q, int j) const { return tab + q * RS + j * EW; }
-  __device__ __forceinline__ uint2* phase() const { return reinterpret_cast<uint2*>(tab + n * RS); }
+  __device__ __forceinline__ uint2* phase() const { return pacc; }
+  __device__ __forceinline__ uint2* phase_of(int w) const { return reinterpret_cast<uint2*>(tab + n * RS) + w * Wb; }
   __device__ __forceinline__ XZ ld(int q, int j) const {
     if (D == 3) {
       const uint4 v = *reinterpret_cast<const uint4*>(entry(q, j));
@@ -98,17 +107,23 @@ struct Geo {
 };
 
 struct PScratch {
-  int4* ops;         // [32] staged op batch
+  int4* ops;         // [NW][32] staged op batch, private to each warp
   uint2* f;          // [Wb] factor planes f = -X[q,i]
+  uint2* dotw;       // [NW][Wb] per-warp partial dot products
+  uint32_t* cnt;     // [4] list lengths / block accumulators
   uint16_t* ar;      // [np] active rows (pivot support) / active generators (det branch)
   uint16_t* br;      // [np] rows whose destabilizer-p entry must be cleared
   uint8_t* xz;       // [np] pivot column: xs | zs << 2   (det branch: factor of active generator k)
 };
 
+__device__ __forceinline__ void cta_sync() {
+  if (blockDim.x == 32) __syncwarp(); else __syncthreads();
+}
+
 // ---- gates: lane j of the warp owns lane word j of every row ------------------------------------------
 template <int D>
 __device__ __forceinline__ void g_h(const Geo<D>& G, int a, bool inverse) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {
+  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
     const XZ v = G.ld(a, j);
     E p = G.ldp(j);
     if (D == 3) {
@@ -124,7 +139,7 @@ __device__ __forceinline__ void g_h(const Geo<D>& G, int a, bool inverse) {
 
 template <int D>
 __device__ __forceinline__ void g_p(const Geo<D>& G, int a, bool inverse) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {
+  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
     const XZ v = G.ld(a, j);
     E p = G.ldp(j);
     if (D == 3) {
@@ -142,7 +157,7 @@ __device__ __forceinline__ void g_p(const Geo<D>& G, int a, bool inverse) {
 // Pauli X^a Z^b on qudit q: phase += po*(b*x - a*z)
 template <int D>
 __device__ __forceinline__ void g_pauli(const Geo<D>& G, int q, uint32_t a, uint32_t b) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {
+  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
     const XZ v = G.ld(q, j);
     E p = G.ldp(j);
     if (D == 3) p = add3(p, add3(smul3(v.x, b), smul3(v.z, (3u - a) % 3u)));
@@ -153,7 +168,7 @@ __device__ __forceinline__ void g_pauli(const Geo<D>& G, int q, uint32_t a, uint
 
 template <int D>
 __device__ __forceinline__ void g_cnot(const Geo<D>& G, int a, int b, bool inverse) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {
+  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
     const XZ va = G.ld(a, j), vb = G.ld(b, j);
     if (D == 3) {
       G.stx(b, j, add3(vb.x, inverse ? neg3(va.x) : va.x));               // x[t] +-= x[c]
@@ -167,7 +182,7 @@ __device__ __forceinline__ void g_cnot(const Geo<D>& G, int a, int b, bool inver
 
 template <int D>
 __device__ __forceinline__ void g_cz(const Geo<D>& G, int a, int b, bool inverse) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {
+  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
     const XZ va = G.ld(a, j), vb = G.ld(b, j);
     E p = G.ldp(j);
     if (D == 3) {
@@ -186,7 +201,7 @@ __device__ __forceinline__ void g_cz(const Geo<D>& G, int a, int b, bool inverse
 
 template <int D>
 __device__ __forceinline__ void g_swap(const Geo<D>& G, int a, int b) {
-  for (int j = threadIdx.x; j < G.Wb; j += 32) {   // lane j swaps lane word j (lane ownership holds across gates)
+  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {   // lane j swaps lane word j (lane ownership holds across gates)
     const XZ va = G.ld(a, j), vb = G.ld(b, j);
     G.st(a, j, vb);
     G.st(b, j, va);
@@ -215,17 +230,31 @@ __device__ __forceinline__ uint32_t p_noise_event(const KParams& p, int64_t j, i
   return a | (b << 8);
 }
 
-// ---- measurement (one warp) ---------------------------------------------------------------------------
+// ---- measurement (whole CTA: 1 or SDIMB_SCHED_WARPS warps) -----------------------------------------------------
 template <int D>
-__device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, int q, int64_t slot,
-                              int64_t shot_local) {
+__device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO;
-  const int n = G.n, np = G.np, Wb = G.Wb, lane = threadIdx.x;
+  const int n = G.n, np = G.np, Wb = G.Wb;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  __syncwarp();
+  cta_sync();                                          // all gates of the previous layer are done
+  // fold the per-warp phase accumulators into accumulator 0; reset the list counters
+  G.pacc = G.phase_of(0);
+  if (tid < 4) S.cnt[tid] = 0;
+  for (int j = tid; j < Wb && nw > 1; j += nt) {
+    E acc = G.ldp(j);
+    for (int w = 1; w < nw; ++w) {
+      uint2* pw = G.phase_of(w) + j;
+      const E o{pw->x, pw->y};
+      acc = (D == 3) ? add3(acc, o) : add4(acc, o);
+      *pw = make_uint2(0u, 0u);
+    }
+    G.stp(j, acc);
+  }
+  cta_sync();
 
-  // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283)
+  // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283); every warp looks itself
   uint32_t best = kNoPivot;
   for (int j = lane; j < np / 32; j += 32) {
     const E x = G.ld(q, j).x;
@@ -251,46 +280,53 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
     const uint32_t e = (D == 3) ? G.getx(q, piv) : 1u;                  // inverse of v mod 3 is v itself
     const uint32_t ps_old = G.getp(piv);
     // one pass down the pivot column AND the destabilizer-p column: support list, values, stale destab entries
-    uint32_t sd_raw = 0;
-    int nr_a = 0, nr_b = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int r = base + lane;
+    uint32_t sd_part = 0;
+    for (int base = 0; base < n; base += nt) {
+      const int r = base + tid;
       uint32_t xr = 0, zr = 0, od = 0;
       if (r < n) {
         const XZ s = G.ld(r, jp), dd = G.ld(r, jd);
         xr = bit2(s.x, bp); zr = bit2(s.z, bp);
         od = bit2(dd.x, bp) | bit2(dd.z, bp);
-        sd_raw += xr * zr;
+        sd_part += xr * zr;
         if (D == 3 && e == 2u) { xr = (xr >> 1) | ((xr & 1u) << 1); zr = (zr >> 1) | ((zr & 1u) << 1); }   // * 2 = negate
         S.xz[r] = (uint8_t)(xr | (zr << 2));
       }
       const bool act = (xr | zr) != 0, stale = !act && od != 0;
       const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, stale);
-      if (act) S.ar[nr_a + __popc(ma & lt)] = (uint16_t)r;
-      if (stale) S.br[nr_b + __popc(mb & lt)] = (uint16_t)r;
-      nr_a += __popc(ma);
-      nr_b += __popc(mb);
+      uint32_t ba = 0, bb = 0;
+      if (lane == 0) {
+        if (ma) ba = atomicAdd(&S.cnt[0], (uint32_t)__popc(ma));
+        if (mb) bb = atomicAdd(&S.cnt[1], (uint32_t)__popc(mb));
+      }
+      ba = __shfl_sync(FULL, ba, 0);
+      bb = __shfl_sync(FULL, bb, 0);
+      if (act) S.ar[ba + __popc(ma & lt)] = (uint16_t)r;
+      if (stale) S.br[bb + __popc(mb & lt)] = (uint16_t)r;
     }
-    sd_raw = __reduce_add_sync(FULL, sd_raw) % D;
-    const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
-    const uint32_t sd = (sd_raw * e * e) % D;
+    sd_part = __reduce_add_sync(FULL, sd_part);
+    if (lane == 0 && sd_part) atomicAdd(&S.cnt[2], sd_part);
     // factors f = -X[q,i] for every lane but the pivot itself
-    for (int j = lane; j < Wb; j += 32) {
+    for (int j = tid; j < Wb; j += nt) {
       E x = G.ld(q, j).x;
       if (j == jp) { x.l &= ~(1u << bp); x.h &= ~(1u << bp); }
       S.f[j] = (D == 3) ? make_uint2(x.h, x.l) : make_uint2(x.l, 0u);
     }
-    __syncwarp();
-    // col_i += f_i * col_p on the pivot's support; lanes split into 32/Wb row groups when Wb divides 32
-    const int groups = (Wb <= 32 && (32 % Wb) == 0) ? 32 / Wb : 1;
-    const int jstep = groups > 1 ? Wb : 32;
-    const int grp = groups > 1 ? lane / Wb : 0;
-    for (int j = groups > 1 ? lane % Wb : lane; j < Wb; j += jstep) {
+    cta_sync();
+    const int nr_a = (int)S.cnt[0], nr_b = (int)S.cnt[1];
+    const uint32_t sd_raw = S.cnt[2] % D;
+    const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
+    const uint32_t sd = (sd_raw * e * e) % D;
+    // col_i += f_i * col_p on the pivot's support.  Threads form row groups: 32/Wb per warp when Wb divides 32.
+    const int gpw = (Wb <= 32 && (32 % Wb) == 0) ? 32 / Wb : 1;
+    const int gtot = gpw * nw, gid = warp * gpw + (gpw > 1 ? lane / Wb : 0);
+    const int jstep = gpw > 1 ? Wb : 32;
+    for (int j = gpw > 1 ? lane % Wb : lane; j < Wb; j += jstep) {
       const uint2 fv = S.f[j];
       const E f{fv.x, fv.y};
       E dot{0u, 0u};
       if (f.l | f.h) {
-        for (int ri = grp; ri < nr_a; ri += groups) {
+        for (int ri = gid; ri < nr_a; ri += gtot) {
           const int r = S.ar[ri];
           const uint32_t c = S.xz[r], s = c & 3u, t = c >> 2;
           const XZ v = G.ld(r, j);
@@ -303,28 +339,38 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
           }
         }
       }
-      for (int off = Wb; off < 32 && groups > 1; off <<= 1) {
+      for (int off = Wb; off < 32 && gpw > 1; off <<= 1) {
         const E o{__shfl_xor_sync(FULL, dot.l, off), __shfl_xor_sync(FULL, dot.h, off)};
         dot = (D == 3) ? add3(dot, o) : E{dot.l ^ o.l, 0u};
       }
-      if (grp == 0 && (f.l | f.h)) {
-        // phase_i += f_i*ps + po*(f_i*dot_i + sd*f_i(f_i-1)/2*po)      (tableau_prime.py:310-312,317-319)
-        E ph = G.ldp(j);
-        if (D == 3) {
-          E t = add3(smul3(f, ps), mul3(dot, f));
-          t = add3(t, smul3(E{f.h, 0u}, sd));                             // f(f-1)/2 = [f == 2]
-          ph = add3(ph, t);
-        } else {
-          ph = add4(ph, E{(ps & 1u) ? f.l : 0u, (ps & 2u) ? f.l : 0u});
-          ph.h ^= dot.l & f.l;
-        }
-        G.stp(j, ph);
-      }
+      if (gpw == 1 || lane < Wb) S.dotw[warp * Wb + j] = make_uint2(dot.l, dot.h);
     }
-    __syncwarp();
+    cta_sync();
+    // phase_i += f_i*ps + po*(f_i*dot_i + sd*f_i(f_i-1)/2*po)      (tableau_prime.py:310-312,317-319)
+    for (int j = tid; j < Wb; j += nt) {
+      const uint2 fv = S.f[j];
+      const E f{fv.x, fv.y};
+      if ((f.l | f.h) == 0) continue;
+      E dot{0u, 0u};
+      for (int w = 0; w < nw; ++w) {
+        const uint2 o = S.dotw[w * Wb + j];
+        dot = (D == 3) ? add3(dot, E{o.x, o.y}) : E{dot.l ^ o.x, 0u};
+      }
+      E ph = G.ldp(j);
+      if (D == 3) {
+        E t = add3(smul3(f, ps), mul3(dot, f));
+        t = add3(t, smul3(E{f.h, 0u}, sd));                               // f(f-1)/2 = [f == 2]
+        ph = add3(ph, t);
+      } else {
+        ph = add4(ph, E{(ps & 1u) ? f.l : 0u, (ps & 2u) ? f.l : 0u});
+        ph.h ^= dot.l & f.l;
+      }
+      G.stp(j, ph);
+    }
+    cta_sync();
     // destabilizer p <- old pivot; stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333).
     // Only rows where something changes are touched: the support (list ar) and stale destabilizer rows (br).
-    for (int i = lane; i < nr_a; i += 32) {
+    for (int i = tid; i < nr_a; i += nt) {
       const int r = S.ar[i];
       const uint32_t c = S.xz[r];
       XZ s = G.ld(r, jp);
@@ -336,7 +382,7 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
       dd.z = setbit2(dd.z, bp, c >> 2);
       G.st(r, jd, dd);
     }
-    for (int i = lane; i < nr_b; i += 32) {
+    for (int i = tid; i < nr_b; i += nt) {
       const int r = S.br[i];
       XZ dd = G.ld(r, jd);
       dd.x = setbit2(dd.x, bp, 0u);
@@ -344,41 +390,45 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
       G.st(r, jd, dd);
     }
     outcome = draw;
-    if (lane == 0) G.setp(np + piv, ps);
-    if (lane == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
+    if (tid == 0) G.setp(np + piv, ps);
+    if (tid == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
     rec = outcome;
   } else {
     // ---- deterministic branch (tableau_prime.py:336-363) ----
-    // ordered list of the generators with factor f_i = destab X[q,i] != 0, straight from the plane words
-    uint32_t a1 = 0;
-    int total = 0;
-    for (int base = 0; base < np / 32; base += 32) {
-      const int j = base + lane;
-      E f{0u, 0u}, ph{0u, 0u};
-      if (j < np / 32) { f = G.ld(q, np / 32 + j).x; ph = G.ldp(j); }
-      uint32_t m = f.l | f.h;
-      const int cnt = __popc(m);
-      int off = cnt;                                                      // inclusive warp scan of the counts
-      for (int d2 = 1; d2 < 32; d2 <<= 1) {
-        const int o = __shfl_up_sync(FULL, off, d2);
-        if (lane >= d2) off += o;
+    // warp 0: ordered list of the generators with factor f_i = destab X[q,i] != 0, straight from the plane words
+    if (warp == 0) {
+      uint32_t a1 = 0;
+      int total = 0;
+      for (int base = 0; base < np / 32; base += 32) {
+        const int j = base + lane;
+        E f{0u, 0u}, ph{0u, 0u};
+        if (j < np / 32) { f = G.ld(q, np / 32 + j).x; ph = G.ldp(j); }
+        uint32_t m = f.l | f.h;
+        const int cnt = __popc(m);
+        int off = cnt;                                                    // inclusive warp scan of the counts
+        for (int d2 = 1; d2 < 32; d2 <<= 1) {
+          const int o = __shfl_up_sync(FULL, off, d2);
+          if (lane >= d2) off += o;
+        }
+        int pos = total + off - cnt;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t fv = bit2(f, b);
+          S.ar[pos] = (uint16_t)(32 * j + b);
+          S.xz[pos] = (uint8_t)fv;
+          a1 += fv * bit2(ph, b);
+          ++pos;
+        }
+        total += __shfl_sync(FULL, off, 31);
       }
-      int pos = total + off - cnt;
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t fv = bit2(f, b);
-        S.ar[pos] = (uint16_t)(32 * j + b);
-        S.xz[pos] = (uint8_t)fv;
-        a1 += fv * bit2(ph, b);
-        ++pos;
-      }
-      total += __shfl_sync(FULL, off, 31);
+      a1 = __reduce_add_sync(FULL, a1);
+      if (lane == 0) { S.cnt[3] = (uint32_t)total; S.cnt[2] = a1 % ORDER; }
     }
-    a1 = __reduce_add_sync(FULL, a1) % ORDER;
-    __syncwarp();
+    cta_sync();
+    const int total = (int)S.cnt[3];
     uint32_t part = 0;
-    for (int r = lane; r < n; r += 32) {
+    for (int r = tid; r < n; r += nt) {
       uint32_t az = 0, cross = 0, sdg = 0;
       for (int k = 0; k < total; ++k) {
         const int g = S.ar[k];
@@ -392,47 +442,54 @@ __device__ uint32_t p_measure(const Geo<D>& G, const KParams& p, PScratch& S, in
       }
       part += (cross + PO * sdg) % D;
     }
-    part = __reduce_add_sync(FULL, part) % D;
-    const uint32_t ap = (a1 + PO * part) % ORDER;
+    part = __reduce_add_sync(FULL, part);
+    if (lane == 0 && part) atomicAdd(&S.cnt[0], part);
+    cta_sync();
+    const uint32_t ap = (S.cnt[2] + PO * (S.cnt[0] % D)) % ORDER;
     outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);        // (-ap // po) % d  (tableau_prime.py:362)
     rec = outcome | SDIMB_REC_DET;
   }
-  if (lane == 0) p.records[shot_local * p.rec_stride + slot] = (uint8_t)rec;
-  __syncwarp();
+  if (tid == 0) p.records[shot_local * p.rec_stride + slot] = (uint8_t)rec;
+  cta_sync();
   return outcome;
 }
 
-// ---- the interpreter: one warp (= one CTA) per shot ---------------------------------------------------------
+// ---- the interpreter: one CTA per shot (1 warp, or SDIMB_SCHED_WARPS warps on a scheduled stream) --------------
 template <int D>
-__global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   Geo<D> G;
   G.n = p.n;
   G.np = (p.n + 31) / 32 * 32;
   G.Wb = 2 * G.np / 32;
   G.RS = Geo<D>::EW * (G.Wb + 1);
   G.tab = reinterpret_cast<uint32_t*>(smem);
-  const int tab_words = (p.n * G.RS + 2 * G.Wb + 3) & ~3;
+  G.pacc = G.phase_of(warp);
+  const int tab_words = (p.n * G.RS + nw * 2 * G.Wb + 3) & ~3;
   PScratch S;
   S.ops = reinterpret_cast<int4*>(G.tab + tab_words);
-  S.f = reinterpret_cast<uint2*>(S.ops + 32);
-  S.ar = reinterpret_cast<uint16_t*>(S.f + G.Wb);
+  S.f = reinterpret_cast<uint2*>(S.ops + 32 * nw);
+  S.dotw = S.f + G.Wb;
+  S.cnt = reinterpret_cast<uint32_t*>(S.dotw + nw * G.Wb);
+  S.ar = reinterpret_cast<uint16_t*>(S.cnt + 4);
   S.br = S.ar + G.np;
   S.xz = reinterpret_cast<uint8_t*>(S.br + G.np);
-  const int lane = threadIdx.x;
+  int4* my_ops = S.ops + 32 * warp;
 
   for (int64_t shot = blockIdx.x; shot < p.shots; shot += gridDim.x) {
     // ---- load: |0...0> or pack from the uint8 store ----
-    for (int i = lane; i < tab_words; i += 32) G.tab[i] = 0u;
-    __syncwarp();
+    for (int i = tid; i < tab_words; i += nt) G.tab[i] = 0u;
+    cta_sync();
     uint8_t* T8 = p.tab ? p.tab + shot * p.shot_bytes : nullptr;
+    G.pacc = G.phase_of(0);
     if (p.flags & SDIMB_FRESH) {
-      for (int q = lane; q < p.n; q += 32) {
+      for (int q = tid; q < p.n; q += nt) {
         G.setz(q, q, 1u);              // stabilizer q = Z_q
         G.setx(q, G.np + q, 1u);       // destabilizer q = X_q
       }
     } else {
-      for (int q = 0; q < p.n; ++q) {
+      for (int q = warp; q < p.n; q += nw) {
         const uint8_t* row8 = T8 + (int64_t)q * p.row_bytes;
         for (int j = lane; j < G.Wb; j += 32) {
           XZ v{E{0u, 0u}, E{0u, 0u}};
@@ -447,7 +504,7 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
           G.st(q, j, v);
         }
       }
-      for (int j = lane; j < G.Wb; j += 32) {
+      for (int j = tid; j < G.Wb; j += nt) {
         E ph{0u, 0u};
         for (int b = 0; b < 32; ++b) {
           const int ln = 32 * j + b;
@@ -459,26 +516,33 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
         G.stp(j, ph);
       }
     }
-    __syncwarp();
+    G.pacc = G.phase_of(warp);
+    cta_sync();
 
     for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
-      // fetch 32 ops, one per lane; the fetching lane resolves N1 events, so only live ops are dispatched
+      // each warp fetches the same 32 ops, one per lane, and keeps the ones it has to execute: collective ops
+      // (measurements, barriers) and its own share of the gates; the fetching lane resolves N1 events, so events
+      // that do not fire are never dispatched
       int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
       if (i0 + lane < p.n_ops) mine = __ldg(p.ops + i0 + lane);
-      bool live = mine.x != SDIMB_OP_I;
-      if (mine.x == SDIMB_OP_N1) {
+      const int owner = (mine.x >> SDIMB_OP_WARP_SHIFT) & 0xFF;
+      mine.x &= SDIMB_OP_MASK;
+      const bool collective = mine.x >= SDIMB_OP_M && mine.x != SDIMB_OP_N1;      // M, M_X, RESET, BARRIER
+      bool live = mine.x != SDIMB_OP_I && (collective || nw == 1 || owner == warp);
+      if (live && mine.x == SDIMB_OP_N1) {
         mine.z = (int)p_noise_event<D>(p, mine.w, shot);
         live = mine.z != 0;
       }
+      if (mine.x == SDIMB_OP_BARRIER && nw == 1) live = false;
       uint32_t todo = __ballot_sync(0xFFFFFFFFu, live);
       __syncwarp();
-      S.ops[lane] = mine;
+      my_ops[lane] = mine;
       __syncwarp();
 #pragma unroll 1
       while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        const int4 op = S.ops[k];
+        const int4 op = my_ops[k];
         switch (op.x) {
           case SDIMB_OP_X: g_pauli<D>(G, op.y, 1u, 0u); break;
           case SDIMB_OP_X_INV: g_pauli<D>(G, op.y, D - 1u, 0u); break;
@@ -494,22 +558,37 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
           case SDIMB_OP_CZ_INV: g_cz<D>(G, op.y, op.z, true); break;
           case SDIMB_OP_SWAP: g_swap<D>(G, op.y, op.z); break;
           case SDIMB_OP_M_X:
-            g_h<D>(G, op.y, true);
+            cta_sync();
+            if (warp == 0) g_h<D>(G, op.y, true);
             // fallthrough
           case SDIMB_OP_M:
           case SDIMB_OP_RESET: {
             const uint32_t m = p_measure<D>(G, p, S, op.y, op.w, shot);
-            if (op.x == SDIMB_OP_RESET && m) g_pauli<D>(G, op.y, D - m, 0u);
+            if (op.x == SDIMB_OP_RESET) {
+              if (m && warp == 0) g_pauli<D>(G, op.y, D - m, 0u);      // program.py:335-339
+              cta_sync();
+            }
             break;
           }
           case SDIMB_OP_N1: g_pauli<D>(G, op.y, (uint32_t)op.z & 0xFFu, (uint32_t)op.z >> 8); break;
+          case SDIMB_OP_BARRIER: cta_sync(); break;
           default: break;
         }
       }
     }
-    __syncwarp();
-    if (p.flags & SDIMB_WRITEBACK) {      // unpack into the uint8 store
-      for (int q = 0; q < p.n; ++q) {
+    cta_sync();
+    if (p.flags & SDIMB_WRITEBACK) {      // fold the accumulators, then unpack into the uint8 store
+      G.pacc = G.phase_of(0);
+      for (int j = tid; j < G.Wb && nw > 1; j += nt) {
+        E acc = G.ldp(j);
+        for (int w = 1; w < nw; ++w) {
+          const uint2 o = G.phase_of(w)[j];
+          acc = (D == 3) ? add3(acc, E{o.x, o.y}) : add4(acc, E{o.x, o.y});
+        }
+        G.stp(j, acc);
+      }
+      cta_sync();
+      for (int q = warp; q < p.n; q += nw) {
         uint8_t* row8 = T8 + (int64_t)q * p.row_bytes;
         for (int ln = lane; ln < p.W; ln += 32) {
           const int half = ln >= p.np, g = half ? ln - p.np : ln;
@@ -518,20 +597,21 @@ __global__ void __launch_bounds__(32) interp_planes_kernel(const __grid_constant
           row8[p.W + ln] = live ? (uint8_t)G.getz(q, half * G.np + g) : 0;
         }
       }
-      for (int ln = lane; ln < p.W; ln += 32) {
+      for (int ln = tid; ln < p.W; ln += nt) {
         const int half = ln >= p.np, g = half ? ln - p.np : ln;
         T8[p.phase_off + ln] = (g < p.n) ? (uint8_t)G.getp(half * G.np + g) : 0;
       }
+      G.pacc = G.phase_of(warp);
     }
-    __syncwarp();
+    cta_sync();
   }
 }
 
-inline size_t planes_smem_bytes(int n, int d) {
+inline size_t planes_smem_bytes(int n, int d, int nw = SDIMB_SCHED_WARPS) {
   const size_t EW = (d == 2) ? 2 : 4;
   const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32, RS = EW * (Wb + 1);
-  const size_t tab_words = ((size_t)n * RS + 2 * Wb + 3) & ~(size_t)3;
-  return 4 * tab_words + 32 * 16 + 8 * Wb + 2 * np + 2 * np + np + 16;
+  const size_t tab_words = ((size_t)n * RS + (size_t)nw * 2 * Wb + 3) & ~(size_t)3;
+  return 4 * tab_words + (size_t)nw * 32 * 16 + 8 * Wb + (size_t)nw * 8 * Wb + 16 + 2 * np + 2 * np + np + 16;
 }
 
 }  // namespace planes

@@ -14,9 +14,11 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -574,7 +576,8 @@ __global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_consta
       if (threadIdx.x < 32) {
         int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
         if (i0 + threadIdx.x < p.n_ops) mine = __ldg(p.ops + i0 + threadIdx.x);
-        bool live = mine.x != SDIMB_OP_I;
+        mine.x &= SDIMB_OP_MASK;             // a scheduled stream carries a warp id here; lanes need no schedule
+        bool live = mine.x != SDIMB_OP_I && mine.x != SDIMB_OP_BARRIER;
         if (mine.x == SDIMB_OP_N1) {
           mine.z = (int)noise_event(p, mine.w, shot);
           live = mine.z != 0;
@@ -793,15 +796,23 @@ int sdimb_run(const SdimbRunArgs* a) {
   if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
   if (use_planes) {
-    const size_t smem = planes::planes_smem_bytes(a->n, a->d);
     auto kern = (a->d == 2) ? planes::interp_planes_kernel<2> : planes::interp_planes_kernel<3>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    // one warp per shot unless shared memory leaves the SM short of warps and the stream is scheduled
+    int nw = 1;
+    size_t smem = planes::planes_smem_bytes(a->n, a->d, 1);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess)
       return SDIMB_ECUDA;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1)
       return SDIMB_ECUDA;
+    if ((a->flags & SDIMB_SCHEDULED) && per_sm < 12) {
+      nw = SDIMB_SCHED_WARPS;
+      smem = planes::planes_smem_bytes(a->n, a->d, nw);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * nw, smem) != cudaSuccess || per_sm < 1)
+        return SDIMB_ECUDA;
+    }
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > a->shots) grid = a->shots;
-    kern<<<(unsigned)grid, 32, smem, (cudaStream_t)a->stream>>>(p);
+    kern<<<(unsigned)grid, 32 * nw, smem, (cudaStream_t)a->stream>>>(p);
     g_launches++;
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
   }
@@ -861,19 +872,30 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const int kernel = plan_kernel(n, d, mode_flags, L.np);
   if (kernel < 0) return kernel;
   const bool resident = kernel >= 1;
+  std::vector<int32_t> sched;
+  const int32_t* up_ops = ops;
+  int64_t up_n = n_ops;
+  uint32_t sched_flag = 0;
+  if (kernel == 2 && n_ops > 0) {          // bit-plane interpreter: upload the layered stream
+    sched.resize((size_t)(2 * n_ops + 1) * 4);
+    rc = sdimb_schedule(n, ops, n_ops, sched.data(), 2 * n_ops + 1, &up_n);
+    if (rc) return rc;
+    up_ops = sched.data();
+    sched_flag = SDIMB_SCHEDULED;
+  }
   rc = SDIMB_ECUDA;
   do {
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) break;
     if (cudaEventRecord(e0, st) != cudaSuccess) break;
-    if (n_ops && cudaMalloc(&d_ops, (size_t)n_ops * 16) != cudaSuccess) break;
+    if (up_n && cudaMalloc(&d_ops, (size_t)up_n * 16) != cudaSuccess) break;
     if (n_meas && cudaMalloc(&d_rec, (size_t)shots * n_meas) != cudaSuccess) break;
     if (replay_meas && n_meas && cudaMalloc(&d_rm, (size_t)shots * n_meas) != cudaSuccess) break;
     if (replay_noise && n_noise && cudaMalloc(&d_rn, (size_t)shots * n_noise * 2) != cudaSuccess) break;
     if (n_noise && noise_thresh24 && cudaMalloc(&d_th, (size_t)n_noise * 4) != cudaSuccess) break;
     if (n_noise && noise_channel && cudaMalloc(&d_ch, (size_t)n_noise) != cudaSuccess) break;
     if (!resident && cudaMalloc(&d_tab, (size_t)shots * L.shot_bytes) != cudaSuccess) break;
-    if (d_ops && cudaMemcpyAsync(d_ops, ops, (size_t)n_ops * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (d_ops && cudaMemcpyAsync(d_ops, up_ops, (size_t)up_n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_rm && cudaMemcpyAsync(d_rm, replay_meas, (size_t)shots * n_meas, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_rn && cudaMemcpyAsync(d_rn, replay_noise, (size_t)shots * n_noise * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_th && cudaMemcpyAsync(d_th, noise_thresh24, (size_t)n_noise * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
@@ -881,10 +903,10 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     SdimbRunArgs a;
     std::memset(&a, 0, sizeof(a));
     a.struct_size = sizeof(a);
-    a.flags = mode_flags | SDIMB_FRESH;
+    a.flags = mode_flags | SDIMB_FRESH | sched_flag;
     a.n = n; a.d = d; a.shots = shots; a.shot_offset = shot_offset;
     a.tableau = d_tab;
-    a.ops = (const int32_t*)d_ops; a.n_ops = n_ops;
+    a.ops = (const int32_t*)d_ops; a.n_ops = up_n;
     a.records = (uint8_t*)d_rec; a.n_meas = n_meas; a.rec_stride = n_meas;
     a.replay_meas = (const uint8_t*)d_rm; a.replay_noise = (const uint8_t*)d_rn;
     a.noise_thresh24 = (const uint32_t*)d_th; a.noise_channel = (const uint8_t*)d_ch; a.n_noise = n_noise;
@@ -907,6 +929,62 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
 }
 
 int64_t sdimb_launch_count(void) { return g_launches.load(); }
+
+int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap, int64_t* out_n) {
+  if (n < 1 || n_ops < 0 || (n_ops > 0 && !ops) || !out || !out_n || out_cap < 2 * n_ops + 1) return SDIMB_EINVAL;
+  // lw[q]: first layer in which row q may be read again (last writer + 1); lr[q]: first layer in which row q
+  // may be written again (last reader or writer + 1).  Layers restart after every collective op.
+  std::vector<int> lw(n, 0), lr(n, 0);
+  std::vector<std::vector<int64_t>> layers;
+  int64_t w = 0;
+  auto flush = [&]() {
+    for (auto& layer : layers) {
+      if (layer.empty()) continue;
+      int k = 0;
+      for (int64_t i : layer) {
+        const int32_t* o = ops + 4 * i;
+        int32_t* r = out + 4 * w++;
+        r[0] = o[0] | ((k++ % SDIMB_SCHED_WARPS) << SDIMB_OP_WARP_SHIFT);
+        r[1] = o[1]; r[2] = o[2]; r[3] = o[3];
+      }
+      int32_t* b = out + 4 * w++;
+      b[0] = SDIMB_OP_BARRIER; b[1] = 0; b[2] = -1; b[3] = -1;
+    }
+    layers.clear();
+    std::fill(lw.begin(), lw.end(), 0);
+    std::fill(lr.begin(), lr.end(), 0);
+  };
+  for (int64_t i = 0; i < n_ops; ++i) {
+    const int32_t* o = ops + 4 * i;
+    const int op = o[0] & SDIMB_OP_MASK, a = o[1], b = o[2];
+    if (op < 0 || op > SDIMB_OP_BARRIER || a < 0 || a >= n) return SDIMB_EOP;
+    if (op == SDIMB_OP_I || op == SDIMB_OP_BARRIER) continue;
+    if (op >= SDIMB_OP_M && op <= SDIMB_OP_RESET) {     // collective: everything before it completes first
+      flush();
+      int32_t* r = out + 4 * w++;
+      r[0] = op; r[1] = a; r[2] = -1; r[3] = o[3];
+      continue;
+    }
+    const bool two = op >= SDIMB_OP_CNOT && op <= SDIMB_OP_SWAP;
+    if (two && (b < 0 || b >= n || b == a)) return SDIMB_EOP;
+    const bool reads_only = (op >= SDIMB_OP_X && op <= SDIMB_OP_Z_INV) || op == SDIMB_OP_N1;
+    int level;
+    if (reads_only) {
+      level = lw[a];
+      lr[a] = std::max(lr[a], level + 1);
+    } else {
+      level = std::max(lw[a], lr[a]);
+      if (two) level = std::max(level, std::max(lw[b], lr[b]));
+      lw[a] = lr[a] = level + 1;
+      if (two) lw[b] = lr[b] = level + 1;
+    }
+    if ((size_t)level >= layers.size()) layers.resize(level + 1);
+    layers[level].push_back(i);
+  }
+  flush();
+  *out_n = w;
+  return SDIMB_OK;
+}
 
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau) {
   SdimbLayout L;

@@ -46,6 +46,8 @@ class TableauEngine:
         self.lib = N.lib()
         dev = self.device
         self.ops = torch.from_numpy(np.ascontiguousarray(prog.ops)).to(dev)
+        # layered stream for the multi-warp bit-plane interpreter (same ops, commuting reorder + barriers)
+        self.ops_sched = torch.from_numpy(N.schedule(prog.num_qudits, prog.ops)).to(dev) if prog.n_ops else None
         self.noise_thresh = torch.from_numpy(prog.noise_thresh24.astype(np.int64)).to(dev).to(torch.int32) \
             if prog.n_noise else None
         if prog.n_noise:
@@ -88,8 +90,11 @@ class TableauEngine:
         op_range     (lo, hi) slice of the op stream, for host-stepped execution
         """
         prog, L, dev = self.prog, self.layout, self.device
-        _, need_tab = self.plan(mode, fresh, keep_tableau)
+        kernel, need_tab = self.plan(mode, fresh, keep_tableau)
         flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
+        use_sched = kernel == "planes-resident" and op_range is None and self.ops_sched is not None
+        if use_sched:
+            flags |= N.SCHEDULED
         with torch.cuda.device(dev):
             if need_tab:
                 if tableau is None:
@@ -113,8 +118,11 @@ class TableauEngine:
             a.n, a.d = prog.num_qudits, prog.dimension
             a.shots, a.shot_offset = shots, shot_offset
             a.tableau = _ptr(tableau) if need_tab else None
-            a.ops = (self.ops.data_ptr() + 16 * lo) if hi > lo else None
-            a.n_ops = hi - lo
+            if use_sched:
+                a.ops, a.n_ops = self.ops_sched.data_ptr(), self.ops_sched.shape[0]
+            else:
+                a.ops = (self.ops.data_ptr() + 16 * lo) if hi > lo else None
+                a.n_ops = hi - lo
             a.records = _ptr(records)
             a.n_meas = prog.n_meas
             a.rec_stride = records.stride(0) if prog.n_meas else 0
