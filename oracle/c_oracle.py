@@ -27,7 +27,12 @@ def _load():
 
 
 def threads() -> int:
-    return int(_load().oracle_max_threads())
+    """Host threads the baseline uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    which must not shrink the CPU baseline, so the count is passed to OpenMP explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def _p(a):
@@ -49,7 +54,8 @@ def run(n, d, ops, shots, shot_offset=0, seed=0, replay_meas=None, replay_noise=
         raise ValueError("noise events need replay_noise or (thresh24, channel)")
     final = np.zeros(4 * n * n + 2 * n, dtype=np.int64) if want_final else None
     rc = _load().oracle_run(n, d, shots, shot_offset, _p(ops), ops.shape[0], _p(rec), n_meas, _p(rm), _p(rn),
-                            _p(th), _p(ch), n_noise, seed & 0xFFFFFFFFFFFFFFFF, _p(final), _p(meas_nnz), nthreads)
+                            _p(th), _p(ch), n_noise, seed & 0xFFFFFFFFFFFFFFFF, _p(final), _p(meas_nnz),
+                            nthreads if nthreads > 0 else threads())
     if rc != 0:
         raise RuntimeError(f"oracle_run failed ({rc})")
     out = None

@@ -1,0 +1,58 @@
+"""Turn gpurun_out/<round>_* captures into the committed summaries under profiles/ (run on the CPU box)."""
+import csv, json, os, shutil, subprocess, sys
+R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+os.makedirs(P, exist_ok=True)
+
+def run(*cmd):
+    return subprocess.run(cmd, capture_output=True, text=True).stdout
+
+# 1. launch list: keep our kernels + a per-kernel share table
+rows = [r for r in csv.reader(open(os.path.join(G, f"{R}_launches.csv"), errors="ignore")) if len(r) > 14 and r[0].isdigit()]
+total = sum(float(r[14]) for r in rows)
+with open(os.path.join(P, f"{R}_launches.csv"), "w") as fh:
+    fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 3 --shots 16384 --no-cpu\n")
+    fh.write("id,kernel,block,grid,duration_ns,share_of_all_launches\n")
+    for r in rows:
+        name = r[4].split("(")[0][-60:]
+        fh.write(f"{r[0]},{name},{r[7]},{r[8]},{r[14]},{float(r[14]) / total:.4f}\n")
+
+# 2. full captures -> text summaries + traffic.json
+want = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "gpu__time_duration.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+traffic = {}
+for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096)):
+    rep = os.path.join(G, f"{R}_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    raw = list(csv.reader(run("ncu", "-i", rep, "--page", "raw", "--csv").splitlines()))
+    hdr, units, vals = raw[0], raw[1], raw[2]
+    m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    lines = run(sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "25")
+    with open(os.path.join(P, f"{R}_ncu_{tag}.txt"), "w") as fh:
+        fh.write(f"# ncu --set full --clock-control none --import-source on, one launch of the headline workload, {shots} shots\n")
+        fh.write(f"kernel: {m.get('Kernel Name', ('?',))[0]}\n")
+        for k in want:
+            if k in m:
+                fh.write(f"{k:68s} {m[k][0]} {m[k][1]}\n")
+        fh.write("\n# hottest source lines (share of stall samples, share of executed warp instructions)\n" + lines)
+    def to_bytes(key):
+        v, u = m[key]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        return float(v) * scale
+    traffic[tag] = {"shots": shots, "dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+                    "duration_ms": float(m["gpu__time_duration.sum"][0])}
+if "headline_planes" in traffic:
+    t = dict(traffic["headline_planes"]); t["all"] = traffic
+    json.dump(t, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+for name in (f"{R}_sanitizer.txt", f"{R}_bench_n1.json", f"{R}_bench_reference.json", f"{R}_bench_n2.json"):
+    src = os.path.join(G, name)
+    if os.path.exists(src):
+        shutil.copy(src, os.path.join(P, name))
+print(os.listdir(P))
