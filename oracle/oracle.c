@@ -140,14 +140,19 @@ static int measure(Tab* t, int q, int draw, int* det, int* nnz) {
     /* _det_measurement (:336-363), restructured row-wise: running ancilla_z per qudit row */
     int64_t ap = 0, cross = 0, sdg = 0;
     const int32_t* f = t->dx + (size_t)q * n;
-    for (int i = 0; i < n; ++i) { ap += (int64_t)f[i] * t->p[i]; *nnz += (f[i] != 0); }
+    int na = 0; /* generators with a non-zero factor, in increasing order (the reference skips the others, :351) */
+    for (int i = 0; i < n; ++i) {
+      if (!f[i]) continue;
+      ap += (int64_t)f[i] * t->p[i];
+      t->xs[na++] = i;
+    }
+    *nnz += na;
     for (int r = 0; r < n; ++r) {
       const int32_t* xr = t->x + (size_t)r * n;
       const int32_t* zr = t->z + (size_t)r * n;
       int64_t az = 0;
-      for (int i = 0; i < n; ++i) {
-        const int fi = f[i];
-        if (!fi) continue;
+      for (int k = 0; k < na; ++k) {
+        const int i = t->xs[k], fi = f[i];
         cross += az * (fi * xr[i]) % d;
         az = (az + fi * zr[i]) % d;
         sdg += (int64_t)xr[i] * zr[i] * (fi * (fi - 1) / 2) % d;

@@ -232,7 +232,8 @@ __device__ __forceinline__ uint32_t p_noise_event(const KParams& p, int64_t j, i
 
 // ---- measurement (whole CTA: 1 or SDIMB_SCHED_WARPS warps) -----------------------------------------------------
 template <int D>
-__device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local) {
+__device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local,
+                              bool fold) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO;
   const int n = G.n, np = G.np, Wb = G.Wb;
@@ -242,7 +243,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
   // fold the per-warp phase accumulators into accumulator 0; reset the list counters
   G.pacc = G.phase_of(0);
   if (tid < 4) S.cnt[tid] = 0;
-  for (int j = tid; j < Wb && nw > 1; j += nt) {
+  for (int j = tid; j < Wb && nw > 1 && fold; j += nt) {
     E acc = G.ldp(j);
     for (int w = 1; w < nw; ++w) {
       uint2* pw = G.phase_of(w) + j;
@@ -262,16 +263,6 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     if (m) { best = 32u * j + (__ffs(m) - 1); break; }
   }
   const uint32_t piv = __reduce_min_sync(FULL, best);
-
-  uint32_t draw;
-  if (p.replay_meas) {
-    draw = p.replay_meas[shot_local * p.n_meas + slot];
-  } else {
-    const uint64_t gshot = (uint64_t)(p.shot_offset + shot_local);
-    const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)slot, 0u, (uint32_t)p.seed,
-                               (uint32_t)(p.seed >> 32));
-    draw = __umulhi(r.x, (uint32_t)D);
-  }
 
   uint32_t outcome, rec;
   if (piv != kNoPivot) {
@@ -294,15 +285,11 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       }
       const bool act = (xr | zr) != 0, stale = !act && od != 0;
       const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, stale);
-      uint32_t ba = 0, bb = 0;
-      if (lane == 0) {
-        if (ma) ba = atomicAdd(&S.cnt[0], (uint32_t)__popc(ma));
-        if (mb) bb = atomicAdd(&S.cnt[1], (uint32_t)__popc(mb));
-      }
-      ba = __shfl_sync(FULL, ba, 0);
-      bb = __shfl_sync(FULL, bb, 0);
-      if (act) S.ar[ba + __popc(ma & lt)] = (uint16_t)r;
-      if (stale) S.br[bb + __popc(mb & lt)] = (uint16_t)r;
+      uint32_t both = 0;                                 // list lengths packed: support | stale << 16
+      if (lane == 0 && (ma | mb)) both = atomicAdd(&S.cnt[0], (uint32_t)__popc(ma) | ((uint32_t)__popc(mb) << 16));
+      both = __shfl_sync(FULL, both, 0);
+      if (act) S.ar[(both & 0xFFFFu) + __popc(ma & lt)] = (uint16_t)r;
+      if (stale) S.br[(both >> 16) + __popc(mb & lt)] = (uint16_t)r;
     }
     sd_part = __reduce_add_sync(FULL, sd_part);
     if (lane == 0 && sd_part) atomicAdd(&S.cnt[2], sd_part);
@@ -313,7 +300,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       S.f[j] = (D == 3) ? make_uint2(x.h, x.l) : make_uint2(x.l, 0u);
     }
     cta_sync();
-    const int nr_a = (int)S.cnt[0], nr_b = (int)S.cnt[1];
+    const int nr_a = (int)(S.cnt[0] & 0xFFFFu), nr_b = (int)(S.cnt[0] >> 16);
     const uint32_t sd_raw = S.cnt[2] % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
@@ -389,7 +376,15 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       dd.z = setbit2(dd.z, bp, 0u);
       G.st(r, jd, dd);
     }
-    outcome = draw;
+    // outcome of a random measurement: replayed draw or Philox (reference: random.choice, tableau_prime.py:332)
+    if (p.replay_meas) {
+      outcome = p.replay_meas[shot_local * p.n_meas + slot];
+    } else {
+      const uint64_t gshot = (uint64_t)(p.shot_offset + shot_local);
+      const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)slot, 0u, (uint32_t)p.seed,
+                                 (uint32_t)(p.seed >> 32));
+      outcome = __umulhi(r.x, (uint32_t)D);
+    }
     if (tid == 0) G.setp(np + piv, ps);
     if (tid == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
     rec = outcome;
@@ -518,6 +513,7 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
     }
     G.pacc = G.phase_of(warp);
     cta_sync();
+    bool dirty = false;                    // some gate may have added to a private phase accumulator since the last fold
 
     for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
       // each warp fetches the same 32 ops, one per lane, and keeps the ones it has to execute: collective ops
@@ -535,6 +531,8 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
       }
       if (mine.x == SDIMB_OP_BARRIER && nw == 1) live = false;
       uint32_t todo = __ballot_sync(0xFFFFFFFFu, live);
+      // positions of ops (executed by ANY warp) that may touch a phase accumulator: identical in every warp
+      const uint32_t gate_pos = __ballot_sync(0xFFFFFFFFu, mine.x != SDIMB_OP_I && !collective);
       __syncwarp();
       my_ops[lane] = mine;
       __syncwarp();
@@ -563,7 +561,9 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
             // fallthrough
           case SDIMB_OP_M:
           case SDIMB_OP_RESET: {
-            const uint32_t m = p_measure<D>(G, p, S, op.y, op.w, shot);
+            const bool fold = dirty || (gate_pos & ((1u << k) - 1u)) != 0;   // gates since the last measurement?
+            const uint32_t m = p_measure<D>(G, p, S, op.y, op.w, shot, fold);
+            dirty = false;
             if (op.x == SDIMB_OP_RESET) {
               if (m && warp == 0) g_pauli<D>(G, op.y, D - m, 0u);      // program.py:335-339
               cta_sync();
@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
           default: break;
         }
       }
+      dirty = dirty || gate_pos != 0;      // conservative: gates of this batch behind its last measurement
     }
     cta_sync();
     if (p.flags & SDIMB_WRITEBACK) {      // fold the accumulators, then unpack into the uint8 store
