@@ -281,7 +281,8 @@ def bench_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
     e2e_value = world * e2e_shots * gates / e2e_t
-    h2d = prog.ops.nbytes + prog.noise_thresh24.nbytes + prog.noise_channel.nbytes
+    up_rows = N.schedule(prog.num_qudits, prog.ops).shape[0] if kernel_name.startswith("planes") else prog.n_ops
+    h2d = up_rows * 16 + prog.noise_thresh24.nbytes + prog.noise_channel.nbytes      # what the call uploads
     d2h = e2e_shots * prog.n_meas
 
     # the device-buffer path and the host-buffer path must agree bit for bit (same Philox counters)
@@ -314,6 +315,40 @@ def bench_ours(args):
         if tj.get("shots"):
             traffic = tj["dram_bytes_per_launch"] * (shots / tj["shots"])
 
+    # ---- BASELINE.json's second metric: gate-update HBM GB/s vs peak.  The gates of the same circuit (no noise,
+    # no measurement) streamed over one uint8 tableau per shot in HBM by the lane interpreter ("global" mode):
+    # every gate reads/writes its dense rows, SURVEY 8d bytes, no residency.  N = 1 only.
+    gate_update = None
+    if world == 1 and not args.no_gate_update:
+        from sdim_b200 import generate_random_clifford_circuit
+        from sdim_b200.ir import compile_circuits
+        w = WORKLOAD
+        gprog = compile_circuits([generate_random_clifford_circuit(w["n"], w["gates"], w["d"], 0, w["circuit_seed"])])
+        geng = TableauEngine(gprog, dev)
+        gshots = 8192
+        gtab = geng.alloc_tableau(gshots)
+        geng.init_tableau(gtab)
+        grec = torch.empty((gshots, 0), dtype=torch.uint8, device=dev)
+        gtimes = []
+        for it in range(3 + 3):
+            flush_l2()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            geng.run(gshots, 0, seed, mode="global", tableau=gtab, fresh=False, keep_tableau=True, records=grec)
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+            if it >= 3:
+                gtimes.append(g0.elapsed_time(g1))
+        gbytes = algorithmic_bytes_per_shot(gprog, [], None) * gshots
+        gms = float(np.mean(gtimes))
+        gate_update = {"kernel": "interp_kernel (uint8 lanes, one tableau per shot in HBM, mode=global)",
+                       "workload": f"{gprog.n_ops} gates of the headline circuit, {gshots} shots, "
+                                   f"{gshots * L.shot_bytes / 2**30:.2f} GiB store, tableaus evolve across launches",
+                       "achieved": gbytes / (gms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": gbytes / (gms * 1e-3) / 1e9 / peak, "launch_ms": gms,
+                       "shot_gates_per_sec": gshots * gprog.n_ops / (gms * 1e-3)}
+        del gtab
+
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -344,6 +379,7 @@ def bench_ours(args):
                      "accounting": "SURVEY 8d per-op bytes; measurements count only generators with non-zero factor "
                                    "(the reference's own skip rule), see DESIGN.md section 4",
                      "achieved_dense": alg_bytes_dense / launch_s / 1e9},
+        "gate_update_hbm": gate_update,
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
     }
@@ -362,6 +398,7 @@ def main():
     ap.add_argument("--cpu-shots", type=int, default=0, help="shots in the CPU baseline sample (0 = calibrate)")
     ap.add_argument("--mode", default=None, choices=[None, "auto", "global", "resident", "lanes", "planes"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gate-update", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

@@ -15,7 +15,8 @@
  *   - device entry points are asynchronous on `stream` (a cudaStream_t passed as void*,
  *     NULL = legacy default stream) and never synchronise; pointers marked [device]
  *     are plain CUDA device addresses owned by the caller (PyTorch in this repo)
- *   - no global mutable state: calls on distinct (stream, buffer) sets may run concurrently
+ *   - the device entry points keep no global mutable state: calls on distinct (stream, buffer) sets may run
+ *     concurrently.  Only sdimb_simulate_host owns state (its reusable workspace) and serialises its callers
  *   - there is NO CPU fallback: without a CUDA device every launch returns SDIMB_ECUDA
  *
  * Tableau store (one tableau per shot; replaces the six int64 arrays of
@@ -129,16 +130,20 @@ int sdimb_run(const SdimbRunArgs* args);
 int sdimb_export(const void* tableau, int n, int d, int64_t shot,
                  int64_t* x, int64_t* z, int64_t* p, int64_t* dx, int64_t* dz, int64_t* dp, void* stream);
 
-/* Same job as sdimb_run with HOST buffers only: allocates device scratch, copies the op stream and
- * noise tables in, simulates from |0...0>, copies the records out and synchronises.  This is the call
- * a non-PyTorch host (e.g. the reference itself through ctypes) makes; `elapsed_ms` (nullable)
- * receives the device time of the whole call measured with CUDA events. */
+/* Same job as sdimb_run with HOST buffers only: schedules the op stream (sdimb_schedule), copies it and the noise
+ * tables in, simulates from |0...0>, copies the records out through pinned staging and synchronises.  Device
+ * scratch, the staging buffer, the stream and the events live in a grow-only workspace that later calls reuse
+ * (calls are serialised internally; sdimb_release_workspace frees it).  This is the call a non-PyTorch host
+ * (e.g. the reference itself through ctypes) makes; `elapsed_ms` (nullable) receives the device time of the
+ * whole call measured with CUDA events. */
 int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,
                         const int32_t* ops, int64_t n_ops,
                         uint8_t* records, int64_t n_meas,
                         const uint8_t* replay_meas, const uint8_t* replay_noise,
                         const uint32_t* noise_thresh24, const uint8_t* noise_channel, int64_t n_noise,
                         uint64_t seed, uint32_t flags, float* elapsed_ms);
+
+int sdimb_release_workspace(void);
 
 /* Host-side op-stream scheduler (no GPU work).  Reorders the gates between two collective ops (M, M_X, RESET)
  * into layers of ops on pairwise disjoint qudits (ASAP levels over row read/write dependencies), assigns the

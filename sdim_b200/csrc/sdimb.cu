@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -49,6 +50,20 @@ __device__ __forceinline__ uint32_t mod_d(const Arith& A, uint32_t x) { return x
 __device__ __forceinline__ uint32_t mod_o(const Arith& A, uint32_t x) { return x - A.order * __umulhi(x, A.mo); }
 __device__ __forceinline__ uint32_t neg_d(const Arith& A, uint32_t x) { return x ? A.d - x : 0u; }
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return (w >> (8 * k)) & 0xFFu; }
+
+// SWAR arithmetic on four packed uint8 lanes, every lane reduced mod m (m <= 127, so a + b < 256 per lane).
+// `rep` = m * 0x01010101, `bias` = (0x80 - m) * 0x01010101: adding the bias sets bit 7 of a lane iff lane >= m.
+struct Swar {
+  uint32_t m, rep, bias;
+};
+__device__ __forceinline__ Swar make_swar(uint32_t m) { return Swar{m, m * 0x01010101u, (0x80u - m) * 0x01010101u}; }
+__device__ __forceinline__ uint32_t swar_reduce(const Swar& S, uint32_t s) {      // lanes in [0, 2m) -> [0, m)
+  const uint32_t ge = ((s + S.bias) >> 7) & 0x01010101u;
+  return s - ge * S.m;
+}
+__device__ __forceinline__ uint32_t swar_add(const Swar& S, uint32_t a, uint32_t b) { return swar_reduce(S, a + b); }
+__device__ __forceinline__ uint32_t swar_neg(const Swar& S, uint32_t a) { return swar_reduce(S, S.rep - a); }
+__device__ __forceinline__ uint32_t swar_sub(const Swar& S, uint32_t a, uint32_t b) { return swar_reduce(S, a + S.rep - b); }
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10, counter = (shot_lo, shot_hi, slot, stream), key = seed.  Host mirror: sdim_b200/rng.py
@@ -138,133 +153,144 @@ __device__ void init_tableau(uint8_t* T, const KParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Unitary gates: every generator lane is independent, so threads sweep 4-lane words with no barrier.
+// Unitary gates: every generator lane is independent, so a thread owns its 4-lane words for the whole gate
+// sequence and consecutive gates need no barrier.  One gate on one word: `r` holds the X/Z words of row a (and
+// row b for two-qudit gates), already loaded — possibly prefetched while the previous gate was computing; the
+// new words are stored here, the new phase word is returned.  Words that cannot change are not rewritten.
 // Closed forms: SURVEY Appendix A-1/A-2 (restating tableau_optimized.py:5-118, tableau_gates.py:27-261,298-329).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gate_h(uint8_t* T, const KParams& p, int a, bool inverse) {
+struct Rows {
+  uint32_t xa, za, xb, zb;
+};
+
+__device__ __forceinline__ bool is_two_qudit(int op) { return op >= SDIMB_OP_CNOT && op <= SDIMB_OP_SWAP; }
+__device__ __forceinline__ bool is_unitary_like(int op) { return op < SDIMB_OP_M || op == SDIMB_OP_N1; }
+
+__device__ __forceinline__ Rows load_rows(const uint8_t* T, const KParams& p, int op, int a, int b, int w) {
+  const int wz = p.W / 4;
+  const uint32_t* rowa = reinterpret_cast<const uint32_t*>(T + (int64_t)a * p.row_bytes);
+  Rows r;
+  r.xa = rowa[w];
+  r.za = rowa[wz + w];
+  r.xb = r.zb = 0u;
+  if (is_two_qudit(op)) {
+    const uint32_t* rowb = reinterpret_cast<const uint32_t*>(T + (int64_t)b * p.row_bytes);
+    r.xb = rowb[w];
+    r.zb = rowb[wz + w];
+  }
+  return r;
+}
+
+// pa, pb: Pauli exponents for X/X_INV/Z/Z_INV/N1 (phase += po*(pb*x - pa*z)), unused otherwise.
+// Additions, subtractions and negations run on all four lanes of a word at once (Swar); only the lane-by-lane
+// products of the phase terms are computed per byte.
+__device__ __forceinline__ uint32_t gate_word(uint8_t* T, const KParams& p, int op, int a, int b, uint32_t pa,
+                                              uint32_t pb, const Rows r, int w, uint32_t ph) {
   const Arith& A = p.A;
-  uint32_t* xa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
-  uint32_t* za = xa + p.W / 4;
-  uint32_t* P = reinterpret_cast<uint32_t*>(T + p.phase_off);
-  for (int w = threadIdx.x; w < p.W / 4; w += blockDim.x) {
-    const uint32_t x = xa[w], z = za[w];
-    if ((x | z) == 0) continue;
-    const uint32_t ph = P[w];
-    uint32_t nx = 0, nz = 0, nph = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t xb = byte_of(x, k), zb = byte_of(z, k);
+  const Swar Sd = make_swar(A.d), So = make_swar(A.order);
+  const int wz = p.W / 4;
+  uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
+  uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
+  switch (op) {
+    case SDIMB_OP_H:
+    case SDIMB_OP_H_INV: {
+      if ((r.xa | r.za) == 0) return ph;
       // phase += po * new_x * new_z == -po * x * z        (tableau_optimized.py:17-30,45-58)
-      uint32_t pb = byte_of(ph, k) + A.order - A.po * mod_d(A, xb * zb);
-      pb = pb >= A.order ? pb - A.order : pb;
-      const uint32_t nxb = inverse ? zb : neg_d(A, zb);   // H: (x,z) <- (-z,x);  H^-1: (x,z) <- (z,-x)
-      const uint32_t nzb = inverse ? neg_d(A, xb) : xb;
-      nx |= nxb << (8 * k); nz |= nzb << (8 * k); nph |= pb << (8 * k);
-    }
-    xa[w] = nx; za[w] = nz; P[w] = nph;
-  }
-}
-
-__device__ __forceinline__ void gate_p(uint8_t* T, const KParams& p, int a, bool inverse) {
-  const Arith& A = p.A;
-  const uint32_t* xa = reinterpret_cast<const uint32_t*>(T + (int64_t)a * p.row_bytes);
-  uint32_t* za = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes) + p.W / 4;
-  uint32_t* P = reinterpret_cast<uint32_t*>(T + p.phase_off);
-  for (int w = threadIdx.x; w < p.W / 4; w += blockDim.x) {
-    const uint32_t x = xa[w];
-    if (x == 0) continue;
-    const uint32_t z = za[w], ph = P[w];
-    uint32_t nz = 0, nph = 0;
+      uint32_t prod = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t xb = byte_of(x, k), zb = byte_of(z, k);
+      for (int k = 0; k < 4; ++k) prod |= (A.po * mod_d(A, byte_of(r.xa, k) * byte_of(r.za, k))) << (8 * k);
+      if (op == SDIMB_OP_H) { rowa[w] = swar_neg(Sd, r.za); rowa[wz + w] = r.xa; }     // (x,z) <- (-z, x)
+      else { rowa[w] = r.za; rowa[wz + w] = swar_neg(Sd, r.xa); }                      // (x,z) <- (z, -x)
+      return swar_sub(So, ph, prod);
+    }
+    case SDIMB_OP_P:
+    case SDIMB_OP_P_INV: {
+      if (r.xa == 0) return ph;
       // even d: phase +-= x^2 (mod 2d); odd d: phase +-= x(x-1)/2 (mod d)   (tableau_optimized.py:62-96)
-      const uint32_t inc = (A.po == 2) ? mod_o(A, xb * xb) : mod_d(A, (xb * (xb - 1u)) >> 1);
-      const uint32_t pb = mod_o(A, byte_of(ph, k) + (inverse ? A.order - inc : inc));
-      const uint32_t nzb = mod_d(A, zb + (inverse ? A.d - xb : xb));
-      nz |= nzb << (8 * k); nph |= pb << (8 * k);
-    }
-    za[w] = nz; P[w] = nph;
-  }
-}
-
-// Conjugation by the Pauli X^a Z^b on qudit q: phase += po * (b*x - a*z).  Covers X, X_INV, Z, Z_INV,
-// N1 noise and the RESET correction (tableau_gates.py:27-137, program.py:335-339).
-__device__ __forceinline__ void gate_pauli(uint8_t* T, const KParams& p, int q, uint32_t a, uint32_t b) {
-  const Arith& A = p.A;
-  const uint32_t* xq = reinterpret_cast<const uint32_t*>(T + (int64_t)q * p.row_bytes);
-  const uint32_t* zq = xq + p.W / 4;
-  uint32_t* P = reinterpret_cast<uint32_t*>(T + p.phase_off);
-  const uint32_t na = a ? A.d - a : 0u;
-  for (int w = threadIdx.x; w < p.W / 4; w += blockDim.x) {
-    const uint32_t x = b ? xq[w] : 0u, z = na ? zq[w] : 0u;
-    if ((x | z) == 0) continue;
-    const uint32_t ph = P[w];
-    uint32_t nph = 0;
+      uint32_t inc = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t t = mod_d(A, b * byte_of(x, k) + na * byte_of(z, k));
-      nph |= mod_o(A, byte_of(ph, k) + A.po * t) << (8 * k);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t xb = byte_of(r.xa, k);
+        inc |= ((A.po == 2) ? mod_o(A, xb * xb) : mod_d(A, (xb * (xb - 1u)) >> 1)) << (8 * k);
+      }
+      if (op == SDIMB_OP_P) { rowa[wz + w] = swar_add(Sd, r.za, r.xa); return swar_add(So, ph, inc); }
+      rowa[wz + w] = swar_sub(Sd, r.za, r.xa);
+      return swar_sub(So, ph, inc);
     }
-    P[w] = nph;
-  }
-}
-
-__device__ __forceinline__ void gate_cnot(uint8_t* T, const KParams& p, int a, int b, bool inverse) {
-  const Arith& A = p.A;
-  uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
-  uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
-  const int wz = p.W / 4;
-  for (int w = threadIdx.x; w < wz; w += blockDim.x) {
-    const uint32_t xa = rowa[w], zb = rowb[wz + w];
-    if ((xa | zb) == 0) continue;
-    const uint32_t xb = rowb[w], za = rowa[wz + w];
-    uint32_t nxb = 0, nza = 0;
+    case SDIMB_OP_X: case SDIMB_OP_X_INV: case SDIMB_OP_Z: case SDIMB_OP_Z_INV: case SDIMB_OP_N1: {
+      // conjugation by X^pa Z^pb: phase += po * (pb*x - pa*z)  (tableau_gates.py:27-137, program.py:335-339)
+      const uint32_t na = pa ? A.d - pa : 0u;
+      const uint32_t x = pb ? r.xa : 0u, z = na ? r.za : 0u;
+      if ((x | z) == 0) return ph;
+      const bool unit_x = pb == 0u || pb == 1u || pb == A.d - 1u, unit_z = pa == 0u || pa == 1u || pa == A.d - 1u;
+      if (unit_x && unit_z) {                                 // exponents +-1: no products, all four lanes at once
+        const uint32_t sx = A.po == 2 ? x << 1 : x, sz = A.po == 2 ? z << 1 : z;
+        uint32_t q = ph;
+        if (pb) q = (pb == 1u) ? swar_add(So, q, sx) : swar_sub(So, q, sx);
+        if (pa) q = (pa == 1u) ? swar_sub(So, q, sz) : swar_add(So, q, sz);
+        return q;
+      }
+      uint32_t t = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // x[t] +-= x[c];  z[c] -+= z[t]        (tableau_optimized.py:99-118, (d-1)*z == -z)
-      const uint32_t xak = byte_of(xa, k), zbk = byte_of(zb, k);
-      nxb |= mod_d(A, byte_of(xb, k) + (inverse ? neg_d(A, xak) : xak)) << (8 * k);
-      nza |= mod_d(A, byte_of(za, k) + (inverse ? zbk : neg_d(A, zbk))) << (8 * k);
+      for (int k = 0; k < 4; ++k) t |= mod_d(A, pb * byte_of(x, k) + na * byte_of(z, k)) << (8 * k);
+      return swar_add(So, ph, A.po == 2 ? t << 1 : t);
     }
-    rowb[w] = nxb; rowa[wz + w] = nza;
-  }
-}
-
-__device__ __forceinline__ void gate_cz(uint8_t* T, const KParams& p, int a, int b, bool inverse) {
-  const Arith& A = p.A;
-  uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
-  uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
-  uint32_t* P = reinterpret_cast<uint32_t*>(T + p.phase_off);
-  const int wz = p.W / 4;
-  for (int w = threadIdx.x; w < wz; w += blockDim.x) {
-    const uint32_t xa = rowa[w], xb = rowb[w];
-    if ((xa | xb) == 0) continue;
-    const uint32_t za = rowa[wz + w], zb = rowb[wz + w], ph = P[w];
-    uint32_t nza = 0, nzb = 0, nph = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    case SDIMB_OP_CNOT: {                                     // x[t] += x[c];  z[c] -= z[t]   (tableau_optimized.py:99-107)
+      if ((r.xa | r.zb) == 0) return ph;
+      rowb[w] = swar_add(Sd, r.xb, r.xa);
+      rowa[wz + w] = swar_sub(Sd, r.za, r.zb);
+      return ph;
+    }
+    case SDIMB_OP_CNOT_INV: {                                 // x[t] -= x[c];  z[c] += z[t]   (tableau_optimized.py:110-118)
+      if ((r.xa | r.zb) == 0) return ph;
+      rowb[w] = swar_sub(Sd, r.xb, r.xa);
+      rowa[wz + w] = swar_add(Sd, r.za, r.zb);
+      return ph;
+    }
+    case SDIMB_OP_CZ:
+    case SDIMB_OP_CZ_INV: {
+      if ((r.xa | r.xb) == 0) return ph;
       // CZ = H^-1(t) CNOT(c,t) H(t) folded: z[a] +-= x[b]; z[b] +-= x[a]; phase +-= po*x[a]*x[b]
-      const uint32_t xak = byte_of(xa, k), xbk = byte_of(xb, k);
-      const uint32_t prod = A.po * mod_d(A, xak * xbk);
-      nph |= mod_o(A, byte_of(ph, k) + (inverse ? A.order - prod : prod)) << (8 * k);
-      nza |= mod_d(A, byte_of(za, k) + (inverse ? neg_d(A, xbk) : xbk)) << (8 * k);
-      nzb |= mod_d(A, byte_of(zb, k) + (inverse ? neg_d(A, xak) : xak)) << (8 * k);
+      uint32_t prod = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) prod |= (A.po * mod_d(A, byte_of(r.xa, k) * byte_of(r.xb, k))) << (8 * k);
+      if (op == SDIMB_OP_CZ) {
+        rowa[wz + w] = swar_add(Sd, r.za, r.xb); rowb[wz + w] = swar_add(Sd, r.zb, r.xa);
+        return swar_add(So, ph, prod);
+      }
+      rowa[wz + w] = swar_sub(Sd, r.za, r.xb); rowb[wz + w] = swar_sub(Sd, r.zb, r.xa);
+      return swar_sub(So, ph, prod);
     }
-    rowa[wz + w] = nza; rowb[wz + w] = nzb; P[w] = nph;
+    case SDIMB_OP_SWAP:
+      rowa[w] = r.xb; rowa[wz + w] = r.zb;
+      rowb[w] = r.xa; rowb[wz + w] = r.za;
+      return ph;
+    default:
+      return ph;
   }
 }
 
-__device__ __forceinline__ void gate_swap(uint8_t* T, const KParams& p, int a, int b) {
-  uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
-  uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
-  const int wz = p.W / 4;
-  // each thread swaps the X and Z words of the lanes it owns (lane ownership must hold across gates: there is
-  // no barrier between consecutive gates)
-  for (int w = threadIdx.x; w < wz; w += blockDim.x) {
-    const uint32_t tx = rowa[w], tz = rowa[wz + w];
-    rowa[w] = rowb[w]; rowa[wz + w] = rowb[wz + w];
-    rowb[w] = tx; rowb[wz + w] = tz;
+// Pauli exponents (a, b) of an op of the phase-only family
+__device__ __forceinline__ void pauli_exponents(const KParams& p, const int4& op, uint32_t& pa, uint32_t& pb) {
+  pa = pb = 0u;
+  switch (op.x) {
+    case SDIMB_OP_X: pa = 1u; break;
+    case SDIMB_OP_X_INV: pa = p.A.d - 1u; break;
+    case SDIMB_OP_Z: pb = 1u; break;
+    case SDIMB_OP_Z_INV: pb = p.A.d - 1u; break;
+    case SDIMB_OP_N1: pa = (uint32_t)op.z & 0xFFu; pb = (uint32_t)op.z >> 8; break;
+    default: break;
+  }
+}
+
+// A whole gate when rows span several words per thread (n > 4 * blockDim): plain loop, phases in memory.
+__device__ __forceinline__ void gate_rows(uint8_t* T, const KParams& p, const int4& op, uint32_t pa, uint32_t pb) {
+  uint32_t* P = reinterpret_cast<uint32_t*>(T + p.phase_off);
+  for (int w = threadIdx.x; w < p.W / 4; w += blockDim.x) {
+    const Rows r = load_rows(T, p, op.x, op.y, op.z, w);
+    const uint32_t ph = P[w];
+    const uint32_t nph = gate_word(T, p, op.x, op.y, op.z, pa, pb, r, w, ph);
+    if (nph != ph) P[w] = nph;
   }
 }
 
@@ -534,7 +560,7 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
 // ---------------------------------------------------------------------------------------------
 // The interpreter: one CTA per shot, grid-stride over shots.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kMaxThreads, 5) interp_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int64_t tab_smem = p.resident ? p.shot_bytes : 0;
   Scratch S;
@@ -570,6 +596,14 @@ __global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_consta
       __syncthreads();
     }
 
+    // When a row is at most one word per thread, the thread's phase word stays in a register between
+    // measurements (gates never read another lane's phase).
+    const int w0 = threadIdx.x;
+    const bool one_word = p.W / 4 <= (int)blockDim.x;
+    const bool own_word = one_word && w0 < p.W / 4;
+    uint32_t* Pw = reinterpret_cast<uint32_t*>(T + p.phase_off) + w0;
+    uint32_t pw = own_word ? *Pw : 0u;
+
     for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
       // warp 0 fetches 32 ops (one per lane) and resolves their N1 events; only live ops are dispatched
       __syncthreads();
@@ -593,34 +627,33 @@ __global__ void __launch_bounds__(kMaxThreads) interp_kernel(const __grid_consta
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
         const int4 op = S.ops[k];
-        switch (op.x) {
-          case SDIMB_OP_X: gate_pauli(T, p, op.y, 1u, 0u); break;
-          case SDIMB_OP_X_INV: gate_pauli(T, p, op.y, A.d - 1u, 0u); break;
-          case SDIMB_OP_Z: gate_pauli(T, p, op.y, 0u, 1u); break;
-          case SDIMB_OP_Z_INV: gate_pauli(T, p, op.y, 0u, A.d - 1u); break;
-          case SDIMB_OP_H: gate_h(T, p, op.y, false); break;
-          case SDIMB_OP_H_INV: gate_h(T, p, op.y, true); break;
-          case SDIMB_OP_P: gate_p(T, p, op.y, false); break;
-          case SDIMB_OP_P_INV: gate_p(T, p, op.y, true); break;
-          case SDIMB_OP_CNOT: gate_cnot(T, p, op.y, op.z, false); break;
-          case SDIMB_OP_CNOT_INV: gate_cnot(T, p, op.y, op.z, true); break;
-          case SDIMB_OP_CZ: gate_cz(T, p, op.y, op.z, false); break;
-          case SDIMB_OP_CZ_INV: gate_cz(T, p, op.y, op.z, true); break;
-          case SDIMB_OP_SWAP: gate_swap(T, p, op.y, op.z); break;
-          case SDIMB_OP_M_X:
-            gate_h(T, p, op.y, true);                          // tableau_gates.py:292-296: H^-1 then measure
-            // fallthrough
-          case SDIMB_OP_M:
-          case SDIMB_OP_RESET: {
-            const uint32_t m = measure(T, p, S, op.y, op.w, shot);
-            if (op.x == SDIMB_OP_RESET && m) gate_pauli(T, p, op.y, A.d - m, 0u);   // program.py:335-339
-            break;
+        if (is_unitary_like(op.x)) {
+          uint32_t pa, pb;
+          pauli_exponents(p, op, pa, pb);
+          if (!one_word) {
+            gate_rows(T, p, op, pa, pb);
+          } else if (own_word) {
+            pw = gate_word(T, p, op.x, op.y, op.z, pa, pb, load_rows(T, p, op.x, op.y, op.z, w0), w0, pw);
           }
-          case SDIMB_OP_N1: gate_pauli(T, p, op.y, (uint32_t)op.z & 0xFFu, (uint32_t)op.z >> 8); break;
-          default: break;   // rejected on the host before launch
+          continue;
+        }
+        // collective ops: M, M_X, RESET
+        if (op.x == SDIMB_OP_M_X) {                          // tableau_gates.py:292-296: H^-1 then measure
+          const int4 h = make_int4(SDIMB_OP_H_INV, op.y, -1, -1);
+          if (!one_word) gate_rows(T, p, h, 0u, 0u);
+          else if (own_word) pw = gate_word(T, p, h.x, h.y, h.z, 0u, 0u, load_rows(T, p, h.x, h.y, h.z, w0), w0, pw);
+        }
+        if (own_word) *Pw = pw;                              // measurement reads and writes phases in memory
+        const uint32_t m = measure(T, p, S, op.y, op.w, shot);
+        if (own_word) pw = *Pw;
+        if (op.x == SDIMB_OP_RESET && m) {                   // program.py:335-339: X applied (-m) mod d times
+          const int4 x = make_int4(SDIMB_OP_N1, op.y, (int)(A.d - m), -1);
+          if (!one_word) gate_rows(T, p, x, A.d - m, 0u);
+          else if (own_word) pw = gate_word(T, p, x.x, x.y, -1, A.d - m, 0u, load_rows(T, p, x.x, x.y, -1, w0), w0, pw);
         }
       }
     }
+    if (own_word) *Pw = pw;
     __syncthreads();
     if (p.resident && (p.flags & SDIMB_WRITEBACK)) {
       const uint4* src = reinterpret_cast<const uint4*>(T);
@@ -844,6 +877,59 @@ int sdimb_export(const void* tableau, int n, int d, int64_t shot, int64_t* x, in
   return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
 }
 
+// Workspace of the host-buffer entry: one grow-only device arena, one grow-only pinned staging buffer, a stream
+// and two events, created on first use and reused by later calls (cudaMalloc/cudaFree per call cost more than
+// the simulation of a small batch).  Calls are serialised by a mutex; sdimb_release_workspace() frees it.
+namespace {
+struct HostWorkspace {
+  std::mutex mu;
+  int device = -1;
+  void* dev = nullptr;
+  size_t dev_cap = 0;
+  void* pin = nullptr;
+  size_t pin_cap = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  void release() {
+    if (dev) cudaFree(dev);
+    if (pin) cudaFreeHost(pin);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (stream) cudaStreamDestroy(stream);
+    dev = pin = nullptr; dev_cap = pin_cap = 0; stream = nullptr; e0 = e1 = nullptr; device = -1;
+  }
+  bool prepare(size_t dev_bytes, size_t pin_bytes) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return false;
+    if (cur != device) { release(); device = cur; }
+    if (!stream && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (!e0 && cudaEventCreate(&e0) != cudaSuccess) return false;
+    if (!e1 && cudaEventCreate(&e1) != cudaSuccess) return false;
+    if (dev_bytes > dev_cap) {
+      if (dev) cudaFree(dev);
+      dev = nullptr; dev_cap = 0;
+      if (cudaMalloc(&dev, dev_bytes) != cudaSuccess) return false;
+      dev_cap = dev_bytes;
+    }
+    if (pin_bytes > pin_cap) {
+      if (pin) cudaFreeHost(pin);
+      pin = nullptr; pin_cap = 0;
+      if (cudaHostAlloc(&pin, pin_bytes, cudaHostAllocDefault) != cudaSuccess) return false;
+      pin_cap = pin_bytes;
+    }
+    return true;
+  }
+};
+HostWorkspace g_ws;
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+int sdimb_release_workspace(void) {
+  std::lock_guard<std::mutex> lock(g_ws.mu);
+  g_ws.release();
+  return SDIMB_OK;
+}
+
 int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const int32_t* ops, int64_t n_ops,
                         uint8_t* records, int64_t n_meas, const uint8_t* replay_meas, const uint8_t* replay_noise,
                         const uint32_t* noise_thresh24, const uint8_t* noise_channel, int64_t n_noise, uint64_t seed,
@@ -862,16 +948,12 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     if (meas && (o[3] < 0 || o[3] >= n_meas)) return SDIMB_EOP;
     if (o[0] == SDIMB_OP_N1 && (o[3] < 0 || o[3] >= n_noise)) return SDIMB_EOP;
   }
+  if (n_noise > 0 && !replay_noise && (!noise_thresh24 || !noise_channel)) return SDIMB_EINVAL;
   if (shots == 0) return SDIMB_OK;
 
-  cudaStream_t st = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  void *d_ops = nullptr, *d_rec = nullptr, *d_rm = nullptr, *d_rn = nullptr, *d_th = nullptr, *d_ch = nullptr,
-       *d_tab = nullptr;
   const uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES | SDIMB_FORCE_PLANES);
   const int kernel = plan_kernel(n, d, mode_flags, L.np);
   if (kernel < 0) return kernel;
-  const bool resident = kernel >= 1;
   std::vector<int32_t> sched;
   const int32_t* up_ops = ops;
   int64_t up_n = n_ops;
@@ -883,19 +965,31 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     up_ops = sched.data();
     sched_flag = SDIMB_SCHEDULED;
   }
+
+  // carve the device arena
+  const size_t b_ops = align256((size_t)up_n * 16), b_rec = align256((size_t)shots * n_meas);
+  const size_t b_rm = replay_meas ? b_rec : 0;
+  const size_t b_rn = replay_noise ? align256((size_t)shots * n_noise * 2) : 0;
+  const size_t b_th = (n_noise && noise_thresh24) ? align256((size_t)n_noise * 4) : 0;
+  const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
+  const size_t b_tab = kernel == 0 ? align256((size_t)shots * L.shot_bytes) : 0;
+  const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + 256;
+
+  std::lock_guard<std::mutex> lock(g_ws.mu);
+  if (!g_ws.prepare(total, b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
+  cudaStream_t st = g_ws.stream;
+  uint8_t* base = (uint8_t*)g_ws.dev;
+  uint8_t* d_ops = base; base += b_ops;
+  uint8_t* d_rec = base; base += b_rec;
+  uint8_t* d_rm = b_rm ? base : nullptr; base += b_rm;
+  uint8_t* d_rn = b_rn ? base : nullptr; base += b_rn;
+  uint8_t* d_th = b_th ? base : nullptr; base += b_th;
+  uint8_t* d_ch = b_ch ? base : nullptr; base += b_ch;
+  uint8_t* d_tab = b_tab ? base : nullptr;
   rc = SDIMB_ECUDA;
   do {
-    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
-    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) break;
-    if (cudaEventRecord(e0, st) != cudaSuccess) break;
-    if (up_n && cudaMalloc(&d_ops, (size_t)up_n * 16) != cudaSuccess) break;
-    if (n_meas && cudaMalloc(&d_rec, (size_t)shots * n_meas) != cudaSuccess) break;
-    if (replay_meas && n_meas && cudaMalloc(&d_rm, (size_t)shots * n_meas) != cudaSuccess) break;
-    if (replay_noise && n_noise && cudaMalloc(&d_rn, (size_t)shots * n_noise * 2) != cudaSuccess) break;
-    if (n_noise && noise_thresh24 && cudaMalloc(&d_th, (size_t)n_noise * 4) != cudaSuccess) break;
-    if (n_noise && noise_channel && cudaMalloc(&d_ch, (size_t)n_noise) != cudaSuccess) break;
-    if (!resident && cudaMalloc(&d_tab, (size_t)shots * L.shot_bytes) != cudaSuccess) break;
-    if (d_ops && cudaMemcpyAsync(d_ops, up_ops, (size_t)up_n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (cudaEventRecord(g_ws.e0, st) != cudaSuccess) break;
+    if (up_n && cudaMemcpyAsync(d_ops, up_ops, (size_t)up_n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_rm && cudaMemcpyAsync(d_rm, replay_meas, (size_t)shots * n_meas, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_rn && cudaMemcpyAsync(d_rn, replay_noise, (size_t)shots * n_noise * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_th && cudaMemcpyAsync(d_th, noise_thresh24, (size_t)n_noise * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
@@ -907,23 +1001,21 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     a.n = n; a.d = d; a.shots = shots; a.shot_offset = shot_offset;
     a.tableau = d_tab;
     a.ops = (const int32_t*)d_ops; a.n_ops = up_n;
-    a.records = (uint8_t*)d_rec; a.n_meas = n_meas; a.rec_stride = n_meas;
-    a.replay_meas = (const uint8_t*)d_rm; a.replay_noise = (const uint8_t*)d_rn;
-    a.noise_thresh24 = (const uint32_t*)d_th; a.noise_channel = (const uint8_t*)d_ch; a.n_noise = n_noise;
+    a.records = d_rec; a.n_meas = n_meas; a.rec_stride = n_meas;
+    a.replay_meas = d_rm; a.replay_noise = d_rn;
+    a.noise_thresh24 = (const uint32_t*)d_th; a.noise_channel = d_ch; a.n_noise = n_noise;
     a.seed = seed; a.stream = st;
     rc = sdimb_run(&a);
     if (rc) break;
     rc = SDIMB_ECUDA;
-    if (d_rec && cudaMemcpyAsync(records, d_rec, (size_t)shots * n_meas, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-    if (cudaEventRecord(e1, st) != cudaSuccess) break;
+    const size_t rec_bytes = (size_t)shots * n_meas;
+    if (rec_bytes && cudaMemcpyAsync(g_ws.pin, d_rec, rec_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+    if (cudaEventRecord(g_ws.e1, st) != cudaSuccess) break;
     if (cudaStreamSynchronize(st) != cudaSuccess) break;
-    if (elapsed_ms && cudaEventElapsedTime(elapsed_ms, e0, e1) != cudaSuccess) break;
+    if (rec_bytes) std::memcpy(records, g_ws.pin, rec_bytes);
+    if (elapsed_ms && cudaEventElapsedTime(elapsed_ms, g_ws.e0, g_ws.e1) != cudaSuccess) break;
     rc = SDIMB_OK;
   } while (0);
-  cudaFree(d_ops); cudaFree(d_rec); cudaFree(d_rm); cudaFree(d_rn); cudaFree(d_th); cudaFree(d_ch); cudaFree(d_tab);
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
-  if (st) cudaStreamDestroy(st);
   if (rc == SDIMB_ECUDA) cudaGetLastError();
   return rc;
 }
