@@ -110,7 +110,8 @@ struct PScratch {
   int4* ops;         // [NW][32] staged op batch, private to each warp
   uint2* f;          // [Wb] factor planes f = -X[q,i]
   uint2* dotw;       // [NW][Wb] per-warp partial dot products
-  uint32_t* cnt;     // [4] list lengths / block accumulators
+  uint32_t* cnt;     // [2][4] list lengths / block accumulators, double-buffered by measurement parity
+  uint32_t parity;   // which half the current measurement uses (uniform across the CTA)
   uint16_t* ar;      // [np] active rows (pivot support) / active generators (det branch)
   uint16_t* br;      // [np] rows whose destabilizer-p entry must be cleared
   uint8_t* xz;       // [np] pivot column: xs | zs << 2   (det branch: factor of active generator k)
@@ -233,27 +234,35 @@ __device__ __forceinline__ uint32_t p_noise_event(const KParams& p, int64_t j, i
 // ---- measurement (whole CTA: 1 or SDIMB_SCHED_WARPS warps) -----------------------------------------------------
 template <int D>
 __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local,
-                              bool fold) {
+                              bool fold, uint32_t draw) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO;
   const int n = G.n, np = G.np, Wb = G.Wb;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  cta_sync();                                          // all gates of the previous layer are done
-  // fold the per-warp phase accumulators into accumulator 0; reset the list counters
+  // `fold` = some gate ran since the last measurement: wait for every warp's gates, then fold the per-warp phase
+  // accumulators into accumulator 0.  Back-to-back measurements skip both barriers (the previous measurement
+  // ended with one and already reset the list counters).
   G.pacc = G.phase_of(0);
-  if (tid < 4) S.cnt[tid] = 0;
-  for (int j = tid; j < Wb && nw > 1 && fold; j += nt) {
-    E acc = G.ldp(j);
-    for (int w = 1; w < nw; ++w) {
-      uint2* pw = G.phase_of(w) + j;
-      const E o{pw->x, pw->y};
-      acc = (D == 3) ? add3(acc, o) : add4(acc, o);
-      *pw = make_uint2(0u, 0u);
+  // counters: this measurement uses one half, and clears the other half for the next one (whose first barrier-free
+  // use is ordered behind this measurement's barriers)
+  uint32_t* const cnt = S.cnt + 4 * S.parity;
+  if (tid < 4) S.cnt[4 * (S.parity ^ 1u) + tid] = 0;
+  S.parity ^= 1u;
+  if (fold) {
+    cta_sync();
+    for (int j = tid; j < Wb && nw > 1; j += nt) {
+      E acc = G.ldp(j);
+      for (int w = 1; w < nw; ++w) {
+        uint2* pw = G.phase_of(w) + j;
+        const E o{pw->x, pw->y};
+        acc = (D == 3) ? add3(acc, o) : add4(acc, o);
+        *pw = make_uint2(0u, 0u);
+      }
+      G.stp(j, acc);
     }
-    G.stp(j, acc);
+    cta_sync();
   }
-  cta_sync();
 
   // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283); every warp looks itself
   uint32_t best = kNoPivot;
@@ -286,13 +295,13 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       const bool act = (xr | zr) != 0, stale = !act && od != 0;
       const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, stale);
       uint32_t both = 0;                                 // list lengths packed: support | stale << 16
-      if (lane == 0 && (ma | mb)) both = atomicAdd(&S.cnt[0], (uint32_t)__popc(ma) | ((uint32_t)__popc(mb) << 16));
+      if (lane == 0 && (ma | mb)) both = atomicAdd(&cnt[0], (uint32_t)__popc(ma) | ((uint32_t)__popc(mb) << 16));
       both = __shfl_sync(FULL, both, 0);
       if (act) S.ar[(both & 0xFFFFu) + __popc(ma & lt)] = (uint16_t)r;
       if (stale) S.br[(both >> 16) + __popc(mb & lt)] = (uint16_t)r;
     }
     sd_part = __reduce_add_sync(FULL, sd_part);
-    if (lane == 0 && sd_part) atomicAdd(&S.cnt[2], sd_part);
+    if (lane == 0 && sd_part) atomicAdd(&cnt[2], sd_part);
     // factors f = -X[q,i] for every lane but the pivot itself
     for (int j = tid; j < Wb; j += nt) {
       E x = G.ld(q, j).x;
@@ -300,8 +309,8 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       S.f[j] = (D == 3) ? make_uint2(x.h, x.l) : make_uint2(x.l, 0u);
     }
     cta_sync();
-    const int nr_a = (int)(S.cnt[0] & 0xFFFFu), nr_b = (int)(S.cnt[0] >> 16);
-    const uint32_t sd_raw = S.cnt[2] % D;
+    const int nr_a = (int)(cnt[0] & 0xFFFFu), nr_b = (int)(cnt[0] >> 16);
+    const uint32_t sd_raw = cnt[2] % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
     // col_i += f_i * col_p on the pivot's support.  Threads form row groups: 32/Wb per warp when Wb divides 32.
@@ -376,15 +385,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       dd.z = setbit2(dd.z, bp, 0u);
       G.st(r, jd, dd);
     }
-    // outcome of a random measurement: replayed draw or Philox (reference: random.choice, tableau_prime.py:332)
-    if (p.replay_meas) {
-      outcome = p.replay_meas[shot_local * p.n_meas + slot];
-    } else {
-      const uint64_t gshot = (uint64_t)(p.shot_offset + shot_local);
-      const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)slot, 0u, (uint32_t)p.seed,
-                                 (uint32_t)(p.seed >> 32));
-      outcome = __umulhi(r.x, (uint32_t)D);
-    }
+    outcome = draw;        // replayed or Philox, resolved when the op was fetched (reference: random.choice, :332)
     if (tid == 0) G.setp(np + piv, ps);
     if (tid == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
     rec = outcome;
@@ -418,10 +419,10 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
         total += __shfl_sync(FULL, off, 31);
       }
       a1 = __reduce_add_sync(FULL, a1);
-      if (lane == 0) { S.cnt[3] = (uint32_t)total; S.cnt[2] = a1 % ORDER; }
+      if (lane == 0) { cnt[3] = (uint32_t)total; cnt[2] = a1 % ORDER; }
     }
     cta_sync();
-    const int total = (int)S.cnt[3];
+    const int total = (int)cnt[3];
     uint32_t part = 0;
     for (int r = tid; r < n; r += nt) {
       uint32_t az = 0, cross = 0, sdg = 0;
@@ -438,9 +439,9 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       part += (cross + PO * sdg) % D;
     }
     part = __reduce_add_sync(FULL, part);
-    if (lane == 0 && part) atomicAdd(&S.cnt[0], part);
+    if (lane == 0 && part) atomicAdd(&cnt[0], part);
     cta_sync();
-    const uint32_t ap = (S.cnt[2] + PO * (S.cnt[0] % D)) % ORDER;
+    const uint32_t ap = (cnt[2] + PO * (cnt[0] % D)) % ORDER;
     outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);        // (-ap // po) % d  (tableau_prime.py:362)
     rec = outcome | SDIMB_REC_DET;
   }
@@ -467,7 +468,8 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   S.f = reinterpret_cast<uint2*>(S.ops + 32 * nw);
   S.dotw = S.f + G.Wb;
   S.cnt = reinterpret_cast<uint32_t*>(S.dotw + nw * G.Wb);
-  S.ar = reinterpret_cast<uint16_t*>(S.cnt + 4);
+  S.ar = reinterpret_cast<uint16_t*>(S.cnt + 8);
+  S.parity = 0;
   S.br = S.ar + G.np;
   S.xz = reinterpret_cast<uint8_t*>(S.br + G.np);
   int4* my_ops = S.ops + 32 * warp;
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   for (int64_t shot = blockIdx.x; shot < p.shots; shot += gridDim.x) {
     // ---- load: |0...0> or pack from the uint8 store ----
     for (int i = tid; i < tab_words; i += nt) G.tab[i] = 0u;
+    if (tid < 8) S.cnt[tid] = 0;
     cta_sync();
     uint8_t* T8 = p.tab ? p.tab + shot * p.shot_bytes : nullptr;
     G.pacc = G.phase_of(0);
@@ -529,6 +532,16 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
         mine.z = (int)p_noise_event<D>(p, mine.w, shot);
         live = mine.z != 0;
       }
+      if (collective && mine.x != SDIMB_OP_BARRIER) {       // outcome this measurement takes if it is random
+        if (p.replay_meas) {
+          mine.z = p.replay_meas[shot * p.n_meas + mine.w];
+        } else {
+          const uint64_t gshot = (uint64_t)(p.shot_offset + shot);
+          const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)mine.w, 0u, (uint32_t)p.seed,
+                                     (uint32_t)(p.seed >> 32));
+          mine.z = (int)__umulhi(r.x, (uint32_t)D);
+        }
+      }
       if (mine.x == SDIMB_OP_BARRIER && nw == 1) live = false;
       uint32_t todo = __ballot_sync(0xFFFFFFFFu, live);
       // positions of ops (executed by ANY warp) that may touch a phase accumulator: identical in every warp
@@ -558,11 +571,12 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
           case SDIMB_OP_M_X:
             cta_sync();
             if (warp == 0) g_h<D>(G, op.y, true);
+            dirty = true;                                                  // row q changed: the measurement must sync
             // fallthrough
           case SDIMB_OP_M:
           case SDIMB_OP_RESET: {
             const bool fold = dirty || (gate_pos & ((1u << k) - 1u)) != 0;   // gates since the last measurement?
-            const uint32_t m = p_measure<D>(G, p, S, op.y, op.w, shot, fold);
+            const uint32_t m = p_measure<D>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);
             dirty = false;
             if (op.x == SDIMB_OP_RESET) {
               if (m && warp == 0) g_pauli<D>(G, op.y, D - m, 0u);      // program.py:335-339
@@ -612,7 +626,7 @@ inline size_t planes_smem_bytes(int n, int d, int nw = SDIMB_SCHED_WARPS) {
   const size_t EW = (d == 2) ? 2 : 4;
   const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32, RS = EW * (Wb + 1);
   const size_t tab_words = ((size_t)n * RS + (size_t)nw * 2 * Wb + 3) & ~(size_t)3;
-  return 4 * tab_words + (size_t)nw * 32 * 16 + 8 * Wb + (size_t)nw * 8 * Wb + 16 + 2 * np + 2 * np + np + 16;
+  return 4 * tab_words + (size_t)nw * 32 * 16 + 8 * Wb + (size_t)nw * 8 * Wb + 32 + 2 * np + 2 * np + np + 16;
 }
 
 }  // namespace planes

@@ -334,7 +334,8 @@ __device__ __forceinline__ uint32_t noise_event(const KParams& p, int64_t j, int
 // ---------------------------------------------------------------------------------------------
 constexpr int kBatch = 4;
 
-__device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int64_t slot, int64_t shot_local) {
+__device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int64_t slot, int64_t shot_local,
+                            uint32_t draw) {
   const Arith& A = p.A;
   const int n = p.n, W = p.W, npad = p.np, nt = blockDim.x, tid = threadIdx.x;
   const int wz = W / 4;
@@ -353,17 +354,6 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
     }
   }
   const uint32_t piv = block_min(best, S.red);
-
-  // outcome used if the measurement is random: replayed draw or Philox (reference: random.choice, :332)
-  uint32_t draw;
-  if (p.replay_meas) {
-    draw = p.replay_meas[shot_local * p.n_meas + slot];
-  } else {
-    const uint64_t gshot = (uint64_t)(p.shot_offset + shot_local);
-    const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)slot, 0u, (uint32_t)p.seed,
-                               (uint32_t)(p.seed >> 32));
-    draw = __umulhi(r.x, A.d);
-  }
 
   uint32_t outcome, rec;
   if (piv != kNoPivot) {
@@ -615,6 +605,17 @@ __global__ void __launch_bounds__(kMaxThreads, 5) interp_kernel(const __grid_con
         if (mine.x == SDIMB_OP_N1) {
           mine.z = (int)noise_event(p, mine.w, shot);
           live = mine.z != 0;
+        } else if (mine.x >= SDIMB_OP_M && mine.x <= SDIMB_OP_RESET) {
+          // outcome this measurement takes if it is random: replayed draw or Philox (reference: random.choice,
+          // tableau_prime.py:332), resolved by the fetching lane so that it is off the measurement's critical path
+          if (p.replay_meas) {
+            mine.z = p.replay_meas[shot * p.n_meas + mine.w];
+          } else {
+            const uint64_t gshot = (uint64_t)(p.shot_offset + shot);
+            const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)mine.w, 0u,
+                                       (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+            mine.z = (int)__umulhi(r.x, A.d);
+          }
         }
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, live);
         S.ops[threadIdx.x] = mine;
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(kMaxThreads, 5) interp_kernel(const __grid_con
           else if (own_word) pw = gate_word(T, p, h.x, h.y, h.z, 0u, 0u, load_rows(T, p, h.x, h.y, h.z, w0), w0, pw);
         }
         if (own_word) *Pw = pw;                              // measurement reads and writes phases in memory
-        const uint32_t m = measure(T, p, S, op.y, op.w, shot);
+        const uint32_t m = measure(T, p, S, op.y, op.w, shot, (uint32_t)op.z);
         if (own_word) pw = *Pw;
         if (op.x == SDIMB_OP_RESET && m) {                   // program.py:335-339: X applied (-m) mod d times
           const int4 x = make_int4(SDIMB_OP_N1, op.y, (int)(A.d - m), -1);

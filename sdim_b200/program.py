@@ -148,9 +148,25 @@ class Program:
         engine = self._get_engine(compiled)
         rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
         rn = None if replay_noise is None else torch.as_tensor(np.asarray(replay_noise, dtype=np.uint8))
-        store = self._initial_store(engine, shots)
-        rec = engine.run(shots, shot_offset, seed, rm, rn, mode=mode, tableau=store, fresh=store is None)
-        out = rec.cpu().numpy()
+        # Shots run in waves sized to the device: a run that needs one HBM tableau per shot (uint8 lanes in global
+        # mode, or a user-supplied initial tableau) must fit next to the records; resident kernels take any count.
+        _, need_tab = engine.plan(mode, fresh=self.initial_tableau is None)
+        wave = shots
+        if need_tab and shots > 0:
+            free_bytes, _total = torch.cuda.mem_get_info(engine.device)
+            per_shot = engine.layout.shot_bytes + 3 * compiled.n_meas + 2 * compiled.n_noise
+            wave = max(1, min(shots, int(0.6 * free_bytes) // max(per_shot, 1)))
+        elif shots > 0:
+            wave = max(1, min(shots, (4 << 30) // max(compiled.n_meas, 1)))       # <= 4 GiB of records per launch
+        out = np.empty((shots, compiled.n_meas), dtype=np.uint8)
+        for lo in range(0, shots, max(wave, 1)):
+            hi = min(shots, lo + wave)
+            store = self._initial_store(engine, hi - lo)
+            rec = engine.run(hi - lo, shot_offset + lo, seed,
+                             None if rm is None else rm[lo:hi], None if rn is None else rn[lo:hi],
+                             mode=mode, tableau=store, fresh=store is None)
+            out[lo:hi] = rec.cpu().numpy()
+            del store, rec
 
         def last_shot_tableau(last=shots - 1):
             one = engine.alloc_tableau(1)
