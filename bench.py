@@ -325,7 +325,7 @@ def bench_ours(args):
         w = WORKLOAD
         gprog = compile_circuits([generate_random_clifford_circuit(w["n"], w["gates"], w["d"], 0, w["circuit_seed"])])
         geng = TableauEngine(gprog, dev)
-        gshots = 148 * 10 * 6        # six full waves of the lane kernel's grid (10 CTAs of 128 threads per SM)
+        gshots = 148 * 12 * 5        # five full waves of the lane kernel grid (12 CTAs of 128 threads per SM)
         gtab = geng.alloc_tableau(gshots)
         geng.init_tableau(gtab)
         grec = torch.empty((gshots, 0), dtype=torch.uint8, device=dev)

@@ -550,7 +550,7 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
 // ---------------------------------------------------------------------------------------------
 // The interpreter: one CTA per shot, grid-stride over shots.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxThreads, 5) interp_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int64_t tab_smem = p.resident ? p.shot_bytes : 0;
   Scratch S;
