@@ -145,6 +145,24 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,
 
 int sdimb_release_workspace(void);
 
+/* Pauli-frame sampler: the reference's default multi-shot mechanism, simulate_frame (sdim/program.py:45-165).
+ * Given the records of ONE reference tableau shot (`reference[k]`, packed record bytes, N1 ignored in that shot as
+ * in sdim/program.py:31,245-247), propagate one Pauli frame per extra shot through the op stream — x frame 0,
+ * z frame uniform (:63-64); H: (x,z)<-(-z,x); H^-1: (z,-x); P: z+=x; CNOT: x[t]+=x[c], z[c]-=z[t]; CZ: z[t]+=x[c],
+ * z[c]+=x[t]; SWAP; N1: (x,z)[q] += (a,b) (:82-120,159-162) — and record (reference + x[q]) mod d at M / M_X
+ * (:121-144), then redraw z[q].  RESET records the PHYSICAL outcome (reference + x[q]) mod d, clears x[q] and
+ * redraws z[q]; the reference records its own unchanged value there (:146-157), which is wrong under noise
+ * (SURVEY Appendix B-5).  `records` rows are the extra shots (global ids shot_offset + local), same packed format,
+ * deterministic flag copied from the reference shot as the reference does (:139).
+ * `frames` is scratch, 2 * n * frames_pitch bytes with frames_pitch = shots rounded up to 128 [device].
+ * Draws: Philox streams 1 (noise, as sdimb_run), 2 (initial z, slot = qudit), 3 (z redraw, slot = measurement),
+ * or the nullable replay arrays replay_z0 [shots][n], replay_zm [shots][n_meas], replay_noise [shots][n_noise][2]. */
+int sdimb_frames(int n, int d, int64_t shots, int64_t shot_offset, const int32_t* ops, int64_t n_ops,
+                 const uint8_t* reference, uint8_t* records, int64_t n_meas, int64_t rec_stride, uint8_t* frames,
+                 const uint8_t* replay_z0, const uint8_t* replay_zm, const uint8_t* replay_noise,
+                 const uint32_t* noise_thresh24, const uint8_t* noise_channel, int64_t n_noise, uint64_t seed,
+                 void* stream);
+
 /* Host-side op-stream scheduler (no GPU work).  Reorders the gates between two collective ops (M, M_X, RESET)
  * into layers of ops on pairwise disjoint qudits (ASAP levels over row read/write dependencies), assigns the
  * ops of a layer round-robin to SDIMB_SCHED_WARPS warps and separates layers with SDIMB_OP_BARRIER.  Ops on

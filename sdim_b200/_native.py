@@ -14,7 +14,7 @@ KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
-                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace")
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames")
 
 
 class SdimbLayout(C.Structure):
@@ -63,6 +63,9 @@ def lib() -> C.CDLL:
                                       C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_float)]
     L.sdimb_launch_count.restype = C.c_int64
     L.sdimb_schedule.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.sdimb_frames.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L

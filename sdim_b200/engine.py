@@ -139,6 +139,40 @@ class TableauEngine:
         self._keepalive = (replay_meas, replay_noise)   # until the stream has consumed them
         return records
 
+    def run_frames(self, shots: int, reference: torch.Tensor, shot_offset: int = 1, seed: int = 0,
+                   replay_z0: Optional[torch.Tensor] = None, replay_zm: Optional[torch.Tensor] = None,
+                   replay_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Pauli-frame sampler (sdimb_frames; reference: simulate_frame, sdim/program.py:45-165).
+
+        `reference` = packed records uint8[n_meas] of one reference tableau shot.  Returns uint8[shots, n_meas]
+        for the extra shots with global ids shot_offset .. shot_offset + shots - 1."""
+        prog, dev = self.prog, self.device
+        with torch.cuda.device(dev):
+            records = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device=dev)
+            pitch = (shots + 127) // 128 * 128
+            frames = torch.empty((2, prog.num_qudits, max(pitch, 1)), dtype=torch.uint8, device=dev)
+            reference = reference.to(device=dev, dtype=torch.uint8).contiguous()
+
+            def dev_u8(t, shape):
+                if t is None:
+                    return None
+                t = t.to(device=dev, dtype=torch.uint8).contiguous()
+                if tuple(t.shape) != shape:
+                    raise ValueError(f"replay array must have shape {shape}")
+                return t
+
+            z0 = dev_u8(replay_z0, (shots, prog.num_qudits))
+            zm = dev_u8(replay_zm, (shots, prog.n_meas))
+            rn = dev_u8(replay_noise, (shots, prog.n_noise, 2))
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            N.check(self.lib.sdimb_frames(prog.num_qudits, prog.dimension, shots, shot_offset, _ptr(self.ops),
+                                          prog.n_ops, _ptr(reference), _ptr(records), prog.n_meas,
+                                          records.stride(0) if prog.n_meas else 0, frames.data_ptr(),
+                                          _ptr(z0), _ptr(zm), _ptr(rn), _ptr(self.noise_thresh),
+                                          _ptr(self.noise_channel), prog.n_noise, seed & 0xFFFFFFFFFFFFFFFF, stream))
+            torch.cuda.current_stream(dev).synchronize()      # replay buffers and frames die with this scope
+        return records
+
     def export(self, tableau: torch.Tensor, shot: int) -> Dict[str, np.ndarray]:
         """Six int64 arrays of one shot in the reference orientation [qudit, generator]."""
         n, dev = self.prog.num_qudits, self.device

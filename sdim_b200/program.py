@@ -127,12 +127,20 @@ class Program:
     # ---- simulate -----------------------------------------------------------------------------------
     def simulate_records(self, shots: int = 1, *, seed: Optional[int] = None, shot_offset: int = 0,
                          replay_meas=None, replay_noise=None, mode: Optional[str] = None,
-                         distributed: bool = False) -> RecordTable:
-        """Run `shots` tableau shots on the GPU and return the packed records (no Python objects)."""
+                         distributed: bool = False, method: str = "tableau") -> RecordTable:
+        """Run `shots` shots on the GPU and return the packed records (no Python objects).
+
+        method="tableau" (default): one full stabilizer tableau per shot.
+        method="frame": the reference's default multi-shot shortcut (sdim/program.py:244-265) — shot 0 is one
+        noiseless reference tableau shot, shots 1.. are Pauli frames propagated on the GPU (sdimb_frames)."""
         compiled = self._compiled()
         if seed is None:
             seed = random.getrandbits(63)       # follows the user's random.seed(), like the reference's draws
-        if distributed:
+        if method not in ("tableau", "frame"):
+            raise ValueError("method must be 'tableau' or 'frame'")
+        if method == "frame":
+            rec = self._run_frames(compiled, shots, seed)
+        elif distributed:
             from .dist import simulate_sharded
             rec = simulate_sharded(self, compiled, shots, seed, mode=mode)
         else:
@@ -142,6 +150,20 @@ class Program:
                             seed=seed, shot_offset=shot_offset)
         self.last_records = table
         return table
+
+    def _run_frames(self, compiled, shots, seed) -> np.ndarray:
+        import torch
+        engine = self._get_engine(compiled)
+        # reference shot: N1 is the identity there (sdim/program.py:31,245-247)
+        quiet = torch.zeros((1, compiled.n_noise, 2), dtype=torch.uint8) if compiled.n_noise else None
+        store = self._initial_store(engine, 1)
+        ref = engine.run(1, 0, seed, None, quiet, tableau=store, fresh=store is None)
+        out = np.empty((shots, compiled.n_meas), dtype=np.uint8)
+        out[:1] = ref.cpu().numpy()
+        if shots > 1:
+            out[1:] = engine.run_frames(shots - 1, ref[0], 1, seed).cpu().numpy()
+        self._tableau_thunk = None
+        return out
 
     def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode) -> np.ndarray:
         import torch
@@ -183,11 +205,14 @@ class Program:
     def simulate(self, shots: int = 1, show_measurement: bool = False, record_tableau: bool = False,
                  force_tableau: bool = False, verbose: bool = False, show_gate: bool = False, exact: bool = False,
                  options: Optional[SimulationOptions] = None, *, seed: Optional[int] = None,
-                 replay_meas=None, replay_noise=None, mode: Optional[str] = None, distributed: bool = False):
+                 replay_meas=None, replay_noise=None, mode: Optional[str] = None, distributed: bool = False,
+                 method: str = "tableau"):
         """Same call as the reference's Program.simulate (sdim/program.py:206-267).
 
         Returns a flat list of MeasurementResult for shots == 1, else `[qudit][round][shot]`.
-        `force_tableau` is accepted and implied: all shots run on the tableau path.
+        By default every shot runs on the tableau path (what the reference does under `force_tableau=True`);
+        `method="frame"` selects the reference's default multi-shot mechanism instead (one reference tableau shot +
+        Pauli frames, sdim/program.py:244-265) unless `force_tableau` / `record_tableau` is set.
         `exact` only concerns composite dimensions and is ignored.
         """
         if options is None:
@@ -199,8 +224,10 @@ class Program:
             tables = self._simulate_stepped(compiled, options, seed, replay_meas, replay_noise, mode)
             values, det, snaps = tables
         else:
+            use_frames = method == "frame" and options.shots > 1 and not options.force_tableau
             table = self.simulate_records(options.shots, seed=seed, replay_meas=replay_meas,
-                                          replay_noise=replay_noise, mode=mode, distributed=distributed)
+                                          replay_noise=replay_noise, mode=mode, distributed=distributed,
+                                          method="frame" if use_frames else "tableau")
             values, det, snaps = table.values, table.deterministic, None
 
         # group as measurement_results[qudit][round][shot]                    (program.py:321-332)

@@ -23,6 +23,8 @@ import numpy as np
 
 STREAM_MEAS = 0
 STREAM_NOISE = 1
+STREAM_FRAME_Z0 = 2      # Pauli-frame sampler: initial z frame, slot = qudit            (sdim/program.py:64)
+STREAM_FRAME_ZM = 3      # Pauli-frame sampler: z redraw after measurement k, slot = k   (sdim/program.py:144,156)
 
 CHANNEL_D, CHANNEL_F, CHANNEL_P = 0, 1, 2
 CHANNEL_CODES = {"d": CHANNEL_D, "f": CHANNEL_F, "p": CHANNEL_P}
@@ -89,3 +91,19 @@ def noise_draws(seed: int, d: int, shot_ids, thresh24, channel) -> np.ndarray:
     b = np.where(channel == CHANNEL_D, r // np.uint64(d), np.where(channel == CHANNEL_P, e, 0))
     out = np.stack((np.where(fire, a, 0), np.where(fire, b, 0)), axis=-1)
     return out.astype(np.uint8)
+
+
+def frame_z0_draws(seed: int, d: int, shot_ids, n: int) -> np.ndarray:
+    """uint8[len(shot_ids), n]: initial z frame of every shot (frame sampler)."""
+    shot_ids = np.asarray(shot_ids, dtype=np.uint64).reshape(-1, 1)
+    slots = np.arange(n, dtype=np.uint64).reshape(1, -1)
+    w0 = _words(seed, shot_ids, slots, STREAM_FRAME_Z0)[0].astype(np.uint64)
+    return ((w0 * np.uint64(d)) >> _S32).astype(np.uint8)
+
+
+def frame_zm_draws(seed: int, d: int, shot_ids, n_meas: int) -> np.ndarray:
+    """uint8[len(shot_ids), n_meas]: z frame redrawn on the measured qudit after measurement k (frame sampler)."""
+    shot_ids = np.asarray(shot_ids, dtype=np.uint64).reshape(-1, 1)
+    slots = np.arange(n_meas, dtype=np.uint64).reshape(1, -1)
+    w0 = _words(seed, shot_ids, slots, STREAM_FRAME_ZM)[0].astype(np.uint64)
+    return ((w0 * np.uint64(d)) >> _S32).astype(np.uint8)

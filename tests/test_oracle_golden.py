@@ -117,3 +117,23 @@ def test_oracle_against_live_reference():
                 assert np.array_equal(arr, arrs[key])
             checked += 1
     assert checked >= 10
+
+
+def test_frame_oracle_matches_reference_simulate_frame():
+    """oracle/frame_oracle.py vs outputs of the unmodified reference simulate_frame (sdim/program.py:45-165),
+    its np.random draws replayed (oracle/make_golden_frames.py)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle.frame_oracle import simulate_frames
+    cases = json.load(open(os.path.join(GOLDEN_DIR, "frame_cases.json")))["cases"]
+    assert len(cases) >= 16 and {c["d"] for c in cases} >= {2, 3, 5, 7}
+    n_reset = 0
+    for c in cases:
+        shots = len(c["z0"])
+        noise = np.array(c["noise_ab"], dtype=np.int64).reshape(shots, -1, 2) if c["noise_ab"] else None
+        got = simulate_frames(c["n"], c["d"], c["ops"], c["reference"], c["z0"], np.array(c["zm"]), noise,
+                              reset_records="reference")
+        assert np.array_equal(got, np.array(c["records"])), c["seed"]
+        n_reset += sum(1 for o in c["ops"] if o[0] == 16)
+    assert n_reset > 20
