@@ -13,7 +13,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
-LIB_PATH = os.path.join(CSRC, "libsdimb.so")
+LIB_PATH = os.environ.get("SDIMB_LIB") or os.path.join(CSRC, "libsdimb.so")   # SDIMB_LIB: A/B a prebuilt variant
 SOURCES = ["sdimb.cu"]
 
 

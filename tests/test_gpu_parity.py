@@ -290,3 +290,23 @@ def test_config5_large_single_tableau():
         arrs = eng.export(eng.tableau, 1)
         for key in ("x", "z", "p", "dx", "dz", "dp"):
             assert np.array_equal(arrs[key], fin[key]), key
+
+
+def test_config2_full_size_ten_thousand_shots():
+    """BASELINE config 2 at its full size: random Clifford d = 3, n = 64, depth 2k + all-qudit measurement, 10^4 shots.
+    All 10^4 x 64 records bit-exact vs the C oracle (same Philox counters), plus the size-independent properties:
+    determinism flags do not depend on the shot, random outcomes are uniform (chi-square per record)."""
+    from oracle import c_oracle
+    from sdim_b200 import generate_random_clifford_circuit
+    from sdim_b200.ir import compile_circuits
+    prog = compile_circuits([generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1)])
+    shots = 10000
+    _, got = _run_gpu(prog, shots, 2026)
+    assert np.array_equal(got, c_oracle.run_philox(prog, shots, 0, 2026))
+    det = (got & 0x80) != 0
+    assert (det == det[0]).all()
+    vals = got & 0x7F
+    for k in np.nonzero(~det[0])[0]:
+        counts = np.bincount(vals[:, k], minlength=3)
+        chi2 = ((counts - shots / 3) ** 2 / (shots / 3)).sum()
+        assert chi2 < 30.0, (k, counts)          # 2 dof; 30 is far beyond any plausible fluctuation over 64 records
