@@ -269,7 +269,7 @@ def bench_ours(args):
     # ---- end to end through the host-buffer C ABI call -------------------------------------------
     e2e_shots = shots
     e2e_times = []
-    simulate_host(prog, min(e2e_shots, 256), lo, seed, mode=args.mode)       # warm
+    simulate_host(prog, e2e_shots, lo, seed, mode=args.mode)   # warm-up: sizes the library's reusable workspace
     for _ in range(max(1, min(args.steps, 3))):
         barrier()
         t0 = time.perf_counter()
@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shots", type=int, default=8192, help="shots per GPU per step")
+    ap.add_argument("--shots", type=int, default=16384, help="shots per GPU per step")
     ap.add_argument("--cpu-shots", type=int, default=0, help="shots in the CPU baseline sample (0 = calibrate)")
     ap.add_argument("--mode", default=None, choices=[None, "auto", "global", "resident", "lanes", "planes"])
     ap.add_argument("--no-cpu", action="store_true")
