@@ -106,6 +106,8 @@ typedef struct SdimbRunArgs {
   int64_t n_noise;
   uint64_t seed;
   void* stream;
+  void* scratch;                 /* [device] nullable, sdimb_scratch_bytes() bytes: shot counter of the bit-plane */
+  int64_t scratch_bytes;         /* interpreter (CTAs then claim shots dynamically instead of grid-striding)      */
 } SdimbRunArgs;
 
 int sdimb_version(void);
@@ -171,6 +173,10 @@ int sdimb_frames(int n, int d, int64_t shots, int64_t shot_offset, const int32_t
  * 2*n_ops + 1 rows; *out_n receives the number written.  Replaces nothing in the reference (its loop is strictly
  * sequential, sdim/program.py:311-312); SURVEY 8f rank 3. */
 int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap, int64_t* out_n);
+
+/* Scratch the bit-plane interpreter can use for (n, d, flags), 0 for the other interpreters.  With it, CTAs claim
+ * shots from an atomic counter (shots differ in cost when noise fires); without it they grid-stride. */
+int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags);
 
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store,
  * 1 uint8 lanes resident in shared memory, 2 bit-plane resident (d = 2, 3); *needs_tableau = whether

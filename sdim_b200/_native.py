@@ -14,7 +14,7 @@ KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
-                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames")
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes")
 
 
 class SdimbLayout(C.Structure):
@@ -29,7 +29,7 @@ class SdimbRunArgs(C.Structure):
                 ("ops", C.c_void_p), ("n_ops", C.c_int64), ("records", C.c_void_p), ("n_meas", C.c_int64),
                 ("rec_stride", C.c_int64), ("replay_meas", C.c_void_p), ("replay_noise", C.c_void_p),
                 ("noise_thresh24", C.c_void_p), ("noise_channel", C.c_void_p), ("n_noise", C.c_int64),
-                ("seed", C.c_uint64), ("stream", C.c_void_p)]
+                ("seed", C.c_uint64), ("stream", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
 
 
 class NativeError(RuntimeError):
@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     L.sdimb_frames.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]
+    L.sdimb_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_uint32]
+    L.sdimb_scratch_bytes.restype = C.c_int64
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L

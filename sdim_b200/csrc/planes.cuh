@@ -63,12 +63,13 @@ __device__ __forceinline__ E setbit2(E w, int b, uint32_t v) {
 template <int D>
 struct Geo {
   static constexpr int EW = (D == 2) ? 2 : 4;   // words per entry
-  uint32_t* tab;                                // shared-memory image
+  uint32_t* tab;                                // shared-memory image of the n rows
+  uint2* ph_base;                               // [NW][Wb] phase accumulators, always in shared memory
   uint2* pacc;                                  // phase accumulator used by ldp/stp (this warp's, or #0 in measure)
   int n, np, Wb, RS;                            // RS = row stride in words = EW * (Wb + 1)
   __device__ __forceinline__ uint32_t* entry(int q, int j) const { return tab + q * RS + j * EW; }
   __device__ __forceinline__ uint2* phase() const { return pacc; }
-  __device__ __forceinline__ uint2* phase_of(int w) const { return reinterpret_cast<uint2*>(tab + n * RS) + w * Wb; }
+  __device__ __forceinline__ uint2* phase_of(int w) const { return ph_base + w * Wb; }
   __device__ __forceinline__ XZ ld(int q, int j) const {
     if (D == 3) {
       const uint4 v = *reinterpret_cast<const uint4*>(entry(q, j));
@@ -115,6 +116,7 @@ struct PScratch {
   uint16_t* ar;      // [np] active rows (pivot support) / active generators (det branch)
   uint16_t* br;      // [np] rows whose destabilizer-p entry must be cleared
   uint8_t* xz;       // [np] pivot column: xs | zs << 2   (det branch: factor of active generator k)
+  int* next;         // [2] shot claimed from the global counter (double-buffered)
 };
 
 __device__ __forceinline__ void cta_sync() {
@@ -460,11 +462,15 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   G.np = (p.n + 31) / 32 * 32;
   G.Wb = 2 * G.np / 32;
   G.RS = Geo<D>::EW * (G.Wb + 1);
-  G.tab = reinterpret_cast<uint32_t*>(smem);
+  const int row_words = (p.n * G.RS + 3) & ~3;
+  uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
+  G.tab = sm;
+  sm += row_words;
+  G.ph_base = reinterpret_cast<uint2*>(sm);
   G.pacc = G.phase_of(warp);
-  const int tab_words = (p.n * G.RS + nw * 2 * G.Wb + 3) & ~3;
+  const int acc_words = (nw * 2 * G.Wb + 3) & ~3;
   PScratch S;
-  S.ops = reinterpret_cast<int4*>(G.tab + tab_words);
+  S.ops = reinterpret_cast<int4*>(sm + acc_words);
   S.f = reinterpret_cast<uint2*>(S.ops + 32 * nw);
   S.dotw = S.f + G.Wb;
   S.cnt = reinterpret_cast<uint32_t*>(S.dotw + nw * G.Wb);
@@ -472,11 +478,20 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   S.parity = 0;
   S.br = S.ar + G.np;
   S.xz = reinterpret_cast<uint8_t*>(S.br + G.np);
+  S.next = reinterpret_cast<int*>(S.xz + G.np + ((4 - (G.np & 3)) & 3));
   int4* my_ops = S.ops + 32 * warp;
 
-  for (int64_t shot = blockIdx.x; shot < p.shots; shot += gridDim.x) {
+  for (int round = 0;; ++round) {
+    // claim the next shot: dynamic when the caller provided a counter (shots differ in cost, CTAs in speed),
+    // static grid-stride otherwise
+    if (tid == 0)
+      S.next[round & 1] = p.shot_counter ? (int)atomicAdd(p.shot_counter, 1u) : (int)(blockIdx.x + round * gridDim.x);
+    cta_sync();
+    const int64_t shot = S.next[round & 1];
+    if (shot >= p.shots) break;
     // ---- load: |0...0> or pack from the uint8 store ----
-    for (int i = tid; i < tab_words; i += nt) G.tab[i] = 0u;
+    for (int i = tid; i < row_words; i += nt) G.tab[i] = 0u;
+    for (int i = tid; i < acc_words; i += nt) reinterpret_cast<uint32_t*>(G.ph_base)[i] = 0u;
     if (tid < 8) S.cnt[tid] = 0;
     cta_sync();
     uint8_t* T8 = p.tab ? p.tab + shot * p.shot_bytes : nullptr;
@@ -622,11 +637,20 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   }
 }
 
-inline size_t planes_smem_bytes(int n, int d, int nw = SDIMB_SCHED_WARPS) {
+// bytes of the row image of one shot (shared memory of a resident CTA, or one global slab of an overflow CTA)
+inline size_t planes_row_bytes(int n, int d) {
   const size_t EW = (d == 2) ? 2 : 4;
   const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32, RS = EW * (Wb + 1);
-  const size_t tab_words = ((size_t)n * RS + (size_t)nw * 2 * Wb + 3) & ~(size_t)3;
-  return 4 * tab_words + (size_t)nw * 32 * 16 + 8 * Wb + (size_t)nw * 8 * Wb + 32 + 2 * np + 2 * np + np + 16;
+  return 4 * (((size_t)n * RS + 3) & ~(size_t)3);
+}
+// shared memory besides the rows: phase accumulators + scratch
+inline size_t planes_scratch_bytes(int n, int nw) {
+  const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32;
+  const size_t acc_words = ((size_t)nw * 2 * Wb + 3) & ~(size_t)3;
+  return 4 * acc_words + (size_t)nw * 32 * 16 + 8 * Wb + (size_t)nw * 8 * Wb + 32 + 2 * np + 2 * np + np + 4 + 8 + 16;
+}
+inline size_t planes_smem_bytes(int n, int d, int nw = SDIMB_SCHED_WARPS) {
+  return planes_row_bytes(n, d) + planes_scratch_bytes(n, nw);
 }
 
 }  // namespace planes

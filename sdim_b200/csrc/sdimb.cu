@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -100,6 +101,7 @@ struct KParams {
   Arith A;
   uint32_t flags;
   int resident;
+  unsigned int* shot_counter;  // bit-plane kernel: next unclaimed shot (nullable: static grid-stride)
 };
 
 // Shared scratch common to both modes (carved from dynamic shared memory after the resident tableau).
@@ -934,6 +936,11 @@ int sdimb_run(const SdimbRunArgs* a) {
     }
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > a->shots) grid = a->shots;
+    if (a->scratch && a->scratch_bytes >= (int64_t)sizeof(unsigned int)) {   // dynamic shot claiming
+      p.shot_counter = (unsigned int*)a->scratch;
+      if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess)
+        return SDIMB_ECUDA;
+    }
     kern<<<(unsigned)grid, 32 * nw, smem, (cudaStream_t)a->stream>>>(p);
     g_launches++;
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
@@ -1062,7 +1069,8 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_th = (n_noise && noise_thresh24) ? align256((size_t)n_noise * 4) : 0;
   const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
   const size_t b_tab = kernel == 0 ? align256((size_t)shots * L.shot_bytes) : 0;
-  const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + 256;
+  const size_t b_scr = align256((size_t)sdimb_scratch_bytes(n, d, mode_flags));
+  const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_scr + 256;
 
   std::lock_guard<std::mutex> lock(g_ws.mu);
   if (!g_ws.prepare(total, b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
@@ -1074,7 +1082,8 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   uint8_t* d_rn = b_rn ? base : nullptr; base += b_rn;
   uint8_t* d_th = b_th ? base : nullptr; base += b_th;
   uint8_t* d_ch = b_ch ? base : nullptr; base += b_ch;
-  uint8_t* d_tab = b_tab ? base : nullptr;
+  uint8_t* d_tab = b_tab ? base : nullptr; base += b_tab;
+  uint8_t* d_scr = b_scr ? base : nullptr;
   rc = SDIMB_ECUDA;
   do {
     if (cudaEventRecord(g_ws.e0, st) != cudaSuccess) break;
@@ -1094,6 +1103,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     a.replay_meas = d_rm; a.replay_noise = d_rn;
     a.noise_thresh24 = (const uint32_t*)d_th; a.noise_channel = d_ch; a.n_noise = n_noise;
     a.seed = seed; a.stream = st;
+    a.scratch = d_scr; a.scratch_bytes = (int64_t)b_scr;
     rc = sdimb_run(&a);
     if (rc) break;
     rc = SDIMB_ECUDA;
@@ -1192,6 +1202,13 @@ int sdimb_frames(int n, int d, int64_t shots, int64_t shot_offset, const int32_t
   frame_kernel<<<(unsigned)grid, 128, 0, (cudaStream_t)stream>>>(p);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+}
+
+int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags) {
+  SdimbLayout L;
+  if (sdimb_layout(n, d, &L)) return 0;
+  if (plan_kernel(n, d, flags, L.np) != 2) return 0;
+  return 256;   // the shot counter
 }
 
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau) {

@@ -55,6 +55,7 @@ class TableauEngine:
             self.noise_channel = torch.from_numpy(prog.noise_channel.copy()).to(dev)
         else:
             self.noise_channel = None
+        self._scratch: Dict[int, torch.Tensor] = {}     # per mode flags: counter + overflow slabs of the plane kernel
         self.tableau: Optional[torch.Tensor] = None     # uint8 [shots, shot_bytes] of the last run that kept it
         self.tableau_shots = 0
 
@@ -66,6 +67,12 @@ class TableauEngine:
         flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
         k, need = N.plan(self.prog.num_qudits, self.prog.dimension, flags)
         return N.KERNEL_NAMES[k], need
+
+    def _scratch_for(self, mode_flags: int) -> Optional[torch.Tensor]:
+        if mode_flags not in self._scratch:
+            nbytes = int(self.lib.sdimb_scratch_bytes(self.prog.num_qudits, self.prog.dimension, mode_flags))
+            self._scratch[mode_flags] = torch.empty(nbytes, dtype=torch.uint8, device=self.device) if nbytes else None
+        return self._scratch[mode_flags]
 
     def fits_resident(self, mode: Optional[str] = None) -> bool:
         return not self.plan(mode)[1]
@@ -133,6 +140,8 @@ class TableauEngine:
             a.n_noise = prog.n_noise
             a.seed = seed & 0xFFFFFFFFFFFFFFFF
             a.stream = torch.cuda.current_stream(dev).cuda_stream
+            scratch = self._scratch_for(self.MODES[mode])
+            a.scratch, a.scratch_bytes = _ptr(scratch), (scratch.numel() if scratch is not None else 0)
             N.check(self.lib.sdimb_run(C.byref(a)))
         if keep_tableau:
             self.tableau, self.tableau_shots = tableau, shots
