@@ -27,6 +27,7 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 
 constexpr int kMaxThreads = 256;
+constexpr int kWideThreads = 1024;
 constexpr uint32_t kNoPivot = 0xFFFFFFFFu;
 constexpr int kSmemLimit = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
@@ -112,20 +113,22 @@ struct Scratch {
   uint32_t* cnt;       // [4]    list lengths
   int4* ops;           // [32]   staged op batch (N1 rows carry the decoded event in .z)
   uint16_t* ar;        // [np]   active rows: qudits on which the pivot acts / active generators (det branch)
+  uint16_t* br;        // [np]   rows outside the support whose destabilizer-p entry is stale
   uint16_t* aw;        // [W/4]  active words: lane quads holding a non-zero factor
   uint8_t* xs;         // [np]   pivot column X (random branch) / factors of the active generators (det branch)
   uint8_t* zs;         // [np]   pivot column Z
   uint8_t* inv;        // [128]  multiplicative inverses mod d
 };
 
+// Block reductions: warp reduce -> one word per warp in shared memory -> every warp reduces those words again with
+// shuffles (one LDS + one redux instead of a 32-step loop per thread; it matters with 1024-thread CTAs).
 __device__ __forceinline__ uint32_t block_sum(uint32_t v, uint32_t* red) {
   v = __reduce_add_sync(0xFFFFFFFFu, v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  uint32_t t = 0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-  return t;
+  const uint32_t lane = threadIdx.x & 31;
+  return __reduce_add_sync(0xFFFFFFFFu, lane < (blockDim.x >> 5) ? red[lane] : 0u);
 }
 
 __device__ __forceinline__ uint32_t block_min(uint32_t v, uint32_t* red) {
@@ -133,9 +136,8 @@ __device__ __forceinline__ uint32_t block_min(uint32_t v, uint32_t* red) {
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  uint32_t t = kNoPivot;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = min(t, red[i]);
-  return t;
+  const uint32_t lane = threadIdx.x & 31;
+  return __reduce_min_sync(0xFFFFFFFFu, lane < (blockDim.x >> 5) ? red[lane] : kNoPivot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -335,6 +337,7 @@ __device__ __forceinline__ uint32_t noise_event(const KParams& p, int64_t j, int
 // and a dense one streams the tableau with full memory-level parallelism.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBatch = 4;
+constexpr int kWalk = 4;     // rows per thread whose column loads are issued together
 
 __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int64_t slot, int64_t shot_local,
                             uint32_t draw) {
@@ -343,7 +346,7 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
   const int wz = W / 4;
   uint8_t* rowq = T + (int64_t)q * p.row_bytes;
   uint8_t* P8 = T + p.phase_off;
-  if (tid < 2) S.cnt[tid] = 0;   // cnt[3] holds the live-op mask of the current batch
+  if (tid < 3) S.cnt[tid] = 0;   // cnt[3] holds the live-op mask of the current batch
   __syncthreads();   // gate writes of other threads' lanes become visible; counters reset
 
   // -- pivot: FIRST stabilizer with an X component on q (tableau_prime.py:273-283) ------------------
@@ -364,13 +367,31 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
     const uint32_t e = S.inv[v];
     const uint32_t ps_old = P8[piv];
     uint32_t sd_raw = 0;
-    for (int r = tid; r < n; r += nt) {                       // pivot column -> xs/zs, active-row list
-      const uint8_t* row = T + (int64_t)r * p.row_bytes;
-      const uint32_t xr = row[piv], zr = row[W + piv];
-      S.xs[r] = (uint8_t)mod_d(A, xr * e);
-      S.zs[r] = (uint8_t)mod_d(A, zr * e);
-      sd_raw += mod_d(A, xr * zr);
-      if (xr | zr) S.ar[atomicAdd(&S.cnt[0], 1u)] = (uint16_t)r;
+    // One walk down the pivot column AND the destabilizer-p column (kWalk rows' loads in flight per thread):
+    // xs/zs, the support list `ar`, and the list `br` of rows outside the support whose destabilizer-p entry is
+    // non-zero and must be cleared when the destabilizer is overwritten with the pivot.
+    for (int base = tid; base < n; base += nt * kWalk) {
+      uint32_t xr[kWalk], zr[kWalk], od[kWalk];
+#pragma unroll
+      for (int u = 0; u < kWalk; ++u) {
+        const int r = base + u * nt;
+        xr[u] = zr[u] = od[u] = 0;
+        if (r < n) {
+          const uint8_t* row = T + (int64_t)r * p.row_bytes;
+          xr[u] = row[piv]; zr[u] = row[W + piv];
+          od[u] = (uint32_t)row[npad + piv] | row[W + npad + piv];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kWalk; ++u) {
+        const int r = base + u * nt;
+        if (r >= n) break;
+        S.xs[r] = (uint8_t)mod_d(A, xr[u] * e);
+        S.zs[r] = (uint8_t)mod_d(A, zr[u] * e);
+        sd_raw += mod_d(A, xr[u] * zr[u]);
+        if (xr[u] | zr[u]) S.ar[atomicAdd(&S.cnt[0], 1u)] = (uint16_t)r;
+        else if (od[u]) S.br[atomicAdd(&S.cnt[2], 1u)] = (uint16_t)r;
+      }
     }
     for (int w = tid; w < wz; w += nt) {                      // factors f = -X[q,i] mod d, active-word list
       const uint32_t xq_w = reinterpret_cast<const uint32_t*>(rowq)[w];
@@ -464,22 +485,22 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
     }
     __syncthreads();
     // destabilizer p <- old pivot, stabilizer p <- Z_q with phase -m*po (tableau_prime.py:323-333).
-    // Column accesses cost one DRAM sector per byte, so only entries that change are written: the
-    // stabilizer lane is non-zero exactly on the pivot's support (the active rows), the destabilizer
-    // lane is read back and rewritten where it differs.
+    // Column accesses cost one DRAM sector per byte, so only entries that change are written: both lanes are
+    // rewritten on the pivot's support (list ar), stale destabilizer entries elsewhere (list br) are cleared.
+    const int nr_b = (int)S.cnt[2];
     for (int i = tid; i < nr_a; i += nt) {
-      uint8_t* row = T + (int64_t)S.ar[i] * p.row_bytes;
-      row[piv] = 0;
-      row[W + piv] = 0;
-    }
-    for (int r = tid; r < n; r += nt) {
+      const int r = S.ar[i];
       uint8_t* row = T + (int64_t)r * p.row_bytes;
-      const uint8_t xs = S.xs[r], zs = S.zs[r];
-      if (row[npad + piv] != xs) row[npad + piv] = xs;
-      if (row[W + npad + piv] != zs) row[W + npad + piv] = zs;
+      row[piv] = 0;
+      row[W + piv] = (r == q) ? 1 : 0;
+      row[npad + piv] = S.xs[r];
+      row[W + npad + piv] = S.zs[r];
     }
-    __syncthreads();
-    if (tid == 0) rowq[W + piv] = 1;
+    for (int i = tid; i < nr_b; i += nt) {
+      uint8_t* row = T + (int64_t)S.br[i] * p.row_bytes;
+      row[npad + piv] = 0;
+      row[W + npad + piv] = 0;
+    }
     outcome = draw;
     if (tid == 0) {
       P8[npad + piv] = (uint8_t)ps;
@@ -499,12 +520,17 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
       const uint32_t mask = __ballot_sync(0xFFFFFFFFu, f != 0);
       if ((tid & 31) == 0) S.red[tid >> 5] = __popc(mask);
       __syncthreads();
-      int off = total, all = total;
-      for (int wv = 0; wv < (nt >> 5); ++wv) {
-        const int c = (int)S.red[wv];
-        if (wv < (tid >> 5)) off += c;
-        all += c;
+      // exclusive scan of the per-warp counts, done by every warp with shuffles
+      const int lane_id = tid & 31;
+      const int mine_cnt = lane_id < (nt >> 5) ? (int)S.red[lane_id] : 0;
+      int incl = mine_cnt;
+#pragma unroll
+      for (int d2 = 1; d2 < 32; d2 <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d2);
+        if (lane_id >= d2) incl += o;
       }
+      const int off = total + __shfl_sync(0xFFFFFFFFu, incl - mine_cnt, tid >> 5);
+      const int all = total + __shfl_sync(0xFFFFFFFFu, incl, 31);
       if (f) {
         const int pos = off + __popc(mask & ((1u << (tid & 31)) - 1u));
         S.ar[pos] = (uint16_t)i;
@@ -552,7 +578,7 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
 // ---------------------------------------------------------------------------------------------
 // The interpreter: one CTA per shot, grid-stride over shots.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_constant__ KParams p) {
+__device__ __forceinline__ void interp_body(const KParams& p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int64_t tab_smem = p.resident ? p.shot_bytes : 0;
   Scratch S;
@@ -562,7 +588,8 @@ __global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_con
   S.cnt = S.red + 32;
   S.ops = reinterpret_cast<int4*>(S.cnt + 4);
   S.ar = reinterpret_cast<uint16_t*>(S.ops + 32);
-  S.aw = S.ar + p.np;
+  S.br = S.ar + p.np;
+  S.aw = S.br + p.np;
   S.xs = reinterpret_cast<uint8_t*>(S.aw + p.W / 4);
   S.zs = S.xs + p.np;
   S.inv = S.zs + p.np;
@@ -666,6 +693,11 @@ __global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_con
     __syncthreads();
   }
 }
+
+// Two launch shapes of the same body: up to 256 threads (many shots in flight, 12 CTAs of 128 threads per SM) and
+// up to 1024 threads for tableaus whose rows span more than 256 lane words (n > 512: few, large shots — config 5).
+__global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_constant__ KParams p) { interp_body(p); }
+__global__ void __launch_bounds__(kWideThreads, 1) interp_kernel_wide(const __grid_constant__ KParams p) { interp_body(p); }
 
 __global__ void init_kernel(uint8_t* tab, int n, int np, int W, int64_t row_bytes, int64_t shot_bytes, int64_t shots) {
   for (int64_t shot = blockIdx.x; shot < shots; shot += gridDim.x) {
@@ -802,13 +834,13 @@ int check_dims(int n, int d) {
 int block_threads(int W) {
   int t = ((W / 4) + 31) / 32 * 32;
   if (t < 32) t = 32;
-  if (t > kMaxThreads) t = kMaxThreads;
+  if (t > kMaxThreads) t = t > kWideThreads ? kWideThreads : t;   // > 256 threads run interp_kernel_wide
   return t;
 }
 
 size_t scratch_bytes(int np) {
   const size_t W = 2 * (size_t)np;
-  return 4 * W + W + 32 * 4 + 4 * 4 + 32 * 16 + 2 * (size_t)np + 2 * (W / 4) + 2 * (size_t)np + 128;
+  return 4 * W + W + 32 * 4 + 4 * 4 + 32 * 16 + 4 * (size_t)np + 2 * (W / 4) + 2 * (size_t)np + 128;
 }
 
 // Which interpreter a (n, d, flags) call runs: 0 = uint8 lanes in global memory, 1 = uint8 lanes resident in
@@ -947,13 +979,14 @@ int sdimb_run(const SdimbRunArgs* a) {
   }
   const int threads = block_threads(L.lanes);
   const size_t smem = scratch + (resident ? (size_t)L.shot_bytes : 0);
-  if (cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  auto lane_kernel = threads > kMaxThreads ? interp_kernel_wide : interp_kernel;
+  if (cudaFuncSetAttribute(lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return SDIMB_ECUDA;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, interp_kernel, threads, smem) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lane_kernel, threads, smem) != cudaSuccess || per_sm < 1)
     return SDIMB_ECUDA;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > a->shots) grid = a->shots;
-  interp_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)a->stream>>>(p);
+  lane_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)a->stream>>>(p);
   g_launches++;
   return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
 }
