@@ -21,3 +21,4 @@ ncu --set full --clock-control none --import-source on -k regex:interp -s 1 -c 1
 python bench.py --steps 5 --warmup 3 --shots 16384 > gpurun_out/${R}_bench_n1.json 2> gpurun_out/${R}_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>/dev/null
 tail -1 gpurun_out/${R}_bench_n1.json | cut -c1-300
+python benchmarks/configs.py > gpurun_out/${R}_configs.json 2> gpurun_out/${R}_configs.err
