@@ -295,6 +295,7 @@ def bench_ours(args):
 
     # ---- roofline of the dominant kernel (the interpreter launch = one step) -------------------------
     det_flags = (records[0].cpu().numpy() & 0x80) != 0
+    # accounting only (never on the measured path): how many generators each measurement really touches
     from oracle import c_oracle
     meas_nnz = c_oracle.measurement_factor_counts(prog, seed) if c_oracle.available() else None
     alg_bytes = algorithmic_bytes_per_shot(prog, det_flags, meas_nnz) * shots
