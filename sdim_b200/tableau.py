@@ -123,6 +123,45 @@ class ExtendedTableau(Tableau):
         self.print_destab_z_block()
         self.print_destab_x_block()
 
+    # ---- the reference's per-gate interface (sdim/tableau/tableau_prime.py:97-292) -----------------------
+    # Kept for callers that drive a tableau by hand.  Every call packs this tableau into the device store, runs
+    # ONE op through the CUDA interpreter and reads the six arrays back (there is no host implementation of the
+    # arithmetic); use Program.simulate for anything performance sensitive.
+    def _device_op(self, gate_name: str, qudit: int, target: Optional[int] = None, device=None):
+        from .circuit import Circuit
+        from .program import Program
+        circuit = Circuit(self.num_qudits, self.dimension)
+        prog = Program(circuit, tableau=self, device=device)
+        from .circuit import CircuitInstruction
+        result = prog.apply_gate(CircuitInstruction(circuit.gate_data, gate_name, qudit, target))
+        t = prog.stabilizer_tableau
+        self.x_block, self.z_block, self.phase_vector = t.x_block, t.z_block, t.phase_vector
+        self.destab_x_block, self.destab_z_block = t.destab_x_block, t.destab_z_block
+        self.destab_phase_vector = t.destab_phase_vector
+        return result
+
+    def hadamard(self, qudit_index: int):
+        self._device_op("H", qudit_index)
+
+    def hadamard_inv(self, qudit_index: int):
+        self._device_op("H_INV", qudit_index)
+
+    def phase(self, qudit_index: int):
+        self._device_op("P", qudit_index)
+
+    def phase_inv(self, qudit_index: int):
+        self._device_op("P_INV", qudit_index)
+
+    def cnot(self, control: int, target: int):
+        self._device_op("CNOT", control, target)
+
+    def cnot_inv(self, control: int, target: int):
+        self._device_op("CNOT_INV", control, target)
+
+    def measure(self, qudit_index: int):
+        """Z-basis measurement of one qudit (tableau_prime.py:262-292); returns a MeasurementResult."""
+        return self._device_op("M", qudit_index)
+
     # ---- conversion to / from the device store -------------------------------------------------
     @classmethod
     def from_arrays(cls, n: int, d: int, arrays: Dict[str, np.ndarray]) -> "ExtendedTableau":

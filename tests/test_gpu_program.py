@@ -230,3 +230,26 @@ def test_verbose_and_show_gate_run(capsys):
     assert "Initial state" in out and "Final step 3" in out and "Destabilizer X Block" in out
     assert "Measured qudit (0)" in out
     assert res[0].measurement_value == res[1].measurement_value and res[1].deterministic
+
+
+def test_extended_tableau_gate_methods_match_oracle():
+    """The reference's per-gate interface on ExtendedTableau (tableau_prime.py:97-292), each call one device op."""
+    from oracle.tableau_oracle import OracleTableau
+    from sdim_b200 import ExtendedTableau
+    for d in (2, 3, 5):
+        t, o = ExtendedTableau(3, d), OracleTableau(3, d)
+        t.hadamard(0); o.hadamard(0)
+        t.cnot(0, 1); o.cnot(0, 1)
+        t.phase(1); o.phase(1)
+        t.hadamard_inv(2); o.hadamard(2, inverse=True)
+        t.cnot_inv(2, 0); o.cnot(2, 0, inverse=True)
+        t.phase_inv(0); o.phase(0, inverse=True)
+        for got, want in zip((t.x_block, t.z_block, t.phase_vector, t.destab_x_block, t.destab_z_block,
+                              t.destab_phase_vector), o.arrays()):
+            assert np.array_equal(got, want)
+        r = t.measure(1)
+        det, m = o.measure(1, lambda: r.measurement_value)
+        assert (r.qudit_index, r.deterministic) == (1, det) and r.measurement_value == m
+        for got, want in zip((t.x_block, t.z_block, t.phase_vector, t.destab_x_block, t.destab_z_block,
+                              t.destab_phase_vector), o.arrays()):
+            assert np.array_equal(got, want)
