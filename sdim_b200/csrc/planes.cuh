@@ -547,7 +547,8 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
         mine.z = (int)p_noise_event<D>(p, mine.w, shot);
         live = mine.z != 0;
       }
-      if (collective && mine.x != SDIMB_OP_BARRIER) {       // outcome this measurement takes if it is random
+      if (collective && mine.x != SDIMB_OP_BARRIER && warp == 0) {   // outcome this measurement takes if it is
+        // random; only warp 0 consumes it (new stabilizer phase, record, RESET correction)
         if (p.replay_meas) {
           mine.z = p.replay_meas[shot * p.n_meas + mine.w];
         } else {
