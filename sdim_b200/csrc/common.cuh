@@ -80,5 +80,6 @@ struct KParams {
   Arith A;
   uint32_t flags;
   int resident;
+  int vec;                     // lane interpreter: lane words per thread (1, or 4 with 128-bit accesses)
   unsigned int* shot_counter;  // bit-plane kernel: next unclaimed shot (nullable: static grid-stride)
 };

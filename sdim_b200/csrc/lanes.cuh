@@ -84,29 +84,32 @@ __device__ __forceinline__ Rows load_rows(const uint8_t* T, const KParams& p, in
 
 // pa, pb: Pauli exponents for X/X_INV/Z/Z_INV/N1 (phase += po*(pb*x - pa*z)), unused otherwise.
 // Additions, subtractions and negations run on all four lanes of a word at once (Swar); only the lane-by-lane
-// products of the phase terms are computed per byte.
-__device__ __forceinline__ uint32_t gate_word(uint8_t* T, const KParams& p, int op, int a, int b, uint32_t pa,
-                                              uint32_t pb, const Rows r, int w, uint32_t ph) {
+// products of the phase terms are computed per byte.  Pure arithmetic: `r` is updated in place, the new phase
+// word is written to `ph`, and the return value says which of the four row words changed (bit 0 xa, 1 za, 2 xb,
+// 3 zb) so that callers store only those.
+enum { CH_XA = 1, CH_ZA = 2, CH_XB = 4, CH_ZB = 8 };
+
+__device__ __forceinline__ uint32_t gate_math(const KParams& p, int op, uint32_t pa, uint32_t pb, Rows& r,
+                                              uint32_t& ph) {
   const Arith& A = p.A;
   const Swar Sd = make_swar(A.d), So = make_swar(A.order);
-  const int wz = p.W / 4;
-  uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
-  uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
   switch (op) {
     case SDIMB_OP_H:
     case SDIMB_OP_H_INV: {
-      if ((r.xa | r.za) == 0) return ph;
+      if ((r.xa | r.za) == 0) return 0;
       // phase += po * new_x * new_z == -po * x * z        (tableau_optimized.py:17-30,45-58)
       uint32_t prod = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) prod |= (A.po * mod_d(A, byte_of(r.xa, k) * byte_of(r.za, k))) << (8 * k);
-      if (op == SDIMB_OP_H) { rowa[w] = swar_neg(Sd, r.za); rowa[wz + w] = r.xa; }     // (x,z) <- (-z, x)
-      else { rowa[w] = r.za; rowa[wz + w] = swar_neg(Sd, r.xa); }                      // (x,z) <- (z, -x)
-      return swar_sub(So, ph, prod);
+      const uint32_t x = r.xa, z = r.za;
+      if (op == SDIMB_OP_H) { r.xa = swar_neg(Sd, z); r.za = x; }            // (x,z) <- (-z, x)
+      else { r.xa = z; r.za = swar_neg(Sd, x); }                             // (x,z) <- (z, -x)
+      ph = swar_sub(So, ph, prod);
+      return CH_XA | CH_ZA;
     }
     case SDIMB_OP_P:
     case SDIMB_OP_P_INV: {
-      if (r.xa == 0) return ph;
+      if (r.xa == 0) return 0;
       // even d: phase +-= x^2 (mod 2d); odd d: phase +-= x(x-1)/2 (mod d)   (tableau_optimized.py:62-96)
       uint32_t inc = 0;
 #pragma unroll
@@ -114,61 +117,103 @@ __device__ __forceinline__ uint32_t gate_word(uint8_t* T, const KParams& p, int 
         const uint32_t xb = byte_of(r.xa, k);
         inc |= ((A.po == 2) ? mod_o(A, xb * xb) : mod_d(A, (xb * (xb - 1u)) >> 1)) << (8 * k);
       }
-      if (op == SDIMB_OP_P) { rowa[wz + w] = swar_add(Sd, r.za, r.xa); return swar_add(So, ph, inc); }
-      rowa[wz + w] = swar_sub(Sd, r.za, r.xa);
-      return swar_sub(So, ph, inc);
+      if (op == SDIMB_OP_P) { r.za = swar_add(Sd, r.za, r.xa); ph = swar_add(So, ph, inc); }
+      else { r.za = swar_sub(Sd, r.za, r.xa); ph = swar_sub(So, ph, inc); }
+      return CH_ZA;
     }
     case SDIMB_OP_X: case SDIMB_OP_X_INV: case SDIMB_OP_Z: case SDIMB_OP_Z_INV: case SDIMB_OP_N1: {
       // conjugation by X^pa Z^pb: phase += po * (pb*x - pa*z)  (tableau_gates.py:27-137, program.py:335-339)
       const uint32_t na = pa ? A.d - pa : 0u;
       const uint32_t x = pb ? r.xa : 0u, z = na ? r.za : 0u;
-      if ((x | z) == 0) return ph;
+      if ((x | z) == 0) return 0;
       const bool unit_x = pb == 0u || pb == 1u || pb == A.d - 1u, unit_z = pa == 0u || pa == 1u || pa == A.d - 1u;
       if (unit_x && unit_z) {                                 // exponents +-1: no products, all four lanes at once
         const uint32_t sx = A.po == 2 ? x << 1 : x, sz = A.po == 2 ? z << 1 : z;
-        uint32_t q = ph;
-        if (pb) q = (pb == 1u) ? swar_add(So, q, sx) : swar_sub(So, q, sx);
-        if (pa) q = (pa == 1u) ? swar_sub(So, q, sz) : swar_add(So, q, sz);
-        return q;
+        if (pb) ph = (pb == 1u) ? swar_add(So, ph, sx) : swar_sub(So, ph, sx);
+        if (pa) ph = (pa == 1u) ? swar_sub(So, ph, sz) : swar_add(So, ph, sz);
+        return 0;
       }
       uint32_t t = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) t |= mod_d(A, pb * byte_of(x, k) + na * byte_of(z, k)) << (8 * k);
-      return swar_add(So, ph, A.po == 2 ? t << 1 : t);
+      ph = swar_add(So, ph, A.po == 2 ? t << 1 : t);
+      return 0;
     }
-    case SDIMB_OP_CNOT: {                                     // x[t] += x[c];  z[c] -= z[t]   (tableau_optimized.py:99-107)
-      if ((r.xa | r.zb) == 0) return ph;
-      rowb[w] = swar_add(Sd, r.xb, r.xa);
-      rowa[wz + w] = swar_sub(Sd, r.za, r.zb);
-      return ph;
-    }
-    case SDIMB_OP_CNOT_INV: {                                 // x[t] -= x[c];  z[c] += z[t]   (tableau_optimized.py:110-118)
-      if ((r.xa | r.zb) == 0) return ph;
-      rowb[w] = swar_sub(Sd, r.xb, r.xa);
-      rowa[wz + w] = swar_add(Sd, r.za, r.zb);
-      return ph;
-    }
+    case SDIMB_OP_CNOT:                                       // x[t] += x[c];  z[c] -= z[t]   (tableau_optimized.py:99-107)
+      if ((r.xa | r.zb) == 0) return 0;
+      r.xb = swar_add(Sd, r.xb, r.xa);
+      r.za = swar_sub(Sd, r.za, r.zb);
+      return CH_XB | CH_ZA;
+    case SDIMB_OP_CNOT_INV:                                   // x[t] -= x[c];  z[c] += z[t]   (tableau_optimized.py:110-118)
+      if ((r.xa | r.zb) == 0) return 0;
+      r.xb = swar_sub(Sd, r.xb, r.xa);
+      r.za = swar_add(Sd, r.za, r.zb);
+      return CH_XB | CH_ZA;
     case SDIMB_OP_CZ:
     case SDIMB_OP_CZ_INV: {
-      if ((r.xa | r.xb) == 0) return ph;
+      if ((r.xa | r.xb) == 0) return 0;
       // CZ = H^-1(t) CNOT(c,t) H(t) folded: z[a] +-= x[b]; z[b] +-= x[a]; phase +-= po*x[a]*x[b]
       uint32_t prod = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) prod |= (A.po * mod_d(A, byte_of(r.xa, k) * byte_of(r.xb, k))) << (8 * k);
       if (op == SDIMB_OP_CZ) {
-        rowa[wz + w] = swar_add(Sd, r.za, r.xb); rowb[wz + w] = swar_add(Sd, r.zb, r.xa);
-        return swar_add(So, ph, prod);
+        r.za = swar_add(Sd, r.za, r.xb); r.zb = swar_add(Sd, r.zb, r.xa);
+        ph = swar_add(So, ph, prod);
+      } else {
+        r.za = swar_sub(Sd, r.za, r.xb); r.zb = swar_sub(Sd, r.zb, r.xa);
+        ph = swar_sub(So, ph, prod);
       }
-      rowa[wz + w] = swar_sub(Sd, r.za, r.xb); rowb[wz + w] = swar_sub(Sd, r.zb, r.xa);
-      return swar_sub(So, ph, prod);
+      return CH_ZA | CH_ZB;
     }
-    case SDIMB_OP_SWAP:
-      rowa[w] = r.xb; rowa[wz + w] = r.zb;
-      rowb[w] = r.xa; rowb[wz + w] = r.za;
-      return ph;
+    case SDIMB_OP_SWAP: {
+      const uint32_t x = r.xa, z = r.za;
+      r.xa = r.xb; r.za = r.zb; r.xb = x; r.zb = z;
+      return CH_XA | CH_ZA | CH_XB | CH_ZB;
+    }
     default:
-      return ph;
+      return 0;
   }
+}
+
+// One gate on one lane word: math + stores of the words that changed; returns the new phase word.
+__device__ __forceinline__ uint32_t gate_word(uint8_t* T, const KParams& p, int op, int a, int b, uint32_t pa,
+                                              uint32_t pb, Rows r, int w, uint32_t ph) {
+  const int wz = p.W / 4;
+  uint32_t* rowa = reinterpret_cast<uint32_t*>(T + (int64_t)a * p.row_bytes);
+  uint32_t* rowb = reinterpret_cast<uint32_t*>(T + (int64_t)b * p.row_bytes);
+  const uint32_t ch = gate_math(p, op, pa, pb, r, ph);
+  if (ch & CH_XA) rowa[w] = r.xa;
+  if (ch & CH_ZA) rowa[wz + w] = r.za;
+  if (ch & CH_XB) rowb[w] = r.xb;
+  if (ch & CH_ZB) rowb[wz + w] = r.zb;
+  return ph;
+}
+
+// One gate on FOUR consecutive lane words owned by one thread (128-bit loads and stores, dispatch and address
+// arithmetic paid once for 16 lanes): the streaming shape of the lane interpreter for wide rows on the HBM store.
+__device__ __forceinline__ void gate_vec4(uint8_t* T, const KParams& p, int op, int a, int b, uint32_t pa, uint32_t pb,
+                                          int w0, uint32_t (&ph)[4]) {
+  const int wz = p.W / 4;
+  uint4* rowa = reinterpret_cast<uint4*>(T + (int64_t)a * p.row_bytes);
+  uint4* rowb = reinterpret_cast<uint4*>(T + (int64_t)b * p.row_bytes);
+  const bool two = is_two_qudit(op);
+  const int v = w0 >> 2, vz = (wz + w0) >> 2;
+  const uint4 xa4 = rowa[v], za4 = rowa[vz];
+  uint4 xb4 = make_uint4(0, 0, 0, 0), zb4 = xb4;
+  if (two) { xb4 = rowb[v]; zb4 = rowb[vz]; }
+  uint32_t xa[4] = {xa4.x, xa4.y, xa4.z, xa4.w}, za[4] = {za4.x, za4.y, za4.z, za4.w};
+  uint32_t xb[4] = {xb4.x, xb4.y, xb4.z, xb4.w}, zb[4] = {zb4.x, zb4.y, zb4.z, zb4.w};
+  uint32_t ch = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    Rows r{xa[c], za[c], xb[c], zb[c]};
+    ch |= gate_math(p, op, pa, pb, r, ph[c]);
+    xa[c] = r.xa; za[c] = r.za; xb[c] = r.xb; zb[c] = r.zb;
+  }
+  if (ch & CH_XA) rowa[v] = make_uint4(xa[0], xa[1], xa[2], xa[3]);
+  if (ch & CH_ZA) rowa[vz] = make_uint4(za[0], za[1], za[2], za[3]);
+  if (ch & CH_XB) rowb[v] = make_uint4(xb[0], xb[1], xb[2], xb[3]);
+  if (ch & CH_ZB) rowb[vz] = make_uint4(zb[0], zb[1], zb[2], zb[3]);
 }
 
 // Pauli exponents (a, b) of an op of the phase-only family
@@ -474,6 +519,7 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
 // ---------------------------------------------------------------------------------------------
 // The interpreter: one CTA per shot, grid-stride over shots.
 // ---------------------------------------------------------------------------------------------
+template <bool VEC4>
 __device__ __forceinline__ void interp_body(const KParams& p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int64_t tab_smem = p.resident ? p.shot_bytes : 0;
@@ -513,11 +559,32 @@ __device__ __forceinline__ void interp_body(const KParams& p) {
 
     // When a row is at most one word per thread, the thread's phase word stays in a register between
     // measurements (gates never read another lane's phase).
-    const int w0 = threadIdx.x;
-    const bool one_word = p.W / 4 <= (int)blockDim.x;
+    constexpr bool vec4 = VEC4;                               // four words (16 lanes) per thread, 128-bit accesses
+    const int w0 = vec4 ? 4 * (int)threadIdx.x : (int)threadIdx.x;
+    const bool one_word = vec4 || p.W / 4 <= (int)blockDim.x;  // the thread's phase word(s) can live in registers
     const bool own_word = one_word && w0 < p.W / 4;
     uint32_t* Pw = reinterpret_cast<uint32_t*>(T + p.phase_off) + w0;
-    uint32_t pw = own_word ? *Pw : 0u;
+    uint32_t pw = (own_word && !vec4) ? *Pw : 0u;
+    uint32_t pw4[4] = {0u, 0u, 0u, 0u};
+    if (own_word && vec4) { const uint4 v = *reinterpret_cast<const uint4*>(Pw); pw4[0] = v.x; pw4[1] = v.y; pw4[2] = v.z; pw4[3] = v.w; }
+    auto phases_out = [&]() {                                 // measurement reads and writes phases in memory
+      if (!own_word) return;
+      if (vec4) *reinterpret_cast<uint4*>(Pw) = make_uint4(pw4[0], pw4[1], pw4[2], pw4[3]);
+      else *Pw = pw;
+    };
+    auto phases_in = [&]() {
+      if (!own_word) return;
+      if (vec4) { const uint4 v = *reinterpret_cast<const uint4*>(Pw); pw4[0] = v.x; pw4[1] = v.y; pw4[2] = v.z; pw4[3] = v.w; }
+      else pw = *Pw;
+    };
+    auto one_gate = [&](int code, int qa, int qb, uint32_t ea, uint32_t eb) {
+      if (!one_word) {
+        gate_rows(T, p, make_int4(code, qa, qb, -1), ea, eb);
+      } else if (own_word) {
+        if (vec4) gate_vec4(T, p, code, qa, qb, ea, eb, w0, pw4);
+        else pw = gate_word(T, p, code, qa, qb, ea, eb, load_rows(T, p, code, qa, qb, w0), w0, pw);
+      }
+    };
 
     for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
       // warp 0 fetches 32 ops (one per lane) and resolves their N1 events; only live ops are dispatched
@@ -556,30 +623,18 @@ __device__ __forceinline__ void interp_body(const KParams& p) {
         if (is_unitary_like(op.x)) {
           uint32_t pa, pb;
           pauli_exponents(p, op, pa, pb);
-          if (!one_word) {
-            gate_rows(T, p, op, pa, pb);
-          } else if (own_word) {
-            pw = gate_word(T, p, op.x, op.y, op.z, pa, pb, load_rows(T, p, op.x, op.y, op.z, w0), w0, pw);
-          }
+          one_gate(op.x, op.y, op.z, pa, pb);
           continue;
         }
         // collective ops: M, M_X, RESET
-        if (op.x == SDIMB_OP_M_X) {                          // tableau_gates.py:292-296: H^-1 then measure
-          const int4 h = make_int4(SDIMB_OP_H_INV, op.y, -1, -1);
-          if (!one_word) gate_rows(T, p, h, 0u, 0u);
-          else if (own_word) pw = gate_word(T, p, h.x, h.y, h.z, 0u, 0u, load_rows(T, p, h.x, h.y, h.z, w0), w0, pw);
-        }
-        if (own_word) *Pw = pw;                              // measurement reads and writes phases in memory
+        if (op.x == SDIMB_OP_M_X) one_gate(SDIMB_OP_H_INV, op.y, -1, 0u, 0u);   // tableau_gates.py:292-296
+        phases_out();
         const uint32_t m = measure(T, p, S, op.y, op.w, shot, (uint32_t)op.z);
-        if (own_word) pw = *Pw;
-        if (op.x == SDIMB_OP_RESET && m) {                   // program.py:335-339: X applied (-m) mod d times
-          const int4 x = make_int4(SDIMB_OP_N1, op.y, (int)(A.d - m), -1);
-          if (!one_word) gate_rows(T, p, x, A.d - m, 0u);
-          else if (own_word) pw = gate_word(T, p, x.x, x.y, -1, A.d - m, 0u, load_rows(T, p, x.x, x.y, -1, w0), w0, pw);
-        }
+        phases_in();
+        if (op.x == SDIMB_OP_RESET && m) one_gate(SDIMB_OP_N1, op.y, -1, A.d - m, 0u);   // program.py:335-339
       }
     }
-    if (own_word) *Pw = pw;
+    phases_out();
     __syncthreads();
     if (p.resident && (p.flags & SDIMB_WRITEBACK)) {
       const uint4* src = reinterpret_cast<const uint4*>(T);
@@ -592,5 +647,8 @@ __device__ __forceinline__ void interp_body(const KParams& p) {
 
 // Two launch shapes of the same body: up to 256 threads (many shots in flight, 12 CTAs of 128 threads per SM) and
 // up to 1024 threads for tableaus whose rows span more than 256 lane words (n > 512: few, large shots — config 5).
-__global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_constant__ KParams p) { interp_body(p); }
-__global__ void __launch_bounds__(kWideThreads, 1) interp_kernel_wide(const __grid_constant__ KParams p) { interp_body(p); }
+__global__ void __launch_bounds__(kMaxThreads, 6) interp_kernel(const __grid_constant__ KParams p) { interp_body<false>(p); }
+__global__ void __launch_bounds__(kWideThreads, 1) interp_kernel_wide(const __grid_constant__ KParams p) { interp_body<false>(p); }
+// streaming shape for gate-dominated streams on the HBM store: 16 lanes per thread, 64 registers (32 one-warp CTAs
+// per SM at n = 256)
+__global__ void __launch_bounds__(kMaxThreads, 4) interp_kernel_stream(const __grid_constant__ KParams p) { interp_body<true>(p); }

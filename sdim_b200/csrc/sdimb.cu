@@ -194,9 +194,12 @@ int sdimb_run(const SdimbRunArgs* a) {
     g_launches++;
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
   }
-  const int threads = block_threads(L.lanes);
+  // wide rows streamed from the HBM store: 16 lanes per thread (fewer, fatter threads; 128-bit accesses)
+  // ... when the stream is gate-dominated: measurements want many threads per shot, gates want few fat ones
+  p.vec = (kernel == 0 && L.lanes / 4 >= 128 && L.lanes / 16 <= kMaxThreads && a->n_meas * 64 <= a->n_ops) ? 4 : 1;
+  const int threads = block_threads(L.lanes / p.vec);
   const size_t smem = scratch + (resident ? (size_t)L.shot_bytes : 0);
-  auto lane_kernel = threads > kMaxThreads ? interp_kernel_wide : interp_kernel;
+  auto lane_kernel = p.vec == 4 ? interp_kernel_stream : threads > kMaxThreads ? interp_kernel_wide : interp_kernel;
   if (cudaFuncSetAttribute(lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return SDIMB_ECUDA;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lane_kernel, threads, smem) != cudaSuccess || per_sm < 1)
