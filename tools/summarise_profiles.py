@@ -27,7 +27,7 @@ want = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
-for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096)):
+for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096), ("gates_stream", 9472)):
     rep = os.path.join(G, f"{R}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -36,7 +36,8 @@ for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096)):
     m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     lines = run(sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "25")
     with open(os.path.join(P, f"{R}_ncu_{tag}.txt"), "w") as fh:
-        fh.write(f"# ncu --set full --clock-control none --import-source on, one launch of the headline workload, {shots} shots\n")
+        what = "the 2000 gates of the headline circuit (no noise, no measurement), uint8 HBM store" if tag == "gates_stream" else "the headline workload"
+        fh.write(f"# ncu --set full --clock-control none --import-source on, one launch of {what}, {shots} shots\n")
         fh.write(f"kernel: {m.get('Kernel Name', ('?',))[0]}\n")
         for k in want:
             if k in m:
