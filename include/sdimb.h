@@ -59,9 +59,12 @@ enum {
   SDIMB_OP_BARRIER = 18   /* layer boundary emitted by sdimb_schedule; never written by users */
 };
 /* In a SCHEDULED stream (output of sdimb_schedule) bits 8..15 of the opcode field carry the warp that
- * executes the op inside its layer; bits 0..7 are the opcode.  An unscheduled stream has those bits 0. */
+ * executes the op inside its layer (index in the layer mod SDIMB_SCHED_WARPS) and bits 16..30 the index in the
+ * layer itself (mod 2^15; the cluster interpreter deals layers over its own number of gate groups); bits 0..7
+ * are the opcode.  An unscheduled stream has those bits 0. */
 #define SDIMB_OP_MASK 0xFF
 #define SDIMB_OP_WARP_SHIFT 8
+#define SDIMB_OP_INDEX_SHIFT 16
 #define SDIMB_SCHED_WARPS 4
 
 /* Record byte: low 7 bits = measured value, bit 7 = deterministic flag
@@ -77,7 +80,11 @@ enum {
 #define SDIMB_FORCE_LANES 0x10u    /* never use the bit-plane interpreter (d = 2, 3), keep uint8 lanes */
 #define SDIMB_FORCE_PLANES 0x20u   /* require the bit-plane resident interpreter (d = 2, 3; else SDIMB_ETOOBIG) */
 #define SDIMB_SCHEDULED 0x40u      /* `ops` is the output of sdimb_schedule: the bit-plane interpreter may run
-                                      SDIMB_SCHED_WARPS warps per shot, one commuting layer at a time */
+                                      SDIMB_SCHED_WARPS warps per shot, one commuting layer at a time; the cluster
+                                      interpreter deals each layer over its gate groups */
+#define SDIMB_CLUSTER 0x80u        /* HBM store: run one shot per thread-block cluster whatever n and shots are
+                                      (default: only for n > 512 with fewer shots than clusters fit on the GPU) */
+#define SDIMB_NO_CLUSTER 0x100u    /* HBM store: never use the cluster interpreter */
 
 typedef struct SdimbLayout {
   int32_t n, d, np, lanes;   /* lanes = W = 2*np */
@@ -178,13 +185,18 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
  * shots from an atomic counter (shots differ in cost when noise fires); without it they grid-stride. */
 int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags);
 
-/* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store,
- * 1 uint8 lanes resident in shared memory, 2 bit-plane resident (d = 2, 3); *needs_tableau = whether
- * SdimbRunArgs.tableau must be a valid store for these flags. */
+/* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store (one CTA or
+ * one thread-block cluster per shot, chosen per call from n and shots), 1 uint8 lanes resident in shared memory,
+ * 2 bit-plane resident (d = 2, 3); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for
+ * these flags. */
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t sdimb_launch_count(void);
+
+/* Cluster size sdimb_run would give the cluster interpreter for (n, d, shots, flags) on the current device;
+ * 0 = that call runs one CTA per shot (or another interpreter).  Needs a CUDA device (else 0). */
+int sdimb_cluster_size(int n, int d, int64_t shots, uint32_t flags);
 
 #ifdef __cplusplus
 }

@@ -8,13 +8,13 @@ from .build import LIB_PATH
 
 OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
 FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT, FORCE_LANES, FORCE_PLANES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
-SCHEDULED = 0x40
+SCHEDULED, CLUSTER, NO_CLUSTER = 0x40, 0x80, 0x100
 OP_BARRIER = 18
 KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
-                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes")
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes", "sdimb_cluster_size")
 
 
 class SdimbLayout(C.Structure):
@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
                                C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]
     L.sdimb_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_uint32]
     L.sdimb_scratch_bytes.restype = C.c_int64
+    L.sdimb_cluster_size.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint32]
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L

@@ -1,0 +1,309 @@
+// Cluster interpreter: ONE tableau per thread-block cluster, for tableaus too large for one SM to serve.
+// Part of libsdimb (sdim_b200/csrc); included by sdimb.cu inside its anonymous namespace.
+//
+// A single large tableau (config 5: n = 4096, d = 5 / 7, 64 MiB) gives the one-CTA interpreter of lanes.cuh
+// one SM's worth of L2 bandwidth (~100 GB/s): a pivot-column walk alone moves 16 K sectors.  Here a cluster of
+// C CTAs (8 portable, 16 with the non-portable opt-in; all on one GPC) owns the shot:
+//
+//   gates         lane-partitioned: CTA c owns lane words [c*wpc, (c+1)*wpc) of EVERY row.  Generator lanes are
+//                 independent under gates, so CTAs never talk during a gate segment.  Inside a CTA the threads
+//                 form `ngroups` = blockDim / wpc groups; on a scheduled stream (sdimb_schedule: layers of gates
+//                 on disjoint qudits) group g executes the gates whose index in the layer is g mod ngroups, one
+//                 lane word per thread, so ngroups * C gates are in flight per layer.  A thread accumulates its
+//                 phase increments in a register; increments are folded into the phase words of the HBM store
+//                 before the next measurement.
+//   measurement   row-partitioned: CTA c owns rows [c*rpc, (c+1)*rpc) for the pivot-column walk, the rank-1
+//                 update and the column writes.  Row q (pivot search, factors) is read by every CTA.  Partial
+//                 dot products, x_p . z_p and the deterministic-branch sums are reduced with distributed-shared-
+//                 memory atomics into the CTA that owns the lane word (phases are lane-partitioned like gates).
+//
+// Synchronisation is the hardware cluster barrier (release/acquire at cluster scope, ~0.2 us):
+//   A   before a measurement that follows gates (lane-partitioned writes -> row-partitioned reads)
+//   B1  random branch only: every CTA has read row q before its owner updates it
+//   B2  partial sums have arrived in their owners' shared memory
+// Nothing else: after B2 a CTA only writes phase words it owns, which no other CTA reads before the next B2
+// (the old pivot phase travels through shared memory), so back-to-back measurements cost one or two barriers
+// and gates after a measurement need none.  All cluster-shared accumulators are double-buffered by measurement
+// parity and zeroed by their owner when consumed: a CTA that races ahead into measurement k+1 adds into the
+// other buffer, and cannot reach measurement k+2 before every CTA has finished k.
+//
+// Same arithmetic as lanes.cuh (its helpers are reused); same reference behaviour (file:line citations there).
+#pragma once
+
+namespace clusters {
+
+namespace cg = cooperative_groups;
+
+constexpr int kClusterThreads = 1024;
+
+struct CScratch : Scratch {
+  uint32_t* dotg;   // [2][4*wpc] cluster-reduced dot products of the lane words this CTA owns (DSMEM target)
+  uint32_t* acc;    // [blockDim] phase increments of the gate groups, staged for the fold
+  uint32_t* xch;    // [2][4]     cluster accumulators: x_p . z_p | old pivot phase | det a1 | det rows (DSMEM target)
+};
+
+struct CGeo {
+  int c, C;         // rank in cluster, cluster size
+  int wpc;          // lane words per CTA (multiple of 32)
+  int r0, r1;       // rows owned in measurements
+  int group, ngroups, w;   // gate group of this thread, groups per CTA, lane word owned (>= W/4: none)
+};
+
+// bytes of dynamic shared memory per CTA
+inline size_t cluster_smem_bytes(int np, int wpc) {
+  const size_t W = 2 * (size_t)np, wz = W / 4;
+  return 4 * W + 4 * wz + 4 * 8 * (size_t)wpc + 4 * kClusterThreads + 4 * 32 + 4 * 4 + 4 * 8   // dot fw dotg acc red cnt xch
+         + 2 * (size_t)np + 2 * (size_t)np + 2 * wz + (size_t)np + (size_t)np + 128 + 64;       // ar br aw xs zs inv
+}
+
+// lane words per CTA for a cluster of C: ceil(wz / C) rounded up to whole warps
+inline int cluster_wpc(int np, int C) {
+  const int wz = np / 2;
+  return ((wz + C - 1) / C + 31) / 32 * 32;
+}
+
+// Fold the gate groups' phase increments into the phase words this CTA owns.
+__device__ __forceinline__ void fold_phases(uint8_t* T, const KParams& p, CScratch& S, const CGeo& g, uint32_t& pw) {
+  const Swar So = make_swar(p.A.order);
+  S.acc[threadIdx.x] = pw;
+  pw = 0u;
+  __syncthreads();
+  if ((int)threadIdx.x < g.wpc && g.w < p.W / 4) {
+    uint32_t sum = 0u;
+    for (int k = 0; k < g.ngroups; ++k) sum = swar_add(So, sum, S.acc[k * g.wpc + threadIdx.x]);
+    if (sum) {
+      uint32_t* Pw = reinterpret_cast<uint32_t*>(T + p.phase_off) + g.w;
+      *Pw = swar_add(So, *Pw, sum);
+    }
+  }
+  __syncthreads();
+}
+
+// Measurement of qudit q in the Z basis (tableau_prime.py:262-363) by the whole cluster.  `par` = parity of this
+// measurement (selects the cluster accumulators).  The caller has made all earlier writes cluster-visible.
+__device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p, CScratch& S, const CGeo& g,
+                            uint32_t par, int q, int64_t slot, int64_t shot_local, uint32_t draw) {
+  const Arith& A = p.A;
+  const int npad = p.np, tid = threadIdx.x;
+  const int wz = p.W / 4;
+  uint8_t* rowq = T + (int64_t)q * p.row_bytes;
+  uint8_t* P8 = T + p.phase_off;
+  uint32_t* xch = S.xch + 4 * par;
+  uint32_t* dotg = S.dotg + (size_t)par * 4 * g.wpc;
+  if (tid < 3) S.cnt[tid] = 0;
+  __syncthreads();
+
+  // every CTA finds the pivot itself: same row, same answer, no exchange
+  const uint32_t piv = block_min(pivot_candidate(rowq, p), S.red);
+
+  uint32_t outcome, rec;
+  if (piv != kNoPivot) {
+    // -- random branch (tableau_prime.py:294-334) ---------------------------------------------------------
+    const uint32_t e = S.inv[rowq[piv]];
+    factor_words(rowq, p, S, piv);                             // whole row q, redundantly per CTA
+    const int own_p = (int)(piv >> 2) / g.wpc, own_d = (int)((npad + piv) >> 2) / g.wpc;
+    // the old pivot phase is only safe to read in the CTA that owns its word: broadcast it
+    if (g.c == own_p && tid < g.C) *cl.map_shared_rank(xch + 1, tid) = P8[piv];
+    cl.sync();                                                 // B1: row q has been read everywhere
+    uint32_t sd_raw = column_walk(T, p, S, piv, e, g.r0, g.r1);
+    sd_raw = mod_d(A, block_sum(sd_raw, S.red));               // barrier: publishes xs/zs/ar/br/fw/aw/dot/cnt
+    const int nr_a = (int)S.cnt[0], nw_a = (int)S.cnt[1];
+    rank1_update(T, p, S, nr_a, nw_a);                         // own rows x all active lane words
+    __syncthreads();
+    column_writes(T, p, S, q, piv, nr_a, (int)S.cnt[2]);       // own rows
+    if (nr_a > 0) {                                            // partial dots -> owners of the lane words
+      for (int i = tid; i < nw_a; i += blockDim.x) {
+        const int w = S.aw[i], o = w / g.wpc;
+        uint32_t* dst = cl.map_shared_rank(dotg, o) + 4 * (w - o * g.wpc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t v = mod_d(A, S.dot[4 * w + k]);
+          if (v) atomicAdd(dst + k, v);
+        }
+      }
+    }
+    if (tid < g.C && sd_raw) atomicAdd(cl.map_shared_rank(xch, tid), sd_raw);
+    cl.sync();                                                 // B2: sums are complete
+    const uint32_t sd_all = mod_d(A, xch[0]), ps_old = xch[1];
+    const uint32_t ps = mod_o(A, ps_old * e + A.po * mod_d(A, sd_all * mod_d(A, (e * (e - 1u)) >> 1)));
+    const uint32_t sd = mod_d(A, mod_d(A, sd_all * e) * e);    // x_p . z_p after exponentiation
+    if (tid < g.wpc && g.w < wz) {                             // phases of the lane words this CTA owns
+      const uint32_t fw = S.fw[g.w];
+      if (fw) {
+        uint32_t* Pw = reinterpret_cast<uint32_t*>(P8) + g.w;
+        uint32_t* dg = dotg + 4 * tid;
+        *Pw = phase_word_update(A, fw, *Pw, dg, sd, ps);
+        *reinterpret_cast<uint4*>(dg) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    outcome = draw;
+    __syncthreads();
+    if (tid == 0) {
+      xch[0] = 0;
+      if (g.c == own_d) P8[npad + piv] = (uint8_t)ps;                           // destabilizer p <- old pivot (phase)
+      if (g.c == own_p) P8[piv] = (uint8_t)mod_o(A, A.order - outcome * A.po);  // stabilizer p <- Z_q, phase -m*po
+    }
+    rec = outcome;
+  } else {
+    // -- deterministic branch (tableau_prime.py:336-363): nothing is written to the tableau --------------
+    uint32_t a1;
+    const int total = det_list(rowq, P8, p, S, g.c * g.wpc, (g.c + 1) * g.wpc, a1);   // phases of owned words only
+    a1 = mod_o(A, block_sum(mod_o(A, a1), S.red));
+    const uint32_t part = mod_d(A, block_sum(det_rows(T, p, S, total, g.r0, g.r1), S.red));
+    if (tid < g.C) {
+      if (a1) atomicAdd(cl.map_shared_rank(xch + 2, tid), a1);
+      if (part) atomicAdd(cl.map_shared_rank(xch + 3, tid), part);
+    }
+    cl.sync();                                                 // B2
+    const uint32_t ap = mod_o(A, mod_o(A, xch[2]) + A.po * mod_d(A, xch[3]));
+    outcome = (A.po == 1) ? neg_d(A, ap) : (((ap + 1u) >> 1) & 1u);   // (-ap // po) % d  (tableau_prime.py:362)
+    rec = outcome | SDIMB_REC_DET;
+    __syncthreads();
+    if (tid == 0) xch[2] = xch[3] = 0;
+  }
+  if (g.c == 0 && tid == 0) p.records[shot_local * p.rec_stride + slot] = (uint8_t)rec;
+  __syncthreads();
+  return outcome;
+}
+
+__global__ void __launch_bounds__(kClusterThreads, 1) interp_cluster_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  cg::cluster_group cl = cg::this_cluster();
+  const Arith& A = p.A;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int wz = p.W / 4;
+  CGeo g;
+  g.c = (int)cl.block_rank();
+  g.C = (int)cl.num_blocks();
+  g.wpc = p.wpc;
+  const int rpc = (p.n + g.C - 1) / g.C;
+  g.r0 = min(p.n, g.c * rpc);
+  g.r1 = min(p.n, g.r0 + rpc);
+  g.ngroups = nt / g.wpc;
+  g.group = tid / g.wpc;
+  g.w = g.group < g.ngroups ? g.c * g.wpc + tid % g.wpc : wz;
+  // gate groups only help on a layered stream; on a plain stream group 0 runs every gate in order
+  const bool layered = (p.flags & SDIMB_SCHEDULED) != 0 && g.ngroups > 1;
+  // does this warp execute gates at all?  (warps are whole groups; the last CTAs may own no lane word)
+  const bool warp_gates = __any_sync(0xFFFFFFFFu, g.w < wz) && (layered || g.group == 0);
+
+  CScratch S;
+  S.dot = reinterpret_cast<uint32_t*>(smem);
+  S.fw = S.dot + p.W;
+  S.dotg = S.fw + wz;
+  S.acc = S.dotg + 8 * g.wpc;
+  S.red = S.acc + kClusterThreads;
+  S.cnt = S.red + 32;
+  S.xch = S.cnt + 4;
+  S.ops = nullptr;
+  S.ar = reinterpret_cast<uint16_t*>(S.xch + 8);
+  S.br = S.ar + p.np;
+  S.aw = S.br + p.np;
+  S.xs = reinterpret_cast<uint8_t*>(S.aw + wz);
+  S.zs = S.xs + p.np;
+  S.inv = S.zs + p.np;
+
+  for (uint32_t v = tid; v < A.d; v += nt) {                  // inverse table; inv[0] unused
+    uint32_t e = 0;
+    for (uint32_t c2 = 1; c2 < A.d; ++c2)
+      if (mod_d(A, v * c2) == 1u) { e = c2; break; }
+    S.inv[v] = (uint8_t)e;
+  }
+  for (int i = tid; i < 8 * g.wpc; i += nt) S.dotg[i] = 0u;
+  if (tid < 8) S.xch[tid] = 0u;
+  cl.sync();                                                   // accumulators are zero before any CTA adds into them
+
+  const int64_t n_clusters = gridDim.x / g.C, cluster_id = blockIdx.x / g.C;
+  uint32_t par = 0;                                            // measurement parity, uniform over the cluster
+  for (int64_t shot = cluster_id; shot < p.shots; shot += n_clusters) {
+    uint8_t* T = p.tab + shot * p.shot_bytes;
+    if (p.flags & SDIMB_FRESH) {                               // |0...0>, split over the cluster
+      uint4* v = reinterpret_cast<uint4*>(T);
+      const int64_t nvec = p.shot_bytes / 16;
+      for (int64_t i = (int64_t)g.c * nt + tid; i < nvec; i += (int64_t)g.C * nt) v[i] = make_uint4(0, 0, 0, 0);
+      cl.sync();
+      for (int q = g.c * nt + tid; q < p.n; q += g.C * nt) {
+        uint8_t* row = T + (int64_t)q * p.row_bytes;
+        row[p.W + q] = 1;      // Z[q][stab q]
+        row[p.np + q] = 1;     // X[q][destab q]
+      }
+      cl.sync();
+    }
+    uint32_t pw = 0u;                                          // this thread's phase increments since the last fold
+    bool dirty = false;                                        // gates since the last fold (uniform over the cluster)
+
+    for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
+      // every warp fetches the same 32 ops, one per lane, and keeps the collective ops plus its group's gates;
+      // the fetching lane resolves N1 events and measurement draws
+      int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
+      if (i0 + lane < p.n_ops) mine = __ldg(p.ops + i0 + lane);
+      const int idx = (int)(((uint32_t)mine.x) >> SDIMB_OP_INDEX_SHIFT);
+      mine.x &= SDIMB_OP_MASK;
+      const bool meas = mine.x >= SDIMB_OP_M && mine.x <= SDIMB_OP_RESET;
+      const bool is_gate = mine.x != SDIMB_OP_I && !meas && mine.x != SDIMB_OP_BARRIER;
+      bool live = meas || (mine.x == SDIMB_OP_BARRIER && layered) ||
+                  (is_gate && warp_gates && (!layered || idx % g.ngroups == g.group));
+      if (live && mine.x == SDIMB_OP_N1) {
+        mine.z = (int)noise_event(p, mine.w, shot);
+        live = mine.z != 0;
+      }
+      if (meas) {                                              // outcome this measurement takes if it is random
+        if (p.replay_meas) {
+          mine.z = p.replay_meas[shot * p.n_meas + mine.w];
+        } else {
+          const uint64_t gshot = (uint64_t)(p.shot_offset + shot);
+          const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)mine.w, 0u, (uint32_t)p.seed,
+                                     (uint32_t)(p.seed >> 32));
+          mine.z = (int)__umulhi(r.x, A.d);
+        }
+      }
+      uint32_t todo = __ballot_sync(0xFFFFFFFFu, live);
+      // positions of gates (executed by ANY group) not yet covered by a fold: identical in every warp of the cluster
+      uint32_t pending = __ballot_sync(0xFFFFFFFFu, is_gate);
+#pragma unroll 1
+      while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        int4 op;
+        op.x = __shfl_sync(0xFFFFFFFFu, mine.x, k);
+        op.y = __shfl_sync(0xFFFFFFFFu, mine.y, k);
+        op.z = __shfl_sync(0xFFFFFFFFu, mine.z, k);
+        op.w = __shfl_sync(0xFFFFFFFFu, mine.w, k);
+        if (is_unitary_like(op.x)) {
+          uint32_t pa, pb;
+          pauli_exponents(p, op, pa, pb);
+          if (g.w < wz) pw = gate_word(T, p, op.x, op.y, op.z, pa, pb, load_rows(T, p, op.x, op.y, op.z, g.w), g.w, pw);
+          continue;
+        }
+        if (op.x == SDIMB_OP_BARRIER) { __syncthreads(); continue; }
+        // collective ops: M, M_X, RESET
+        const uint32_t below = (1u << k) - 1u;
+        bool after_gates = dirty || (pending & below) != 0;
+        pending &= ~below;
+        if (op.x == SDIMB_OP_M_X) {                            // tableau_gates.py:292-296: H^-1, then measure
+          if (g.group == 0 && g.w < wz)
+            pw = gate_word(T, p, SDIMB_OP_H_INV, op.y, -1, 0u, 0u, load_rows(T, p, SDIMB_OP_H_INV, op.y, -1, g.w), g.w, pw);
+          after_gates = true;
+        }
+        if (after_gates) {
+          fold_phases(T, p, S, g, pw);
+          cl.sync();                                           // A: lane-partitioned writes -> row-partitioned reads
+        }
+        const uint32_t m = measure(cl, T, p, S, g, par, op.y, op.w, shot, (uint32_t)op.z);
+        par ^= 1u;
+        dirty = false;
+        if (op.x == SDIMB_OP_RESET && m) {                     // program.py:335-339: X^(-m) brings the qudit to |0>
+          if (g.group == 0 && g.w < wz)
+            pw = gate_word(T, p, SDIMB_OP_N1, op.y, -1, A.d - m, 0u, load_rows(T, p, SDIMB_OP_N1, op.y, -1, g.w), g.w, pw);
+          dirty = true;
+        }
+      }
+      dirty = dirty || pending != 0;                           // gates behind the batch's last measurement
+    }
+    fold_phases(T, p, S, g, pw);
+    cl.sync();                                                 // the shot is complete in the store
+  }
+  cl.sync();                                                   // no CTA leaves while its shared memory may be addressed
+}
+
+}  // namespace clusters

@@ -82,4 +82,5 @@ struct KParams {
   int resident;
   int vec;                     // lane interpreter: lane words per thread (1, or 4 with 128-bit accesses)
   unsigned int* shot_counter;  // bit-plane kernel: next unclaimed shot (nullable: static grid-stride)
+  int wpc;                     // cluster interpreter: lane words owned by each CTA of the cluster
 };

@@ -281,26 +281,249 @@ __device__ __forceinline__ uint32_t noise_event(const KParams& p, int64_t j, int
 constexpr int kBatch = 4;
 constexpr int kWalk = 4;     // rows per thread whose column loads are issued together
 
+// The pieces of a measurement.  They take explicit row / lane ranges so that the one-CTA interpreter below (whole
+// tableau) and the cluster interpreter in clusters.cuh (one slice of the rows per CTA) share them.
+
+// Pivot: FIRST stabilizer with an X component on q (tableau_prime.py:273-283).  Thread-local candidate; the caller
+// reduces it with block_min.
+__device__ __forceinline__ uint32_t pivot_candidate(const uint8_t* rowq, const KParams& p) {
+  const uint32_t* xq = reinterpret_cast<const uint32_t*>(rowq);
+  for (int w = threadIdx.x; w < p.np / 4; w += blockDim.x) {
+    const uint32_t x = xq[w];
+    if (x) return 4u * w + ((__ffs(x) - 1) >> 3);
+  }
+  return kNoPivot;
+}
+
+// One walk down the pivot column AND the destabilizer-p column over rows [r_lo, r_hi) (kWalk rows' loads in flight
+// per thread): xs/zs (exponentiate, tableau_prime.py:365-380, folded in), the support list `ar` (count cnt[0]), and
+// the list `br` (count cnt[2]) of rows outside the support whose destabilizer-p entry is non-zero and must be
+// cleared when the destabilizer is overwritten with the pivot.  Returns this thread's share of x_p . z_p.
+__device__ __forceinline__ uint32_t column_walk(const uint8_t* T, const KParams& p, Scratch& S, uint32_t piv,
+                                                uint32_t e, int r_lo, int r_hi) {
+  const Arith& A = p.A;
+  const int W = p.W, npad = p.np, nt = blockDim.x;
+  uint32_t sd_raw = 0;
+  for (int base = r_lo + threadIdx.x; base < r_hi; base += nt * kWalk) {
+    uint32_t xr[kWalk], zr[kWalk], od[kWalk];
+#pragma unroll
+    for (int u = 0; u < kWalk; ++u) {
+      const int r = base + u * nt;
+      xr[u] = zr[u] = od[u] = 0;
+      if (r < r_hi) {
+        const uint8_t* row = T + (int64_t)r * p.row_bytes;
+        xr[u] = row[piv]; zr[u] = row[W + piv];
+        od[u] = (uint32_t)row[npad + piv] | row[W + npad + piv];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kWalk; ++u) {
+      const int r = base + u * nt;
+      if (r >= r_hi) break;
+      S.xs[r] = (uint8_t)mod_d(A, xr[u] * e);
+      S.zs[r] = (uint8_t)mod_d(A, zr[u] * e);
+      sd_raw += mod_d(A, xr[u] * zr[u]);
+      if (xr[u] | zr[u]) S.ar[atomicAdd(&S.cnt[0], 1u)] = (uint16_t)r;
+      else if (od[u]) S.br[atomicAdd(&S.cnt[2], 1u)] = (uint16_t)r;
+    }
+  }
+  return sd_raw;
+}
+
+// Factors f = -X[q,i] mod d of every lane but the pivot, packed per lane word (fw), the active-word list `aw`
+// (count cnt[1]) and zeroed dot accumulators of the active words.
+__device__ __forceinline__ void factor_words(const uint8_t* rowq, const KParams& p, Scratch& S, uint32_t piv) {
+  const Arith& A = p.A;
+  for (int w = threadIdx.x; w < p.W / 4; w += blockDim.x) {
+    const uint32_t xq_w = reinterpret_cast<const uint32_t*>(rowq)[w];
+    uint32_t fw = 0;
+    if (xq_w) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (4u * w + k != piv) fw |= neg_d(A, byte_of(xq_w, k)) << (8 * k);   // the pivot itself is skipped
+    }
+    S.fw[w] = fw;
+    if (fw) {
+      S.aw[atomicAdd(&S.cnt[1], 1u)] = (uint16_t)w;
+      *reinterpret_cast<uint4*>(S.dot + 4 * w) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+// col_i += f_i * col_p over all (active row, active word) pairs; pair id = ri * nw_a + wi.  Partial dot products
+// Z[:,i] . x_p (old Z) of the rows in `ar` are added to S.dot.
+__device__ __forceinline__ void rank1_update(uint8_t* T, const KParams& p, Scratch& S, int nr_a, int nw_a) {
+  const Arith& A = p.A;
+  const int nt = blockDim.x, tid = threadIdx.x, wz = p.W / 4;
+  if (nw_a <= 0) return;
+  const int npairs = nr_a * nw_a;
+  const int dw = nt % nw_a, dr = nt / nw_a;
+  int wi = tid % nw_a, ri = tid / nw_a;
+  int cur_w = -1;
+  uint32_t dot0 = 0, dot1 = 0, dot2 = 0, dot3 = 0;
+  for (int base = tid; base < npairs; base += nt * kBatch) {
+    uint32_t xw[kBatch], zw[kBatch];
+    int rr[kBatch], ww[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      rr[u] = -1;
+      if (base + u * nt < npairs) {
+        rr[u] = S.ar[ri];
+        ww[u] = S.aw[wi];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(T + (int64_t)rr[u] * p.row_bytes) + ww[u];
+        xw[u] = src[0];
+        zw[u] = src[wz];
+        wi += dw; ri += dr;
+        if (wi >= nw_a) { wi -= nw_a; ++ri; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (rr[u] < 0) continue;
+      if (ww[u] != cur_w) {
+        if (cur_w >= 0) {
+          atomicAdd(&S.dot[4 * cur_w + 0], dot0); atomicAdd(&S.dot[4 * cur_w + 1], dot1);
+          atomicAdd(&S.dot[4 * cur_w + 2], dot2); atomicAdd(&S.dot[4 * cur_w + 3], dot3);
+        }
+        cur_w = ww[u]; dot0 = dot1 = dot2 = dot3 = 0;
+      }
+      const uint32_t s = S.xs[rr[u]], t = S.zs[rr[u]], fw = S.fw[ww[u]];
+      const uint32_t z0 = byte_of(zw[u], 0), z1 = byte_of(zw[u], 1), z2 = byte_of(zw[u], 2), z3 = byte_of(zw[u], 3);
+      dot0 = mod_d(A, dot0 + z0 * s); dot1 = mod_d(A, dot1 + z1 * s);    // Z[:,i] . x_p (old Z)
+      dot2 = mod_d(A, dot2 + z2 * s); dot3 = mod_d(A, dot3 + z3 * s);
+      uint32_t nx = 0, nz = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t fk = byte_of(fw, k);
+        nx |= mod_d(A, byte_of(xw[u], k) + fk * s) << (8 * k);
+        nz |= mod_d(A, byte_of(zw[u], k) + fk * t) << (8 * k);
+      }
+      uint32_t* dst = reinterpret_cast<uint32_t*>(T + (int64_t)rr[u] * p.row_bytes) + ww[u];
+      dst[0] = nx;
+      dst[wz] = nz;
+    }
+  }
+  if (cur_w >= 0) {
+    atomicAdd(&S.dot[4 * cur_w + 0], dot0); atomicAdd(&S.dot[4 * cur_w + 1], dot1);
+    atomicAdd(&S.dot[4 * cur_w + 2], dot2); atomicAdd(&S.dot[4 * cur_w + 3], dot3);
+  }
+}
+
+// New phase word of four generators:
+// phase_i += f_i * phase_p + po * (f_i * (Z_i . x_p) + (x_p . z_p) * f_i(f_i-1)/2 * po)     (:310-312,317-319)
+__device__ __forceinline__ uint32_t phase_word_update(const Arith& A, uint32_t fw, uint32_t ph, const uint32_t* dot4,
+                                                      uint32_t sd, uint32_t ps) {
+  uint32_t nph = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t fk = byte_of(fw, k);
+    const uint32_t g = mod_d(A, (fk * (fk - 1u)) >> 1);
+    const uint32_t cp = mod_d(A, mod_d(A, dot4[k]) * fk + sd * g * A.po);
+    nph |= mod_o(A, byte_of(ph, k) + fk * ps + A.po * cp) << (8 * k);
+  }
+  return nph;
+}
+
+// destabilizer p <- old pivot, stabilizer p <- Z_q (tableau_prime.py:323-333) on the rows of the lists.
+// Column accesses cost one DRAM sector per byte, so only entries that change are written: both lanes are
+// rewritten on the pivot's support (list ar), stale destabilizer entries elsewhere (list br) are cleared.
+__device__ __forceinline__ void column_writes(uint8_t* T, const KParams& p, Scratch& S, int q, uint32_t piv, int nr_a,
+                                              int nr_b) {
+  const int W = p.W, npad = p.np;
+  for (int i = threadIdx.x; i < nr_a; i += blockDim.x) {
+    const int r = S.ar[i];
+    uint8_t* row = T + (int64_t)r * p.row_bytes;
+    row[piv] = 0;
+    row[W + piv] = (r == q) ? 1 : 0;
+    row[npad + piv] = S.xs[r];
+    row[W + npad + piv] = S.zs[r];
+  }
+  for (int i = threadIdx.x; i < nr_b; i += blockDim.x) {
+    uint8_t* row = T + (int64_t)S.br[i] * p.row_bytes;
+    row[npad + piv] = 0;
+    row[W + npad + piv] = 0;
+  }
+}
+
+// Deterministic branch, part 1: ordered compaction of the generators with a non-zero factor f_i = destab X[q,i]
+// into S.ar / S.xs (order matters: the cross term uses the running ancilla, :354-357).  Returns the list length;
+// `a1` receives this thread's share of sum_i f_i * phase_i over the generators whose phase word lies in
+// [pw_lo, pw_hi).  Contains block barriers: call it from uniform code.
+__device__ __forceinline__ int det_list(const uint8_t* rowq, const uint8_t* P8, const KParams& p, Scratch& S,
+                                        int pw_lo, int pw_hi, uint32_t& a1) {
+  const int n = p.n, npad = p.np, nt = blockDim.x, tid = threadIdx.x;
+  int total = 0;
+  a1 = 0;
+  __syncthreads();   // every warp has finished reading S.red in block_min before it is reused below
+  for (int base = 0; base < n; base += nt) {
+    const int i = base + tid;
+    const uint32_t f = (i < n) ? rowq[npad + i] : 0u;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, f != 0);
+    if ((tid & 31) == 0) S.red[tid >> 5] = __popc(mask);
+    __syncthreads();
+    // exclusive scan of the per-warp counts, done by every warp with shuffles
+    const int lane_id = tid & 31;
+    const int mine_cnt = lane_id < (nt >> 5) ? (int)S.red[lane_id] : 0;
+    int incl = mine_cnt;
+#pragma unroll
+    for (int d2 = 1; d2 < 32; d2 <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d2);
+      if (lane_id >= d2) incl += o;
+    }
+    const int off = total + __shfl_sync(0xFFFFFFFFu, incl - mine_cnt, tid >> 5);
+    const int all = total + __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (f) {
+      const int pos = off + __popc(mask & ((1u << (tid & 31)) - 1u));
+      S.ar[pos] = (uint16_t)i;
+      S.xs[pos] = (uint8_t)f;
+      if ((i >> 2) >= pw_lo && (i >> 2) < pw_hi) a1 += f * P8[i];
+    }
+    total = all;
+    __syncthreads();
+  }
+  return total;
+}
+
+// Deterministic branch, part 2: this thread's share, over rows [r_lo, r_hi), of
+// sum_r ( ancilla_z . (f * x_i) + po * (x_i . z_i) * f(f-1)/2 ) accumulated over the list in order.
+__device__ __forceinline__ uint32_t det_rows(const uint8_t* T, const KParams& p, const Scratch& S, int total,
+                                             int r_lo, int r_hi) {
+  const Arith& A = p.A;
+  uint32_t part = 0;
+  for (int r = r_lo + threadIdx.x; r < r_hi; r += blockDim.x) {
+    const uint8_t* xr = T + (int64_t)r * p.row_bytes;
+    const uint8_t* zr = xr + p.W;
+    uint32_t az = 0, cross = 0, sdg = 0;
+    for (int base = 0; base < total; base += kBatch) {
+      uint32_t xi[kBatch], zi[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+        if (base + u < total) { const int g = S.ar[base + u]; xi[u] = xr[g]; zi[u] = zr[g]; }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (base + u >= total) break;
+        const uint32_t f = S.xs[base + u];
+        cross = mod_d(A, cross + mod_d(A, f * xi[u]) * az);  // ancilla_z . (f * x_i), running ancilla
+        az = mod_d(A, az + f * zi[u]);
+        sdg = mod_d(A, sdg + mod_d(A, xi[u] * zi[u]) * mod_d(A, (f * (f - 1u)) >> 1));
+      }
+    }
+    part += mod_d(A, cross + A.po * sdg);
+  }
+  return part;
+}
+
 __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int64_t slot, int64_t shot_local,
                             uint32_t draw) {
   const Arith& A = p.A;
-  const int n = p.n, W = p.W, npad = p.np, nt = blockDim.x, tid = threadIdx.x;
-  const int wz = W / 4;
+  const int n = p.n, npad = p.np, nt = blockDim.x, tid = threadIdx.x;
+  const int wz = p.W / 4;
   uint8_t* rowq = T + (int64_t)q * p.row_bytes;
   uint8_t* P8 = T + p.phase_off;
   if (tid < 3) S.cnt[tid] = 0;   // cnt[3] holds the live-op mask of the current batch
   __syncthreads();   // gate writes of other threads' lanes become visible; counters reset
 
-  // -- pivot: FIRST stabilizer with an X component on q (tableau_prime.py:273-283) ------------------
-  uint32_t best = kNoPivot;
-  {
-    const uint32_t* xq = reinterpret_cast<const uint32_t*>(rowq);
-    for (int w = tid; w < npad / 4; w += nt) {
-      const uint32_t x = xq[w];
-      if (x) { best = 4u * w + ((__ffs(x) - 1) >> 3); break; }
-    }
-  }
-  const uint32_t piv = block_min(best, S.red);
+  const uint32_t piv = block_min(pivot_candidate(rowq, p), S.red);
 
   uint32_t outcome, rec;
   if (piv != kNoPivot) {
@@ -308,203 +531,33 @@ __device__ uint32_t measure(uint8_t* T, const KParams& p, Scratch& S, int q, int
     const uint32_t v = rowq[piv];
     const uint32_t e = S.inv[v];
     const uint32_t ps_old = P8[piv];
-    uint32_t sd_raw = 0;
-    // One walk down the pivot column AND the destabilizer-p column (kWalk rows' loads in flight per thread):
-    // xs/zs, the support list `ar`, and the list `br` of rows outside the support whose destabilizer-p entry is
-    // non-zero and must be cleared when the destabilizer is overwritten with the pivot.
-    for (int base = tid; base < n; base += nt * kWalk) {
-      uint32_t xr[kWalk], zr[kWalk], od[kWalk];
-#pragma unroll
-      for (int u = 0; u < kWalk; ++u) {
-        const int r = base + u * nt;
-        xr[u] = zr[u] = od[u] = 0;
-        if (r < n) {
-          const uint8_t* row = T + (int64_t)r * p.row_bytes;
-          xr[u] = row[piv]; zr[u] = row[W + piv];
-          od[u] = (uint32_t)row[npad + piv] | row[W + npad + piv];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kWalk; ++u) {
-        const int r = base + u * nt;
-        if (r >= n) break;
-        S.xs[r] = (uint8_t)mod_d(A, xr[u] * e);
-        S.zs[r] = (uint8_t)mod_d(A, zr[u] * e);
-        sd_raw += mod_d(A, xr[u] * zr[u]);
-        if (xr[u] | zr[u]) S.ar[atomicAdd(&S.cnt[0], 1u)] = (uint16_t)r;
-        else if (od[u]) S.br[atomicAdd(&S.cnt[2], 1u)] = (uint16_t)r;
-      }
-    }
-    for (int w = tid; w < wz; w += nt) {                      // factors f = -X[q,i] mod d, active-word list
-      const uint32_t xq_w = reinterpret_cast<const uint32_t*>(rowq)[w];
-      uint32_t fw = 0;
-      if (xq_w) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (4u * w + k != piv) fw |= neg_d(A, byte_of(xq_w, k)) << (8 * k);   // the pivot itself is skipped
-      }
-      S.fw[w] = fw;
-      if (fw) {
-        S.aw[atomicAdd(&S.cnt[1], 1u)] = (uint16_t)w;
-        *reinterpret_cast<uint4*>(S.dot + 4 * w) = make_uint4(0, 0, 0, 0);
-      }
-    }
+    uint32_t sd_raw = column_walk(T, p, S, piv, e, 0, n);
+    factor_words(rowq, p, S, piv);
     sd_raw = mod_d(A, block_sum(sd_raw, S.red));              // barrier: publishes xs/zs/ar/fw/aw/dot/cnt
     const uint32_t ps = mod_o(A, ps_old * e + A.po * mod_d(A, sd_raw * mod_d(A, (e * (e - 1u)) >> 1)));
     const uint32_t sd = mod_d(A, mod_d(A, sd_raw * e) * e);   // x_p . z_p after exponentiation
     const int nr_a = (int)S.cnt[0], nw_a = (int)S.cnt[1];
-
-    // col_i += f_i * col_p over all (active row, active word) pairs; pair id = ri * nw_a + wi
-    if (nw_a > 0) {
-      const int npairs = nr_a * nw_a;
-      const int dw = nt % nw_a, dr = nt / nw_a;
-      int wi = tid % nw_a, ri = tid / nw_a;
-      int cur_w = -1;
-      uint32_t dot0 = 0, dot1 = 0, dot2 = 0, dot3 = 0;
-      for (int base = tid; base < npairs; base += nt * kBatch) {
-        uint32_t xw[kBatch], zw[kBatch];
-        int rr[kBatch], ww[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          rr[u] = -1;
-          if (base + u * nt < npairs) {
-            rr[u] = S.ar[ri];
-            ww[u] = S.aw[wi];
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(T + (int64_t)rr[u] * p.row_bytes) + ww[u];
-            xw[u] = src[0];
-            zw[u] = src[wz];
-            wi += dw; ri += dr;
-            if (wi >= nw_a) { wi -= nw_a; ++ri; }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          if (rr[u] < 0) continue;
-          if (ww[u] != cur_w) {
-            if (cur_w >= 0) {
-              atomicAdd(&S.dot[4 * cur_w + 0], dot0); atomicAdd(&S.dot[4 * cur_w + 1], dot1);
-              atomicAdd(&S.dot[4 * cur_w + 2], dot2); atomicAdd(&S.dot[4 * cur_w + 3], dot3);
-            }
-            cur_w = ww[u]; dot0 = dot1 = dot2 = dot3 = 0;
-          }
-          const uint32_t s = S.xs[rr[u]], t = S.zs[rr[u]], fw = S.fw[ww[u]];
-          const uint32_t z0 = byte_of(zw[u], 0), z1 = byte_of(zw[u], 1), z2 = byte_of(zw[u], 2), z3 = byte_of(zw[u], 3);
-          dot0 = mod_d(A, dot0 + z0 * s); dot1 = mod_d(A, dot1 + z1 * s);    // Z[:,i] . x_p (old Z)
-          dot2 = mod_d(A, dot2 + z2 * s); dot3 = mod_d(A, dot3 + z3 * s);
-          uint32_t nx = 0, nz = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t fk = byte_of(fw, k);
-            nx |= mod_d(A, byte_of(xw[u], k) + fk * s) << (8 * k);
-            nz |= mod_d(A, byte_of(zw[u], k) + fk * t) << (8 * k);
-          }
-          uint32_t* dst = reinterpret_cast<uint32_t*>(T + (int64_t)rr[u] * p.row_bytes) + ww[u];
-          dst[0] = nx;
-          dst[wz] = nz;
-        }
-      }
-      if (cur_w >= 0) {
-        atomicAdd(&S.dot[4 * cur_w + 0], dot0); atomicAdd(&S.dot[4 * cur_w + 1], dot1);
-        atomicAdd(&S.dot[4 * cur_w + 2], dot2); atomicAdd(&S.dot[4 * cur_w + 3], dot3);
-      }
-    }
+    rank1_update(T, p, S, nr_a, nw_a);
     __syncthreads();
-    // phase_i += f_i * phase_p + po * (f_i * (Z_i . x_p) + (x_p . z_p) * f_i(f_i-1)/2 * po)     (:310-312,317-319)
     for (int i = tid; i < nw_a; i += nt) {
       const int w = S.aw[i];
-      const uint32_t fw = S.fw[w];
       uint32_t* Pw = reinterpret_cast<uint32_t*>(P8) + w;
-      const uint32_t ph = *Pw;
-      uint32_t nph = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t fk = byte_of(fw, k);
-        const uint32_t g = mod_d(A, (fk * (fk - 1u)) >> 1);
-        const uint32_t cp = mod_d(A, mod_d(A, S.dot[4 * w + k]) * fk + sd * g * A.po);
-        nph |= mod_o(A, byte_of(ph, k) + fk * ps + A.po * cp) << (8 * k);
-      }
-      *Pw = nph;
+      *Pw = phase_word_update(A, S.fw[w], *Pw, S.dot + 4 * w, sd, ps);
     }
     __syncthreads();
-    // destabilizer p <- old pivot, stabilizer p <- Z_q with phase -m*po (tableau_prime.py:323-333).
-    // Column accesses cost one DRAM sector per byte, so only entries that change are written: both lanes are
-    // rewritten on the pivot's support (list ar), stale destabilizer entries elsewhere (list br) are cleared.
-    const int nr_b = (int)S.cnt[2];
-    for (int i = tid; i < nr_a; i += nt) {
-      const int r = S.ar[i];
-      uint8_t* row = T + (int64_t)r * p.row_bytes;
-      row[piv] = 0;
-      row[W + piv] = (r == q) ? 1 : 0;
-      row[npad + piv] = S.xs[r];
-      row[W + npad + piv] = S.zs[r];
-    }
-    for (int i = tid; i < nr_b; i += nt) {
-      uint8_t* row = T + (int64_t)S.br[i] * p.row_bytes;
-      row[npad + piv] = 0;
-      row[W + npad + piv] = 0;
-    }
+    column_writes(T, p, S, q, piv, nr_a, (int)S.cnt[2]);
     outcome = draw;
     if (tid == 0) {
-      P8[npad + piv] = (uint8_t)ps;
-      P8[piv] = (uint8_t)mod_o(A, A.order - outcome * A.po);
+      P8[npad + piv] = (uint8_t)ps;                           // destabilizer p <- old pivot (phase)
+      P8[piv] = (uint8_t)mod_o(A, A.order - outcome * A.po);  // stabilizer p <- Z_q with phase -m*po
     }
     rec = outcome;
   } else {
     // -- deterministic branch (tableau_prime.py:336-363): ordered accumulation over generators ----------
-    // Ordered compaction of the generators with a non-zero factor f_i = destab X[q,i] (order matters: the
-    // cross term uses the running ancilla, :354-357).
-    uint32_t a1 = 0;
-    int total = 0;
-    __syncthreads();   // every warp has finished reading S.red in block_min before it is reused below
-    for (int base = 0; base < n; base += nt) {
-      const int i = base + tid;
-      const uint32_t f = (i < n) ? rowq[npad + i] : 0u;
-      const uint32_t mask = __ballot_sync(0xFFFFFFFFu, f != 0);
-      if ((tid & 31) == 0) S.red[tid >> 5] = __popc(mask);
-      __syncthreads();
-      // exclusive scan of the per-warp counts, done by every warp with shuffles
-      const int lane_id = tid & 31;
-      const int mine_cnt = lane_id < (nt >> 5) ? (int)S.red[lane_id] : 0;
-      int incl = mine_cnt;
-#pragma unroll
-      for (int d2 = 1; d2 < 32; d2 <<= 1) {
-        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d2);
-        if (lane_id >= d2) incl += o;
-      }
-      const int off = total + __shfl_sync(0xFFFFFFFFu, incl - mine_cnt, tid >> 5);
-      const int all = total + __shfl_sync(0xFFFFFFFFu, incl, 31);
-      if (f) {
-        const int pos = off + __popc(mask & ((1u << (tid & 31)) - 1u));
-        S.ar[pos] = (uint16_t)i;
-        S.xs[pos] = (uint8_t)f;
-        a1 += f * P8[i];
-      }
-      total = all;
-      __syncthreads();
-    }
+    uint32_t a1;
+    const int total = det_list(rowq, P8, p, S, 0, wz, a1);
     a1 = mod_o(A, block_sum(mod_o(A, a1), S.red));            // sum_i f_i * phase_i; publishes the lists
-    uint32_t part = 0;
-    for (int r = tid; r < n; r += nt) {
-      const uint8_t* xr = T + (int64_t)r * p.row_bytes;
-      const uint8_t* zr = xr + W;
-      uint32_t az = 0, cross = 0, sdg = 0;
-      for (int base = 0; base < total; base += kBatch) {
-        uint32_t xi[kBatch], zi[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          if (base + u < total) { const int g = S.ar[base + u]; xi[u] = xr[g]; zi[u] = zr[g]; }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          if (base + u >= total) break;
-          const uint32_t f = S.xs[base + u];
-          cross = mod_d(A, cross + mod_d(A, f * xi[u]) * az);  // ancilla_z . (f * x_i), running ancilla
-          az = mod_d(A, az + f * zi[u]);
-          sdg = mod_d(A, sdg + mod_d(A, xi[u] * zi[u]) * mod_d(A, (f * (f - 1u)) >> 1));
-        }
-      }
-      part += mod_d(A, cross + A.po * sdg);
-    }
-    part = mod_d(A, block_sum(part, S.red));
+    const uint32_t part = mod_d(A, block_sum(det_rows(T, p, S, total, 0, n), S.red));
     const uint32_t ap = mod_o(A, a1 + A.po * part);
     // (-ap // po) % d with Python floor semantics (tableau_prime.py:362)
     outcome = (A.po == 1) ? neg_d(A, ap) : (((ap + 1u) >> 1) & 1u);

@@ -6,6 +6,7 @@
 //   common.cuh        mod-d arithmetic, SWAR lanes, Philox4x32-10, kernel parameter block
 //   lanes.cuh         uint8-lane interpreter, any prime d <= 127 (shared memory or HBM store)
 //   planes.cuh        bit-plane interpreter for d = 2, 3 (shared-memory resident, 1 or 4 warps per shot)
+//   clusters.cuh      uint8-lane interpreter with one shot per thread-block cluster (large tableaus, few shots)
 //   util_kernels.cuh  |0...0> fill and export of the uint8 store
 //   frames.cuh        Pauli-frame sampler
 //
@@ -18,6 +19,7 @@
 #include "sdimb.h"
 
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <atomic>
@@ -31,6 +33,7 @@ namespace {
 
 #include "common.cuh"
 #include "lanes.cuh"
+#include "clusters.cuh"
 #include "planes.cuh"
 #include "util_kernels.cuh"
 #include "frames.cuh"
@@ -74,6 +77,47 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
   if ((flags & SDIMB_FORCE_RESIDENT) && !fits) return SDIMB_ETOOBIG;
   if (planes_fit && !(flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES))) return 2;
   return (fits && !(flags & SDIMB_FORCE_GLOBAL)) ? 1 : 0;
+}
+
+// Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
+// one CTA per shot.  By default only tableaus with rows wider than one 256-thread CTA (n > 512) and fewer shots
+// than clusters fit on the GPU: C = 16 (non-portable size) while shots * 16 fits on the SMs, then 8, 4, 2.
+// SDIMB_CLUSTER forces it (tests; size from the environment variable SDIMB_CLUSTER_SIZE, default 8).
+int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags, int sms) {
+  if (flags & SDIMB_NO_CLUSTER) return 0;
+  const bool forced = (flags & SDIMB_CLUSTER) != 0;
+  if (!forced && (L.lanes / 4 <= kMaxThreads || shots * 2 > sms)) return 0;
+  int want = 16;
+  if (forced) {
+    const char* env = std::getenv("SDIMB_CLUSTER_SIZE");
+    want = env ? std::atoi(env) : 8;
+    if (want != 1 && want != 2 && want != 4 && want != 8 && want != 16) want = 8;
+  } else {
+    while (want > 2 && shots * want > sms) want >>= 1;
+  }
+  auto kern = clusters::interp_cluster_kernel;
+  for (int C = want; C >= 1; C >>= 1) {
+    const int wpc = clusters::cluster_wpc(L.np, C);
+    const size_t smem = clusters::cluster_smem_bytes(L.np, wpc);
+    if (wpc > clusters::kClusterThreads || smem > (size_t)kSmemLimit) {
+      if (wpc > clusters::kClusterThreads) return 0;      // smaller clusters only make it worse
+      continue;
+    }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, C > 8 ? 1 : 0) != cudaSuccess) break;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(clusters::kClusterThreads);
+    cfg.dynamicSmemBytes = smem; cfg.attrs = attr; cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc >= 1) return C;
+    cudaGetLastError();
+    if (!forced && C == 2) break;
+  }
+  cudaGetLastError();
+  return 0;
 }
 
 }  // namespace
@@ -194,6 +238,28 @@ int sdimb_run(const SdimbRunArgs* a) {
     g_launches++;
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
   }
+  if (kernel == 0) {
+    const int C = plan_cluster(L, a->shots, a->flags, sms);
+    if (C >= 1) {                                    // one shot per thread-block cluster
+      auto kern = clusters::interp_cluster_kernel;
+      p.wpc = clusters::cluster_wpc(L.np, C);
+      const size_t smem = clusters::cluster_smem_bytes(L.np, p.wpc);
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(clusters::kClusterThreads);
+      cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)a->stream; cfg.attrs = attr; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); return SDIMB_ECUDA; }
+      const int64_t n_clusters = a->shots < nc ? a->shots : nc;
+      cfg.gridDim = dim3((unsigned)(n_clusters * C));
+      const cudaError_t err = cudaLaunchKernelEx(&cfg, kern, p);
+      g_launches++;
+      if (err != cudaSuccess) { cudaGetLastError(); return SDIMB_ECUDA; }
+      return SDIMB_OK;
+    }
+  }
   // wide rows streamed from the HBM store: 16 lanes per thread (fewer, fatter threads; 128-bit accesses)
   // ... when the stream is gate-dominated: measurements want many threads per shot, gates want few fat ones
   p.vec = (kernel == 0 && L.lanes / 4 >= 128 && L.lanes / 16 <= kMaxThreads && a->n_meas * 64 <= a->n_ops) ? 4 : 1;
@@ -300,14 +366,17 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   if (n_noise > 0 && !replay_noise && (!noise_thresh24 || !noise_channel)) return SDIMB_EINVAL;
   if (shots == 0) return SDIMB_OK;
 
-  const uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES | SDIMB_FORCE_PLANES);
+  const uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES |
+                                       SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER);
   const int kernel = plan_kernel(n, d, mode_flags, L.np);
   if (kernel < 0) return kernel;
   std::vector<int32_t> sched;
   const int32_t* up_ops = ops;
   int64_t up_n = n_ops;
   uint32_t sched_flag = 0;
-  if (kernel == 2 && n_ops > 0) {          // bit-plane interpreter: upload the layered stream
+  // bit-plane interpreter and cluster interpreter (wide rows on the HBM store): upload the layered stream
+  const bool maybe_cluster = kernel == 0 && !(flags & SDIMB_NO_CLUSTER) && (L.lanes / 4 > kMaxThreads || (flags & SDIMB_CLUSTER));
+  if ((kernel == 2 || maybe_cluster) && n_ops > 0) {
     sched.resize((size_t)(2 * n_ops + 1) * 4);
     rc = sdimb_schedule(n, ops, n_ops, sched.data(), 2 * n_ops + 1, &up_n);
     if (rc) return rc;
@@ -374,6 +443,19 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
 
 int64_t sdimb_launch_count(void) { return g_launches.load(); }
 
+int sdimb_cluster_size(int n, int d, int64_t shots, uint32_t flags) {
+  SdimbLayout L;
+  if (sdimb_layout(n, d, &L) || shots < 1) return 0;
+  if (plan_kernel(n, d, flags, L.np) != 0) return 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return plan_cluster(L, shots, flags, sms);
+}
+
 int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap, int64_t* out_n) {
   if (n < 1 || n_ops < 0 || (n_ops > 0 && !ops) || !out || !out_n || out_cap < 2 * n_ops + 1) return SDIMB_EINVAL;
   // lw[q]: first layer in which row q may be read again (last writer + 1); lr[q]: first layer in which row q
@@ -388,7 +470,9 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
       for (int64_t i : layer) {
         const int32_t* o = ops + 4 * i;
         int32_t* r = out + 4 * w++;
-        r[0] = o[0] | ((k++ % SDIMB_SCHED_WARPS) << SDIMB_OP_WARP_SHIFT);
+        r[0] = (o[0] & SDIMB_OP_MASK) | ((k % SDIMB_SCHED_WARPS) << SDIMB_OP_WARP_SHIFT) |
+               ((k & 0x7FFF) << SDIMB_OP_INDEX_SHIFT);
+        ++k;
         r[1] = o[1]; r[2] = o[2]; r[3] = o[3];
       }
       int32_t* b = out + 4 * w++;

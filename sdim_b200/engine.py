@@ -36,8 +36,10 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 class TableauEngine:
     # auto: bit-plane resident for d in {2,3} when it fits, else uint8 lanes resident when they fit, else global
+    # (HBM store).  On the HBM store the library runs one CTA per shot, or one thread-block cluster per shot for
+    # large tableaus with few shots; "cluster" / "global-cta" pin that choice (tests, A/B timings).
     MODES = {None: 0, "auto": 0, "global": N.FORCE_GLOBAL, "resident": N.FORCE_RESIDENT, "lanes": N.FORCE_LANES,
-             "planes": N.FORCE_PLANES}
+             "planes": N.FORCE_PLANES, "cluster": N.FORCE_GLOBAL | N.CLUSTER, "global-cta": N.FORCE_GLOBAL | N.NO_CLUSTER}
 
     def __init__(self, prog: CompiledProgram, device=None):
         self.prog = prog
@@ -67,6 +69,11 @@ class TableauEngine:
         flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
         k, need = N.plan(self.prog.num_qudits, self.prog.dimension, flags)
         return N.KERNEL_NAMES[k], need
+
+    def cluster_size(self, shots: int, mode: Optional[str] = None) -> int:
+        """Thread-block cluster size the library would use for `shots` shots in `mode` (0: one CTA per shot)."""
+        with torch.cuda.device(self.device):
+            return int(self.lib.sdimb_cluster_size(self.prog.num_qudits, self.prog.dimension, shots, self.MODES[mode]))
 
     def _scratch_for(self, mode_flags: int) -> Optional[torch.Tensor]:
         if mode_flags not in self._scratch:
@@ -99,7 +106,10 @@ class TableauEngine:
         prog, L, dev = self.prog, self.layout, self.device
         kernel, need_tab = self.plan(mode, fresh, keep_tableau)
         flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
-        use_sched = kernel == "planes-resident" and op_range is None and self.ops_sched is not None
+        # layered stream: the multi-warp bit-plane CTAs and the cluster interpreter's gate groups want it; the
+        # one-CTA lane kernels ignore the layering (the reorder is exact, tests/test_schedule.py)
+        wants_layers = kernel == "planes-resident" or (kernel == "lanes-global" and self.cluster_size(shots, mode) > 0)
+        use_sched = wants_layers and op_range is None and self.ops_sched is not None
         if use_sched:
             flags |= N.SCHEDULED
         with torch.cuda.device(dev):

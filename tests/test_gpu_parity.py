@@ -14,7 +14,7 @@ def _engine(n, d, ops):
     return prog, TableauEngine(prog)
 
 
-@pytest.mark.parametrize("mode", ["resident", "global", "planes"])
+@pytest.mark.parametrize("mode", ["resident", "global", "planes", "cluster"])
 def test_golden_random_circuits_replay(golden_random, mode):
     """Every reference golden case: records AND all six final arrays, bit-exact, under replayed draws."""
     import torch
@@ -290,6 +290,71 @@ def test_config5_large_single_tableau():
         arrs = eng.export(eng.tableau, 1)
         for key in ("x", "z", "p", "dx", "dz", "dp"):
             assert np.array_equal(arrs[key], fin[key]), key
+
+
+# ---------------------------------------------------------------------------------------------------
+# Cluster interpreter (one shot per thread-block cluster, sdim_b200/csrc/clusters.cuh)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("csize", [1, 2, 8, 16])
+@pytest.mark.parametrize("d,n,depth", [(2, 97, 2500), (3, 100, 2500), (5, 33, 800), (7, 70, 1500), (13, 300, 3000)])
+def test_cluster_interpreter_matches_c_oracle(d, n, depth, csize, monkeypatch):
+    """Every opcode, all noise channels, ragged n, for several cluster sizes (lane words and rows are dealt over the
+    CTAs differently for each): records of all shots and the final tableau, bit-exact vs the C oracle."""
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine
+    monkeypatch.setenv("SDIMB_CLUSTER_SIZE", str(csize))
+    prog = random_program(seed=3000 * d + n, n=n, d=d, depth=depth)
+    eng = TableauEngine(prog)
+    shots, seed = 40, 99 + d
+    assert eng.plan("cluster")[0] == "lanes-global"
+    assert eng.cluster_size(shots, "cluster") == csize
+    assert eng.cluster_size(shots, "global-cta") == 0
+    got = eng.run(shots, 0, seed, mode="cluster", keep_tableau=True).cpu().numpy()
+    want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
+                             channel=prog.noise_channel, want_final=True)
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, shots - 1)
+    for key in ("x", "z", "p", "dx", "dz", "dp"):
+        assert np.array_equal(arrs[key], fin[key]), key
+
+
+def test_cluster_continue_from_store_and_stepped(monkeypatch):
+    """!FRESH path and the unlayered stream of the cluster interpreter: stepping through the op stream in chunks on
+    a persistent store gives the records and the store of one fused launch (and of the one-CTA kernel)."""
+    from make_cases import random_program
+    from sdim_b200.engine import TableauEngine
+    import torch
+    monkeypatch.setenv("SDIMB_CLUSTER_SIZE", "4")
+    prog = random_program(seed=61, n=45, d=5, depth=400)
+    eng = TableauEngine(prog)
+    fused = eng.run(6, 0, 3, keep_tableau=True, mode="cluster").cpu().numpy()
+    fused_tab = eng.tableau.clone()
+    cta = eng.run(6, 0, 3, keep_tableau=True, mode="global-cta").cpu().numpy()
+    assert np.array_equal(fused, cta) and torch.equal(eng.tableau, fused_tab)
+    store = eng.alloc_tableau(6)
+    eng.init_tableau(store)
+    rec = torch.zeros((6, prog.n_meas), dtype=torch.uint8, device="cuda")
+    for lo in range(0, prog.n_ops, 7):
+        eng.run(6, 0, 3, keep_tableau=True, tableau=store, fresh=False, op_range=(lo, min(lo + 7, prog.n_ops)),
+                records=rec, mode="cluster")
+    assert np.array_equal(rec.cpu().numpy(), fused)
+    assert torch.equal(store, fused_tab)
+
+
+def test_cluster_is_the_default_for_a_large_single_tableau():
+    """Config 5 shape (n = 1024 here): few shots of a wide tableau go to a 16-CTA cluster by default; many shots keep
+    one CTA per shot; both agree with each other (the oracle comparison is test_config5_large_single_tableau)."""
+    from sdim_b200 import generate_random_clifford_circuit
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    prog = compile_circuits([generate_random_clifford_circuit(1024, 4096, 5, measurement_rounds=1, seed=1)])
+    eng = TableauEngine(prog)
+    assert eng.cluster_size(1) == 16 and eng.cluster_size(9) == 16 and eng.cluster_size(18) == 8
+    assert eng.cluster_size(1000) == 0
+    a = eng.run(3, 0, 3).cpu().numpy()
+    b = eng.run(3, 0, 3, mode="global-cta").cpu().numpy()
+    assert np.array_equal(a, b)
 
 
 def test_config2_full_size_ten_thousand_shots():
