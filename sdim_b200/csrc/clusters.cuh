@@ -40,6 +40,7 @@ struct CScratch : Scratch {
   uint32_t* dotg;   // [2][4*wpc] cluster-reduced dot products of the lane words this CTA owns (DSMEM target)
   uint32_t* acc;    // [blockDim] phase increments of the gate groups, staged for the fold
   uint32_t* xch;    // [2][4]     cluster accumulators: x_p . z_p | old pivot phase | det a1 | det rows (DSMEM target)
+  uint32_t* rowx;   // [W/4]      X half of the row being measured (stabilizer lanes, then destabilizer lanes)
 };
 
 struct CGeo {
@@ -52,7 +53,7 @@ struct CGeo {
 // bytes of dynamic shared memory per CTA
 inline size_t cluster_smem_bytes(int np, int wpc) {
   const size_t W = 2 * (size_t)np, wz = W / 4;
-  return 4 * W + 4 * wz + 4 * 8 * (size_t)wpc + 4 * kClusterThreads + 4 * 32 + 4 * 4 + 4 * 8   // dot fw dotg acc red cnt xch
+  return 4 * W + 4 * wz + 4 * wz + 4 * 8 * (size_t)wpc + 4 * kClusterThreads + 4 * 32 + 4 * 4 + 4 * 8   // dot fw rowx dotg acc red cnt xch
          + 2 * (size_t)np + 2 * (size_t)np + 2 * wz + (size_t)np + (size_t)np + 128 + 64;       // ar br aw xs zs inv
 }
 
@@ -79,8 +80,110 @@ __device__ __forceinline__ void fold_phases(uint8_t* T, const KParams& p, CScrat
   __syncthreads();
 }
 
+// Row q is what every branch of a measurement starts from (pivot search, factors, deterministic factor list), and
+// on the HBM store every dependent pass over it is a memory round trip.  It is staged ONCE: the X half of the row
+// (all W lanes, stabilizers then destabilizers) goes to shared memory, and the thread's pivot candidate — FIRST
+// stabilizer with an X component on q (tableau_prime.py:273-283) — falls out of the same loads.
+__device__ __forceinline__ uint32_t stage_row(const uint8_t* rowq, const KParams& p, uint32_t* rowx) {
+  const uint32_t* xq = reinterpret_cast<const uint32_t*>(rowq);
+  const int wz = p.W / 4, ws = p.np / 4;
+  uint32_t best = kNoPivot;
+  for (int w = threadIdx.x; w < wz; w += blockDim.x) {
+    const uint32_t x = xq[w];
+    rowx[w] = x;
+    if (x && w < ws && best == kNoPivot) best = 4u * w + ((__ffs(x) - 1) >> 3);
+  }
+  return best;
+}
+
+// Factors f = -X[q,i] mod d of the four lanes of word w; the pivot itself is skipped.
+__device__ __forceinline__ uint32_t factor_word(const Arith& A, uint32_t xq_w, int w, uint32_t piv) {
+  uint32_t fw = 0;
+  if (xq_w) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (4u * w + k != piv) fw |= neg_d(A, byte_of(xq_w, k)) << (8 * k);
+  }
+  return fw;
+}
+
+// factor_words (lanes.cuh) from the staged row
+__device__ __forceinline__ void factor_words_staged(const uint32_t* rowx, const KParams& p, Scratch& S, uint32_t piv) {
+  for (int w = threadIdx.x; w < p.W / 4; w += blockDim.x) {
+    const uint32_t fw = factor_word(p.A, rowx[w], w, piv);
+    S.fw[w] = fw;
+    if (fw) {
+      S.aw[atomicAdd(&S.cnt[1], 1u)] = (uint16_t)w;
+      *reinterpret_cast<uint4*>(S.dot + 4 * w) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+// det_list (lanes.cuh) from the staged row: ordered compaction of the generators with f_i = destab X[q,i] != 0,
+// four generators (one word) per thread and pass — one pass for n <= 4 * blockDim.  The phase loads behind `a1`
+// are issued here and not waited for.
+__device__ __forceinline__ int det_list_staged(const uint32_t* rowx, const uint8_t* P8, const KParams& p, Scratch& S,
+                                               int pw_lo, int pw_hi, uint32_t& a1) {
+  const int ws = p.np / 4, nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int total = 0;
+  a1 = 0;
+  __syncthreads();   // every warp has finished reading S.red in block_min before it is reused below
+  for (int base = 0; base < ws; base += nt) {
+    const int j = base + tid;
+    const uint32_t fq = (j < ws) ? rowx[ws + j] : 0u;          // destab X[q, 4j .. 4j+3]; padding lanes hold 0
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c += byte_of(fq, k) != 0;
+    int incl = c;                                              // inclusive scan inside the warp
+#pragma unroll
+    for (int d2 = 1; d2 < 32; d2 <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d2);
+      if (lane >= d2) incl += o;
+    }
+    if (lane == 31) S.red[warp] = (uint32_t)incl;
+    __syncthreads();
+    const int mine_cnt = lane < (nt >> 5) ? (int)S.red[lane] : 0;   // exclusive scan of the warp totals, by every warp
+    int incl2 = mine_cnt;
+#pragma unroll
+    for (int d2 = 1; d2 < 32; d2 <<= 1) {
+      const int o = __shfl_up_sync(0xFFFFFFFFu, incl2, d2);
+      if (lane >= d2) incl2 += o;
+    }
+    int pos = total + __shfl_sync(0xFFFFFFFFu, incl2 - mine_cnt, warp) + incl - c;
+    total += __shfl_sync(0xFFFFFFFFu, incl2, 31);
+    if (c) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t f = byte_of(fq, k);
+        if (f) {
+          const int i = 4 * j + k;
+          S.ar[pos] = (uint16_t)i;
+          S.xs[pos] = (uint8_t)f;
+          if (j >= pw_lo && j < pw_hi) a1 += f * P8[i];
+          ++pos;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  return total;
+}
+
+// Two block sums behind one barrier pair: a mod order, b mod d.
+__device__ __forceinline__ void block_sum2(const Arith& A, uint32_t& a, uint32_t& b, uint32_t* red) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t wa = mod_o(A, __reduce_add_sync(0xFFFFFFFFu, a)), wb = mod_d(A, __reduce_add_sync(0xFFFFFFFFu, b));
+  __syncthreads();
+  if (lane == 0) red[threadIdx.x >> 5] = wa | (wb << 16);
+  __syncthreads();
+  const uint32_t v = lane < (blockDim.x >> 5) ? red[lane] : 0u;
+  a = mod_o(A, __reduce_add_sync(0xFFFFFFFFu, v & 0xFFFFu));
+  b = mod_d(A, __reduce_add_sync(0xFFFFFFFFu, v >> 16));
+}
+
 // Measurement of qudit q in the Z basis (tableau_prime.py:262-363) by the whole cluster.  `par` = parity of this
 // measurement (selects the cluster accumulators).  The caller has made all earlier writes cluster-visible.
+// Dependent memory round trips: row q | pivot column | rank-1 update (random), row q | generator columns (det.).
 __device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p, CScratch& S, const CGeo& g,
                             uint32_t par, int q, int64_t slot, int64_t shot_local, uint32_t draw) {
   const Arith& A = p.A;
@@ -91,19 +194,25 @@ __device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p,
   uint32_t* xch = S.xch + 4 * par;
   uint32_t* dotg = S.dotg + (size_t)par * 4 * g.wpc;
   if (tid < 3) S.cnt[tid] = 0;
-  __syncthreads();
-
-  // every CTA finds the pivot itself: same row, same answer, no exchange
-  const uint32_t piv = block_min(pivot_candidate(rowq, p), S.red);
+  // every CTA stages row q and finds the pivot itself: same row, same answer, no exchange
+  const uint32_t piv = block_min(stage_row(rowq, p, S.rowx), S.red);   // its barriers publish rowx and the counters
 
   uint32_t outcome, rec;
   if (piv != kNoPivot) {
     // -- random branch (tableau_prime.py:294-334) ---------------------------------------------------------
-    const uint32_t e = S.inv[rowq[piv]];
-    factor_words(rowq, p, S, piv);                             // whole row q, redundantly per CTA
+    const uint32_t e = S.inv[byte_of(S.rowx[piv >> 2], piv & 3)];
+    factor_words_staged(S.rowx, p, S, piv);                    // whole row q, redundantly per CTA
     const int own_p = (int)(piv >> 2) / g.wpc, own_d = (int)((npad + piv) >> 2) / g.wpc;
-    // the old pivot phase is only safe to read in the CTA that owns its word: broadcast it
-    if (g.c == own_p && tid < g.C) *cl.map_shared_rank(xch + 1, tid) = P8[piv];
+    // Loads whose latency hides behind the column walk.  Phase words are only ever written by the CTA that owns
+    // them, so the owner may read them before the barriers: the old pivot phase (broadcast below, every CTA needs
+    // it) and this thread's own phase word if it holds a non-zero factor.
+    uint32_t ps_mine = 0, fw_own = 0, ph_own = 0;
+    if (g.c == own_p && tid < g.C) ps_mine = P8[piv];
+    uint32_t* Pw = reinterpret_cast<uint32_t*>(P8) + g.w;
+    if (tid < g.wpc && g.w < wz) {
+      fw_own = factor_word(A, S.rowx[g.w], g.w, piv);
+      if (fw_own) ph_own = *Pw;
+    }
     cl.sync();                                                 // B1: row q has been read everywhere
     uint32_t sd_raw = column_walk(T, p, S, piv, e, g.r0, g.r1);
     sd_raw = mod_d(A, block_sum(sd_raw, S.red));               // barrier: publishes xs/zs/ar/br/fw/aw/dot/cnt
@@ -122,19 +231,18 @@ __device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p,
         }
       }
     }
-    if (tid < g.C && sd_raw) atomicAdd(cl.map_shared_rank(xch, tid), sd_raw);
+    if (tid < g.C) {
+      if (sd_raw) atomicAdd(cl.map_shared_rank(xch, tid), sd_raw);
+      if (g.c == own_p) *cl.map_shared_rank(xch + 1, tid) = ps_mine;
+    }
     cl.sync();                                                 // B2: sums are complete
     const uint32_t sd_all = mod_d(A, xch[0]), ps_old = xch[1];
     const uint32_t ps = mod_o(A, ps_old * e + A.po * mod_d(A, sd_all * mod_d(A, (e * (e - 1u)) >> 1)));
     const uint32_t sd = mod_d(A, mod_d(A, sd_all * e) * e);    // x_p . z_p after exponentiation
-    if (tid < g.wpc && g.w < wz) {                             // phases of the lane words this CTA owns
-      const uint32_t fw = S.fw[g.w];
-      if (fw) {
-        uint32_t* Pw = reinterpret_cast<uint32_t*>(P8) + g.w;
-        uint32_t* dg = dotg + 4 * tid;
-        *Pw = phase_word_update(A, fw, *Pw, dg, sd, ps);
-        *reinterpret_cast<uint4*>(dg) = make_uint4(0, 0, 0, 0);
-      }
+    if (fw_own) {                                              // phases of the lane words this CTA owns
+      uint32_t* dg = dotg + 4 * tid;
+      *Pw = phase_word_update(A, fw_own, ph_own, dg, sd, ps);
+      *reinterpret_cast<uint4*>(dg) = make_uint4(0, 0, 0, 0);
     }
     outcome = draw;
     __syncthreads();
@@ -147,9 +255,10 @@ __device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p,
   } else {
     // -- deterministic branch (tableau_prime.py:336-363): nothing is written to the tableau --------------
     uint32_t a1;
-    const int total = det_list(rowq, P8, p, S, g.c * g.wpc, (g.c + 1) * g.wpc, a1);   // phases of owned words only
-    a1 = mod_o(A, block_sum(mod_o(A, a1), S.red));
-    const uint32_t part = mod_d(A, block_sum(det_rows(T, p, S, total, g.r0, g.r1), S.red));
+    const int total = det_list_staged(S.rowx, P8, p, S, g.c * g.wpc, (g.c + 1) * g.wpc, a1);   // phases of owned words
+    uint32_t part = det_rows(T, p, S, total, g.r0, g.r1);
+    a1 = mod_o(A, a1);
+    block_sum2(A, a1, part, S.red);
     if (tid < g.C) {
       if (a1) atomicAdd(cl.map_shared_rank(xch + 2, tid), a1);
       if (part) atomicAdd(cl.map_shared_rank(xch + 3, tid), part);
@@ -190,7 +299,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1) interp_cluster_kernel(cons
   CScratch S;
   S.dot = reinterpret_cast<uint32_t*>(smem);
   S.fw = S.dot + p.W;
-  S.dotg = S.fw + wz;
+  S.rowx = S.fw + wz;
+  S.dotg = S.rowx + wz;
   S.acc = S.dotg + 8 * g.wpc;
   S.red = S.acc + kClusterThreads;
   S.cnt = S.red + 32;
