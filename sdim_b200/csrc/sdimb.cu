@@ -83,6 +83,14 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
 // one CTA per shot.  By default only tableaus with rows wider than one 256-thread CTA (n > 512) and fewer shots
 // than clusters fit on the GPU: C = 16 (non-portable size) while shots * 16 fits on the SMs, then 8, 4, 2.
 // SDIMB_CLUSTER forces it (tests; size from the environment variable SDIMB_CLUSTER_SIZE, default 8).
+int cluster_threads(int wpc) {
+  int t = 512;
+  if (const char* env = std::getenv("SDIMB_CLUSTER_THREADS")) t = std::atoi(env);   // developer knob (A/B timings)
+  t = t >= 1024 ? 1024 : t >= 512 ? 512 : 256;
+  while (t < wpc) t *= 2;                          // a CTA needs one thread per lane word it owns
+  return t;
+}
+
 int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags, int sms) {
   if (flags & SDIMB_NO_CLUSTER) return 0;
   const bool forced = (flags & SDIMB_CLUSTER) != 0;
@@ -95,10 +103,10 @@ int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags, int sms) {
   } else {
     while (want > 2 && shots * want > sms) want >>= 1;
   }
-  auto kern = clusters::interp_cluster_kernel;
   for (int C = want; C >= 1; C >>= 1) {
     const int wpc = clusters::cluster_wpc(L.np, C);
     const size_t smem = clusters::cluster_smem_bytes(L.np, wpc);
+    auto kern = clusters::cluster_kernel_for(cluster_threads(wpc));
     if (wpc > clusters::kClusterThreads || smem > (size_t)kSmemLimit) {
       if (wpc > clusters::kClusterThreads) return 0;      // smaller clusters only make it worse
       continue;
@@ -109,7 +117,7 @@ int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags, int sms) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(clusters::kClusterThreads);
+    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3((unsigned)cluster_threads(wpc));
     cfg.dynamicSmemBytes = smem; cfg.attrs = attr; cfg.numAttrs = 1;
     int nc = 0;
     if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc >= 1) return C;
@@ -241,14 +249,15 @@ int sdimb_run(const SdimbRunArgs* a) {
   if (kernel == 0) {
     const int C = plan_cluster(L, a->shots, a->flags, sms);
     if (C >= 1) {                                    // one shot per thread-block cluster
-      auto kern = clusters::interp_cluster_kernel;
       p.wpc = clusters::cluster_wpc(L.np, C);
+      const int cthreads = cluster_threads(p.wpc);
+      auto kern = clusters::cluster_kernel_for(cthreads);
       const size_t smem = clusters::cluster_smem_bytes(L.np, p.wpc);
       cudaLaunchConfig_t cfg = {};
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3(clusters::kClusterThreads);
+      cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3((unsigned)cthreads);
       cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)a->stream; cfg.attrs = attr; cfg.numAttrs = 1;
       int nc = 0;
       if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); return SDIMB_ECUDA; }
@@ -442,6 +451,17 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
 }
 
 int64_t sdimb_launch_count(void) { return g_launches.load(); }
+
+#ifdef SDIMB_PHASE_CLOCKS
+// developer build only: read (and clear) the cluster interpreter's per-phase clock accumulators
+int sdimb_debug_phase_clocks(unsigned long long* out32) {
+  unsigned long long zero[32] = {0};
+  if (cudaDeviceSynchronize() != cudaSuccess) return SDIMB_ECUDA;
+  if (cudaMemcpyFromSymbol(out32, clusters::g_phase_clk, sizeof(zero)) != cudaSuccess) return SDIMB_ECUDA;
+  if (cudaMemcpyToSymbol(clusters::g_phase_clk, zero, sizeof(zero)) != cudaSuccess) return SDIMB_ECUDA;
+  return SDIMB_OK;
+}
+#endif
 
 int sdimb_cluster_size(int n, int d, int64_t shots, uint32_t flags) {
   SdimbLayout L;
