@@ -42,6 +42,9 @@ def time_tableau(prog, shots, reps=3):
         eng.run(shots, 0, 1, tableau=tab, records=rec)
     e1.record()
     torch.cuda.synchronize()
+    csize = eng.cluster_size(shots) if kernel == "lanes-global" else 0
+    if csize:
+        kernel += f", {csize}-CTA cluster per shot"
     return eng, kernel, e0.elapsed_time(e1) / reps
 
 

@@ -80,8 +80,9 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
 }
 
 // Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
-// one CTA per shot.  By default only tableaus with rows wider than one 256-thread CTA (n > 512) and fewer shots
-// than clusters fit on the GPU: C = 16 (non-portable size) while shots * 16 fits on the SMs, then 8, 4, 2.
+// one CTA per shot.  By default only tableaus with rows wider than one 256-thread CTA (n > 512), and the largest
+// cluster size (16 = the non-portable maximum, then 8, 4, 2) of which the GPU can keep one per shot resident at the
+// same time (cudaOccupancyMaxActiveClusters: a cluster lives on one GPC); more shots than that run one CTA each.
 // SDIMB_CLUSTER forces it (tests; size from the environment variable SDIMB_CLUSTER_SIZE, default 8).
 int cluster_threads(int wpc) {
   int t = 512;
@@ -91,40 +92,41 @@ int cluster_threads(int wpc) {
   return t;
 }
 
-int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags, int sms) {
-  if (flags & SDIMB_NO_CLUSTER) return 0;
-  const bool forced = (flags & SDIMB_CLUSTER) != 0;
-  if (!forced && (L.lanes / 4 <= kMaxThreads || shots * 2 > sms)) return 0;
-  int want = 16;
-  if (forced) {
-    const char* env = std::getenv("SDIMB_CLUSTER_SIZE");
-    want = env ? std::atoi(env) : 8;
-    if (want != 1 && want != 2 && want != 4 && want != 8 && want != 16) want = 8;
-  } else {
-    while (want > 2 && shots * want > sms) want >>= 1;
-  }
-  for (int C = want; C >= 1; C >>= 1) {
-    const int wpc = clusters::cluster_wpc(L.np, C);
-    const size_t smem = clusters::cluster_smem_bytes(L.np, wpc);
-    auto kern = clusters::cluster_kernel_for(cluster_threads(wpc));
-    if (wpc > clusters::kClusterThreads || smem > (size_t)kSmemLimit) {
-      if (wpc > clusters::kClusterThreads) return 0;      // smaller clusters only make it worse
-      continue;
-    }
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, C > 8 ? 1 : 0) != cudaSuccess) break;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3((unsigned)cluster_threads(wpc));
-    cfg.dynamicSmemBytes = smem; cfg.attrs = attr; cfg.numAttrs = 1;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc >= 1) return C;
+// co-resident clusters of size C for this layout, 0 if the shape cannot run
+int max_active_clusters(const SdimbLayout& L, int C) {
+  const int wpc = clusters::cluster_wpc(L.np, C);
+  const size_t smem = clusters::cluster_smem_bytes(L.np, wpc);
+  if (wpc > clusters::kClusterThreads || smem > (size_t)kSmemLimit) return 0;
+  auto kern = clusters::cluster_kernel_for(cluster_threads(wpc));
+  int nc = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)C); cfg.blockDim = dim3((unsigned)cluster_threads(wpc));
+  cfg.dynamicSmemBytes = smem; cfg.attrs = attr; cfg.numAttrs = 1;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, C > 8 ? 1 : 0) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) {
     cudaGetLastError();
-    if (!forced && C == 2) break;
+    return 0;
   }
-  cudaGetLastError();
+  return nc;
+}
+
+int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags) {
+  if (flags & SDIMB_NO_CLUSTER) return 0;
+  if (flags & SDIMB_CLUSTER) {
+    const char* env = std::getenv("SDIMB_CLUSTER_SIZE");
+    int want = env ? std::atoi(env) : 8;
+    if (want != 1 && want != 2 && want != 4 && want != 8 && want != 16) want = 8;
+    for (int C = want; C >= 1; C >>= 1)
+      if (max_active_clusters(L, C) >= 1) return C;
+    return 0;
+  }
+  if (L.lanes / 4 <= kMaxThreads) return 0;
+  for (int C = 16; C >= 2; C >>= 1)
+    if (max_active_clusters(L, C) >= shots) return C;
   return 0;
 }
 
@@ -247,7 +249,7 @@ int sdimb_run(const SdimbRunArgs* a) {
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
   }
   if (kernel == 0) {
-    const int C = plan_cluster(L, a->shots, a->flags, sms);
+    const int C = plan_cluster(L, a->shots, a->flags);
     if (C >= 1) {                                    // one shot per thread-block cluster
       p.wpc = clusters::cluster_wpc(L.np, C);
       const int cthreads = cluster_threads(p.wpc);
@@ -467,13 +469,12 @@ int sdimb_cluster_size(int n, int d, int64_t shots, uint32_t flags) {
   SdimbLayout L;
   if (sdimb_layout(n, d, &L) || shots < 1) return 0;
   if (plan_kernel(n, d, flags, L.np) != 0) return 0;
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  return plan_cluster(L, shots, flags, sms);
+  return plan_cluster(L, shots, flags);
 }
 
 int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap, int64_t* out_n) {
