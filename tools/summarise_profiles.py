@@ -27,7 +27,7 @@ want = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
-for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096), ("gates_stream", 9472)):
+for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096), ("gates_stream", 9472), ("config5_cluster", 1)):
     rep = os.path.join(G, f"{R}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -36,7 +36,9 @@ for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096), 
     m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     lines = run(sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "25")
     with open(os.path.join(P, f"{R}_ncu_{tag}.txt"), "w") as fh:
-        what = "the 2000 gates of the headline circuit (no noise, no measurement), uint8 HBM store" if tag == "gates_stream" else "the headline workload"
+        what = {"gates_stream": "the 2000 gates of the headline circuit (no noise, no measurement), uint8 HBM store",
+                "config5_cluster": "config 5 (random Clifford d = 5, n = 4096, 8192 gates + 4096 measurements, one 64 MiB tableau) on a 16-CTA cluster"
+                }.get(tag, "the headline workload")
         fh.write(f"# ncu --set full --clock-control none --import-source on, one launch of {what}, {shots} shots\n")
         fh.write(f"kernel: {m.get('Kernel Name', ('?',))[0]}\n")
         for k in want:
@@ -52,7 +54,8 @@ for tag, shots in (("headline_planes", 16384), ("headline_lanes_global", 4096), 
 if "headline_planes" in traffic:
     t = dict(traffic["headline_planes"]); t["all"] = traffic
     json.dump(t, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-for name in (f"{R}_sanitizer.txt", f"{R}_bench_n1.json", f"{R}_bench_reference.json", f"{R}_bench_n2.json"):
+for name in (f"{R}_sanitizer.txt", f"{R}_bench_n1.json", f"{R}_bench_reference.json", f"{R}_bench_n2.json",
+             f"{R}_configs.json", f"{R}_config5_breakdown.txt"):
     src = os.path.join(G, name)
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, name))
