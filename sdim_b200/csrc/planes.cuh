@@ -67,6 +67,8 @@ struct Geo {
   uint2* ph_base;                               // [NW][Wb] phase accumulators, always in shared memory
   uint2* pacc;                                  // phase accumulator used by ldp/stp (this warp's, or #0 in measure)
   int n, np, Wb, RS;                            // RS = row stride in words = EW * (Wb + 1)
+  int gpw, gsub, j0, jstep;                     // rank-1 update: row groups per warp (32 / Wb when Wb divides 32), this
+                                                // lane's group inside the warp, its first lane word and its word stride
   __device__ __forceinline__ uint32_t* entry(int q, int j) const { return tab + q * RS + j * EW; }
   __device__ __forceinline__ uint2* phase() const { return pacc; }
   __device__ __forceinline__ uint2* phase_of(int w) const { return ph_base + w * Wb; }
@@ -288,11 +290,14 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       uint32_t xr = 0, zr = 0, od = 0;
       if (r < n) {
         const XZ s = G.ld(r, jp), dd = G.ld(r, jd);
-        xr = bit2(s.x, bp); zr = bit2(s.z, bp);
-        od = bit2(dd.x, bp) | bit2(dd.z, bp);
-        sd_part += xr * zr;
-        if (D == 3 && e == 2u) { xr = (xr >> 1) | ((xr & 1u) << 1); zr = (zr >> 1) | ((zr & 1u) << 1); }   // * 2 = negate
-        S.xz[r] = (uint8_t)(xr | (zr << 2));
+        const uint32_t bm = 1u << bp;
+        od = (dd.x.l | dd.x.h | dd.z.l | dd.z.h) & bm;
+        if ((s.x.l | s.x.h | s.z.l | s.z.h) & bm) {            // the pivot acts on few qudits: most rows stop here
+          xr = bit2(s.x, bp); zr = bit2(s.z, bp);
+          sd_part += xr * zr;
+          if (D == 3 && e == 2u) { xr = (xr >> 1) | ((xr & 1u) << 1); zr = (zr >> 1) | ((zr & 1u) << 1); }   // * 2 = negate
+          S.xz[r] = (uint8_t)(xr | (zr << 2));
+        }
       }
       const bool act = (xr | zr) != 0, stale = !act && od != 0;
       const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, stale);
@@ -315,11 +320,10 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     const uint32_t sd_raw = cnt[2] % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
-    // col_i += f_i * col_p on the pivot's support.  Threads form row groups: 32/Wb per warp when Wb divides 32.
-    const int gpw = (Wb <= 32 && (32 % Wb) == 0) ? 32 / Wb : 1;
-    const int gtot = gpw * nw, gid = warp * gpw + (gpw > 1 ? lane / Wb : 0);
-    const int jstep = gpw > 1 ? Wb : 32;
-    for (int j = gpw > 1 ? lane % Wb : lane; j < Wb; j += jstep) {
+    // col_i += f_i * col_p on the pivot's support.  Threads form row groups: 32/Wb per warp when Wb divides 32
+    // (geometry precomputed in Geo: the divisions cost more than the update of a sparse measurement).
+    const int gpw = G.gpw, gtot = gpw * nw, gid = warp * gpw + G.gsub, jstep = G.jstep;
+    for (int j = G.j0; j < Wb; j += jstep) {
       const uint2 fv = S.f[j];
       const E f{fv.x, fv.y};
       E dot{0u, 0u};
@@ -432,6 +436,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
         const int g = S.ar[k];
         const uint32_t f = S.xz[k];
         const XZ v = G.ld(r, g >> 5);
+        if (((v.x.l | v.x.h | v.z.l | v.z.h) >> (g & 31) & 1u) == 0) continue;   // generator g is the identity on row r
         const uint32_t xi = bit2(v.x, g & 31), zi = bit2(v.z, g & 31);
         cross += (f * xi) * az;                                           // ancilla_z . (f * x_i), running ancilla
         az = (az + f * zi) % D;
@@ -462,6 +467,10 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   G.np = (p.n + 31) / 32 * 32;
   G.Wb = 2 * G.np / 32;
   G.RS = Geo<D>::EW * (G.Wb + 1);
+  G.gpw = (G.Wb <= 32 && (32 % G.Wb) == 0) ? 32 / G.Wb : 1;
+  G.gsub = G.gpw > 1 ? lane / G.Wb : 0;
+  G.j0 = G.gpw > 1 ? lane % G.Wb : lane;
+  G.jstep = G.gpw > 1 ? G.Wb : 32;
   const int row_words = (p.n * G.RS + 3) & ~3;
   uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
   G.tab = sm;
