@@ -54,6 +54,7 @@ struct CScratch : Scratch {
   uint32_t* rowx;   // [2][W/4]   X half of the row being measured (stabilizer lanes, then destabilizer lanes), and
                     //            of the row of the next measurement while it is being prefetched
   uint32_t* ring;   // [kRing]    CTA 0: packed partial sums of barrier-free deterministic measurements (DSMEM target)
+  uint32_t* red2;   // [32]       reduction scratch of the factor-list scan (block_min / block_sum own `red`)
 };
 
 struct CGeo {
@@ -66,7 +67,7 @@ struct CGeo {
 // bytes of dynamic shared memory per CTA
 inline size_t cluster_smem_bytes(int np, int wpc) {
   const size_t W = 2 * (size_t)np, wz = W / 4;
-  return 4 * W + 4 * wz + 8 * wz + 4 * 8 * (size_t)wpc + 4 * kClusterThreads + 4 * 32 + 4 * 4 + 4 * 8 + 4 * 64   // dot fw rowx dotg acc red cnt xch ring
+  return 4 * W + 4 * wz + 8 * wz + 4 * 8 * (size_t)wpc + 4 * kClusterThreads + 4 * 32 + 4 * 4 + 4 * 8 + 4 * 64 + 4 * 32   // dot fw rowx dotg acc red cnt xch ring red2
          + 2 * (size_t)np + 2 * (size_t)np + 2 * wz + (size_t)np + (size_t)np + 128 + 64;       // ar br aw xs zs inv
 }
 
@@ -160,10 +161,12 @@ __device__ __forceinline__ void factor_words_staged(const uint32_t* rowx, const 
 }
 
 // det_list (lanes.cuh) from the staged row: ordered compaction of the generators with f_i = destab X[q,i] != 0,
-// four generators (one word) per thread and pass — one pass for n <= 4 * blockDim.  The phase loads behind `a1`
-// are issued here and not waited for: the last pass leaves them in (pf, pv) and the caller adds
-// sum_k pf[k] * pv[k] to a1 once its own loads are in flight.
-__device__ __forceinline__ int det_list_staged(const uint32_t* rowx, const uint8_t* P8, const KParams& p, Scratch& S,
+// four generators (one word) per thread and pass — one pass for n <= 4 * blockDim.  (Sixteen generators per thread
+// and a single pass at n = 4096 measured slower: the unrolled 16-way emit costs more than the second pass.)  The
+// phase loads behind `a1` are issued here and not waited for: the last pass leaves them in (pf, pv) and the caller
+// adds sum_k pf[k] * pv[k] to a1 once its own loads are in flight.  Uses its own reduction scratch (red2), so it
+// needs no barrier against block_min before it; ends with a barrier (the lists are published).
+__device__ __forceinline__ int det_list_staged(const uint32_t* rowx, const uint8_t* P8, const KParams& p, CScratch& S,
                                                int pw_lo, int pw_hi, uint32_t& a1, uint32_t (&pf)[4],
                                                uint32_t (&pv)[4]) {
   const int ws = p.np / 4, nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,7 +174,6 @@ __device__ __forceinline__ int det_list_staged(const uint32_t* rowx, const uint8
   a1 = 0;
   pf[0] = pf[1] = pf[2] = pf[3] = 0u;
   pv[0] = pv[1] = pv[2] = pv[3] = 0u;
-  __syncthreads();   // every warp has finished reading S.red in block_min before it is reused below
   for (int base = 0; base < ws; base += nt) {
     const int j = base + tid;
     const uint32_t fq = (j < ws) ? rowx[ws + j] : 0u;          // destab X[q, 4j .. 4j+3]; padding lanes hold 0
@@ -187,9 +189,9 @@ __device__ __forceinline__ int det_list_staged(const uint32_t* rowx, const uint8
       excl = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
       wtotal = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
     }
-    if (lane == 0) S.red[warp] = (uint32_t)wtotal;
+    if (lane == 0) S.red2[warp] = (uint32_t)wtotal;
     __syncthreads();
-    const uint32_t rv = lane < (nt >> 5) ? S.red[lane] : 0u;
+    const uint32_t rv = lane < (nt >> 5) ? S.red2[lane] : 0u;
     const int all = (int)__reduce_add_sync(0xFFFFFFFFu, rv);
     if (any) {
       int pos = total + (int)__reduce_add_sync(0xFFFFFFFFu, lane < warp ? rv : 0u) + excl;
@@ -211,11 +213,12 @@ __device__ __forceinline__ int det_list_staged(const uint32_t* rowx, const uint8
   return total;
 }
 
-// Two block sums behind one barrier pair: a mod order, b mod d.
-__device__ __forceinline__ void block_sum2(const Arith& A, uint32_t& a, uint32_t& b, uint32_t* red) {
+// Two block sums behind one barrier pair: a mod order, b mod d.  `fenced` = a barrier since the last use of `red`
+// has already been passed by every thread (the leading barrier is skipped).
+__device__ __forceinline__ void block_sum2(const Arith& A, uint32_t& a, uint32_t& b, uint32_t* red, bool fenced) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t wa = mod_o(A, __reduce_add_sync(0xFFFFFFFFu, a)), wb = mod_d(A, __reduce_add_sync(0xFFFFFFFFu, b));
-  __syncthreads();
+  if (!fenced) __syncthreads();
   if (lane == 0) red[threadIdx.x >> 5] = wa | (wb << 16);
   __syncthreads();
   const uint32_t v = lane < (blockDim.x >> 5) ? red[lane] : 0u;
@@ -348,7 +351,8 @@ __device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p,
       if (g.c == own_p) P8[piv] = (uint8_t)mod_o(A, A.order - outcome * A.po);  // stabilizer p <- Z_q, phase -m*po
       if (g.c == 0) p.records[shot_local * p.rec_stride + slot] = (uint8_t)outcome;
     }
-    __syncthreads();
+    // no closing barrier: the next op that reads what thread 0 just wrote is a measurement (two block barriers in
+    // its pivot search come first) or a gate (phase words are not read by gates; the fold starts with a barrier)
     PHASE(12);
     return outcome;
   }
@@ -359,7 +363,8 @@ __device__ uint32_t measure(cg::cluster_group& cl, uint8_t* T, const KParams& p,
   uint32_t part = det_rows(T, p, S, total, g.r0, g.r1);
   PHASE(2);
   a1 = mod_o(A, a1 + pf[0] * pv[0] + pf[1] * pv[1] + pf[2] * pv[2] + pf[3] * pv[3]);
-  block_sum2(A, a1, part, S.red);                              // its barriers also retire this measurement's lists
+  block_sum2(A, a1, part, S.red, true);                        // fenced by the barrier that published the lists; its
+                                                               // own barrier also retires them
   PHASE(3);
   if (!need_outcome) {
     // nobody but the record needs the outcome: one packed atomic to CTA 0, no barrier
@@ -427,8 +432,9 @@ __global__ void __launch_bounds__(THREADS, 1) interp_cluster_kernel(const __grid
   S.cnt = S.red + 32;
   S.xch = S.cnt + 4;
   S.ring = S.xch + 8;
+  S.red2 = S.ring + kRing;
   S.ops = nullptr;
-  S.ar = reinterpret_cast<uint16_t*>(S.ring + kRing);
+  S.ar = reinterpret_cast<uint16_t*>(S.red2 + 32);
   S.br = S.ar + p.np;
   S.aw = S.br + p.np;
   S.xs = reinterpret_cast<uint8_t*>(S.aw + wz);
