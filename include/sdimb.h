@@ -78,7 +78,8 @@ enum {
 #define SDIMB_FORCE_GLOBAL 0x4u    /* never stage the tableau in shared memory */
 #define SDIMB_FORCE_RESIDENT 0x8u  /* require the shared-memory resident uint8-lane interpreter (else SDIMB_ETOOBIG) */
 #define SDIMB_FORCE_LANES 0x10u    /* never use the bit-plane interpreter (d = 2, 3), keep uint8 lanes */
-#define SDIMB_FORCE_PLANES 0x20u   /* require the bit-plane resident interpreter (d = 2, 3; else SDIMB_ETOOBIG) */
+#define SDIMB_FORCE_PLANES 0x20u   /* require the bit-plane resident interpreter (d = 2, 3; else SDIMB_ETOOBIG); with
+                                      SDIMB_FORCE_GLOBAL: the bit-plane interpreter on a global image (scratch) */
 #define SDIMB_SCHEDULED 0x40u      /* `ops` is the output of sdimb_schedule: the bit-plane interpreter may run
                                       SDIMB_SCHED_WARPS warps per shot, one commuting layer at a time; the cluster
                                       interpreter deals each layer over its gate groups */
@@ -181,14 +182,16 @@ int sdimb_frames(int n, int d, int64_t shots, int64_t shot_offset, const int32_t
  * sequential, sdim/program.py:311-312); SURVEY 8f rank 3. */
 int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap, int64_t* out_n);
 
-/* Scratch the bit-plane interpreter can use for (n, d, flags), 0 for the other interpreters.  With it, CTAs claim
- * shots from an atomic counter (shots differ in cost when noise fires); without it they grid-stride. */
+/* Scratch the bit-plane interpreter uses for (n, d, flags), 0 for the other interpreters.  Resident interpreter
+ * (optional): a shot counter, CTAs then claim shots dynamically (shots differ in cost when noise fires) instead of
+ * grid-striding.  Global-image interpreter (d = 2, 3 beyond the shared-memory limit; REQUIRED): the counter plus
+ * one bit-plane image per CTA the current device keeps resident. */
 int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags);
 
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store (one CTA or
  * one thread-block cluster per shot, chosen per call from n and shots), 1 uint8 lanes resident in shared memory,
- * 2 bit-plane resident (d = 2, 3); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for
- * these flags. */
+ * 2 bit-plane resident (d = 2, 3), 3 bit planes on a global image held in SdimbRunArgs.scratch (d = 2, 3 beyond
+ * the shared-memory limit); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for these flags. */
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */

@@ -10,7 +10,7 @@ OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
 FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT, FORCE_LANES, FORCE_PLANES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 SCHEDULED, CLUSTER, NO_CLUSTER = 0x40, 0x80, 0x100
 OP_BARRIER = 18
-KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident"}
+KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident", 3: "planes-global"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",

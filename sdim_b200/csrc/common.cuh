@@ -83,4 +83,5 @@ struct KParams {
   int vec;                     // lane interpreter: lane words per thread (1, or 4 with 128-bit accesses)
   unsigned int* shot_counter;  // bit-plane kernel: next unclaimed shot (nullable: static grid-stride)
   int wpc;                     // cluster interpreter: lane words owned by each CTA of the cluster
+  uint32_t* plane_slab;        // bit-plane interpreter on a global image: gridDim slabs of planes_row_bytes each
 };

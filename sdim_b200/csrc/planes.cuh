@@ -458,7 +458,11 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
 }
 
 // ---- the interpreter: one CTA per shot (1 warp, or SDIMB_SCHED_WARPS warps on a scheduled stream) --------------
-template <int D>
+// GLOBAL = false: the row image lives in shared memory (the resident interpreter).  GLOBAL = true: it lives in a
+// per-CTA slab of caller-provided scratch (L2 / HBM) — the same bit planes for tableaus beyond the shared-memory
+// limit (d = 3: n > ~440, d = 2: n > ~630), 4x / 8x fewer bytes per gate than the uint8 lanes; phase accumulators and
+// measurement scratch stay in shared memory.  Two instantiations, so the resident one keeps LDS / STS.
+template <int D, bool GLOBAL>
 __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
@@ -473,8 +477,12 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
   G.jstep = G.gpw > 1 ? G.Wb : 32;
   const int row_words = (p.n * G.RS + 3) & ~3;
   uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
-  G.tab = sm;
-  sm += row_words;
+  if (GLOBAL) {
+    G.tab = p.plane_slab + (int64_t)blockIdx.x * row_words;
+  } else {
+    G.tab = sm;
+    sm += row_words;
+  }
   G.ph_base = reinterpret_cast<uint2*>(sm);
   G.pacc = G.phase_of(warp);
   const int acc_words = (nw * 2 * G.Wb + 3) & ~3;

@@ -64,19 +64,41 @@ size_t scratch_bytes(int np) {
 }
 
 // Which interpreter a (n, d, flags) call runs: 0 = uint8 lanes in global memory, 1 = uint8 lanes resident in
-// shared memory, 2 = bit-plane resident (d = 2, 3).  Negative = error code.
+// shared memory, 2 = bit-plane resident (d = 2, 3), 3 = bit planes on a global image in caller scratch (d = 2, 3
+// when the planes do not fit in shared memory, or FORCE_PLANES | FORCE_GLOBAL).  Negative = error code.
 int plan_kernel(int n, int d, uint32_t flags, int np) {
-  if ((flags & SDIMB_FORCE_GLOBAL) && (flags & (SDIMB_FORCE_RESIDENT | SDIMB_FORCE_PLANES))) return SDIMB_EINVAL;
+  if ((flags & SDIMB_FORCE_GLOBAL) && (flags & SDIMB_FORCE_RESIDENT)) return SDIMB_EINVAL;
   if ((flags & SDIMB_FORCE_LANES) && (flags & SDIMB_FORCE_PLANES)) return SDIMB_EINVAL;
   SdimbLayout L;
   const int rc = sdimb_layout(n, d, &L);
   if (rc) return rc;
   const bool fits = (size_t)L.shot_bytes + scratch_bytes(np) <= (size_t)kSmemLimit;
-  const bool planes_fit = (d == 2 || d == 3) && planes::planes_smem_bytes(n, d) <= (size_t)kSmemLimit;
+  const bool planes_ok = d == 2 || d == 3;
+  const bool planes_fit = planes_ok && planes::planes_smem_bytes(n, d) <= (size_t)kSmemLimit;
+  const bool planes_global_ok = planes_ok && n <= 0xFFFF && planes::planes_scratch_bytes(n, SDIMB_SCHED_WARPS) <= (size_t)kSmemLimit;
+  if ((flags & SDIMB_FORCE_PLANES) && (flags & SDIMB_FORCE_GLOBAL)) return planes_global_ok ? 3 : SDIMB_ETOOBIG;
   if ((flags & SDIMB_FORCE_PLANES) && !planes_fit) return SDIMB_ETOOBIG;
   if ((flags & SDIMB_FORCE_RESIDENT) && !fits) return SDIMB_ETOOBIG;
-  if (planes_fit && !(flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES))) return 2;
+  const bool free_choice = !(flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES | SDIMB_CLUSTER));
+  if (planes_fit && free_choice) return 2;
+  if (planes_global_ok && !fits && free_choice) return 3;
   return (fits && !(flags & SDIMB_FORCE_GLOBAL)) ? 1 : 0;
+}
+
+// CTAs of the bit-plane interpreter on a global image that the current device keeps resident (its grid never
+// exceeds this), and the shared memory one of them needs.
+int planes_global_ctas(int n, int d, size_t* smem_out) {
+  const size_t smem = planes::planes_scratch_bytes(n, SDIMB_SCHED_WARPS);
+  if (smem_out) *smem_out = smem;
+  auto kern = (d == 2) ? planes::interp_planes_kernel<2, true> : planes::interp_planes_kernel<3, true>;
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * SDIMB_SCHED_WARPS, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  return sms * per_sm;
 }
 
 // Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
@@ -193,7 +215,7 @@ int sdimb_run(const SdimbRunArgs* a) {
   const int kernel = plan_kernel(a->n, a->d, a->flags, L.np);
   if (kernel < 0) return kernel;
   const size_t scratch = scratch_bytes(L.np);
-  const bool use_planes = kernel == 2, resident = kernel >= 1;
+  const bool use_planes = kernel == 2, resident = kernel >= 1;   // 3 keeps its image in scratch: no store needed either
   const bool need_tab = !resident || !(a->flags & SDIMB_FRESH) || (a->flags & SDIMB_WRITEBACK);
   if (need_tab && !a->tableau) return SDIMB_EINVAL;
 
@@ -222,8 +244,26 @@ int sdimb_run(const SdimbRunArgs* a) {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
+  if (kernel == 3) {
+    // bit planes on a global image: 4 warps per shot, one slab of scratch per resident CTA, shots claimed dynamically
+    size_t smem = 0;
+    const int max_ctas = planes_global_ctas(a->n, a->d, &smem);
+    const size_t slab = planes::planes_row_bytes(a->n, a->d);
+    if (max_ctas < 1) return SDIMB_ECUDA;
+    if (!a->scratch || a->scratch_bytes < (int64_t)(256 + slab)) return SDIMB_EINVAL;
+    int64_t grid = (a->scratch_bytes - 256) / (int64_t)slab;
+    if (grid > max_ctas) grid = max_ctas;
+    if (grid > a->shots) grid = a->shots;
+    auto kern = (a->d == 2) ? planes::interp_planes_kernel<2, true> : planes::interp_planes_kernel<3, true>;
+    p.shot_counter = (unsigned int*)a->scratch;
+    p.plane_slab = (uint32_t*)((uint8_t*)a->scratch + 256);
+    if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
+    kern<<<(unsigned)grid, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p);
+    g_launches++;
+    return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+  }
   if (use_planes) {
-    auto kern = (a->d == 2) ? planes::interp_planes_kernel<2> : planes::interp_planes_kernel<3>;
+    auto kern = (a->d == 2) ? planes::interp_planes_kernel<2, false> : planes::interp_planes_kernel<3, false>;
     // one warp per shot unless shared memory leaves the SM short of warps and the stream is scheduled
     int nw = 1;
     size_t smem = planes::planes_smem_bytes(a->n, a->d, 1);
@@ -387,7 +427,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   uint32_t sched_flag = 0;
   // bit-plane interpreter and cluster interpreter (wide rows on the HBM store): upload the layered stream
   const bool maybe_cluster = kernel == 0 && !(flags & SDIMB_NO_CLUSTER) && (L.lanes / 4 > kMaxThreads || (flags & SDIMB_CLUSTER));
-  if ((kernel == 2 || maybe_cluster) && n_ops > 0) {
+  if ((kernel == 2 || kernel == 3 || maybe_cluster) && n_ops > 0) {
     sched.resize((size_t)(2 * n_ops + 1) * 4);
     rc = sdimb_schedule(n, ops, n_ops, sched.data(), 2 * n_ops + 1, &up_n);
     if (rc) return rc;
@@ -565,8 +605,14 @@ int sdimb_frames(int n, int d, int64_t shots, int64_t shot_offset, const int32_t
 int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags) {
   SdimbLayout L;
   if (sdimb_layout(n, d, &L)) return 0;
-  if (plan_kernel(n, d, flags, L.np) != 2) return 0;
-  return 256;   // the shot counter
+  const int k = plan_kernel(n, d, flags, L.np);
+  if (k == 2) return 256;   // the shot counter
+  if (k == 3) {             // the shot counter + one image per CTA the device keeps resident (148 x 8 without a device)
+    int ctas = planes_global_ctas(n, d, nullptr);
+    if (ctas < 1) ctas = 148 * 8;
+    return 256 + (int64_t)ctas * (int64_t)planes::planes_row_bytes(n, d);
+  }
+  return 0;
 }
 
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau) {
@@ -576,7 +622,7 @@ int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau) {
   const int k = plan_kernel(n, d, flags, L.np);
   if (k < 0) return k;
   if (kernel) *kernel = k;
-  if (needs_tableau) *needs_tableau = (k == 0 || !(flags & SDIMB_FRESH) || (flags & SDIMB_WRITEBACK)) ? 1 : 0;
+  if (needs_tableau) *needs_tableau = (k == 0 || !(flags & SDIMB_FRESH) || (flags & SDIMB_WRITEBACK)) ? 1 : 0;   // k = 3 keeps its image in scratch
   return SDIMB_OK;
 }
 

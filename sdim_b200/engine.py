@@ -35,11 +35,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class TableauEngine:
-    # auto: bit-plane resident for d in {2,3} when it fits, else uint8 lanes resident when they fit, else global
-    # (HBM store).  On the HBM store the library runs one CTA per shot, or one thread-block cluster per shot for
+    # auto: bit-plane resident for d in {2,3} when it fits (bit planes on a global image when it does not), else
+    # uint8 lanes resident when they fit, else global (HBM store).  On the HBM store the library runs one CTA per shot, or one thread-block cluster per shot for
     # large tableaus with few shots; "cluster" / "global-cta" pin that choice (tests, A/B timings).
     MODES = {None: 0, "auto": 0, "global": N.FORCE_GLOBAL, "resident": N.FORCE_RESIDENT, "lanes": N.FORCE_LANES,
-             "planes": N.FORCE_PLANES, "cluster": N.FORCE_GLOBAL | N.CLUSTER, "global-cta": N.FORCE_GLOBAL | N.NO_CLUSTER}
+             "planes": N.FORCE_PLANES, "planes-global": N.FORCE_PLANES | N.FORCE_GLOBAL,
+             "cluster": N.FORCE_GLOBAL | N.CLUSTER, "global-cta": N.FORCE_GLOBAL | N.NO_CLUSTER}
 
     def __init__(self, prog: CompiledProgram, device=None):
         self.prog = prog
@@ -108,7 +109,8 @@ class TableauEngine:
         flags = self.MODES[mode] | (N.FRESH if fresh else 0) | (N.WRITEBACK if keep_tableau else 0)
         # layered stream: the multi-warp bit-plane CTAs and the cluster interpreter's gate groups want it; the
         # one-CTA lane kernels ignore the layering (the reorder is exact, tests/test_schedule.py)
-        wants_layers = kernel == "planes-resident" or (kernel == "lanes-global" and self.cluster_size(shots, mode) > 0)
+        wants_layers = kernel in ("planes-resident", "planes-global") or \
+            (kernel == "lanes-global" and self.cluster_size(shots, mode) > 0)
         use_sched = wants_layers and op_range is None and self.ops_sched is not None
         if use_sched:
             flags |= N.SCHEDULED

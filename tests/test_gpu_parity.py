@@ -14,14 +14,14 @@ def _engine(n, d, ops):
     return prog, TableauEngine(prog)
 
 
-@pytest.mark.parametrize("mode", ["resident", "global", "planes", "cluster"])
+@pytest.mark.parametrize("mode", ["resident", "global", "planes", "cluster", "planes-global"])
 def test_golden_random_circuits_replay(golden_random, mode):
     """Every reference golden case: records AND all six final arrays, bit-exact, under replayed draws."""
     import torch
     checked = 0
     for case in golden_random:
         n, d, ops = case["n"], case["d"], case["ops"]
-        if mode == "planes" and d > 3:
+        if mode.startswith("planes") and d > 3:
             continue
         prog, eng = _engine(n, d, ops)
         assert prog.n_ops == sum(1 for o in ops if o[0] != 0)
@@ -40,7 +40,7 @@ def test_golden_random_circuits_replay(golden_random, mode):
                 assert np.array_equal(arrs[key], np.array(case["final"][key])), \
                     f"final {key} differs: seed {case['seed']} n={n} d={d}"
         checked += 1
-    assert checked == (len(golden_random) if mode != "planes" else sum(c["d"] <= 3 for c in golden_random))
+    assert checked == (len(golden_random) if not mode.startswith("planes") else sum(c["d"] <= 3 for c in golden_random))
     assert checked >= 40
 
 
@@ -56,12 +56,12 @@ def _run_gpu(prog, shots, seed, mode=None, shot_offset=0, keep=False):
 
 @pytest.mark.parametrize("d,n,depth", [(2, 5, 120), (2, 40, 900), (2, 97, 2500), (3, 1, 30), (3, 17, 500), (3, 64, 1500), (3, 100, 2500),
                                         (5, 33, 800), (7, 16, 400), (11, 9, 300), (13, 21, 500), (127, 6, 200)])
-@pytest.mark.parametrize("mode", ["resident", "global", "planes"])
+@pytest.mark.parametrize("mode", ["resident", "global", "planes", "planes-global"])
 def test_philox_mode_matches_c_oracle(d, n, depth, mode):
     """Every opcode incl. M_X, RESET, SWAP and all three noise channels; ragged n (not a multiple of 16)."""
     from make_cases import random_program
     from oracle import c_oracle
-    if mode == "planes" and d > 3:
+    if mode.startswith("planes") and d > 3:
         pytest.skip("bit planes exist for d = 2, 3")
     prog = random_program(seed=1000 * d + n, n=n, d=d, depth=depth)
     shots, seed = 96, 2026 + d
@@ -213,6 +213,27 @@ def test_planes_kernel_large_resident(d, n):
         assert np.array_equal(arrs[key], fin[key]), key
     lanes = TableauEngine(prog).run(64, 0, seed, mode="lanes").cpu().numpy()
     assert np.array_equal(lanes, want[:64])
+
+
+@pytest.mark.parametrize("d,n,depth", [(3, 500, 4000), (2, 700, 6000)])
+def test_planes_on_a_global_image_beyond_the_shared_memory_limit(d, n, depth):
+    """d = 2, 3 tableaus whose bit planes do not fit in shared memory run the same plane interpreter on an image in
+    scratch memory (auto mode), bit-exact vs the C oracle incl. the final tableau, and identical to the uint8 lanes."""
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine
+    prog = random_program(seed=11 * n + d, n=n, d=d, depth=depth, p_meas=0.03)
+    eng = TableauEngine(prog)
+    assert eng.plan(None) == ("planes-global", False) and eng.plan("lanes")[0] == "lanes-global"
+    shots, seed = 24, 31
+    got = eng.run(shots, 0, seed, keep_tableau=True).cpu().numpy()
+    want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
+                             channel=prog.noise_channel, want_final=True)
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, shots - 1)
+    for key in ("x", "z", "p", "dx", "dz", "dp"):
+        assert np.array_equal(arrs[key], fin[key]), key
+    assert np.array_equal(eng.run(shots, 0, seed, mode="lanes").cpu().numpy(), want)
 
 
 def test_planes_continue_from_store_and_stepped():

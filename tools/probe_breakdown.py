@@ -35,4 +35,4 @@ for name, c in variants.items():
     prog = compile_circuits([c])
     ms = timeit(prog, shots, mode)
     print(f"{name:14s} ops={prog.n_ops:5d} meas={prog.n_meas:4d} shots={shots} {ms:9.3f} ms  "
-          f"{shots * max(prog.n_user_gates,1) / ms / 1e3:10.3e} shot*gates/s")
+          f"{shots * max(prog.n_user_gates,1) / ms * 1e3:10.3e} shot*gates/s")
