@@ -340,6 +340,48 @@ def test_cluster_interpreter_matches_c_oracle(d, n, depth, csize, monkeypatch):
         assert np.array_equal(arrs[key], fin[key]), key
 
 
+@pytest.mark.parametrize("d,n", [(5, 150), (2, 97), (7, 700)])
+def test_cluster_runs_of_measurements(d, n):
+    """Runs of M ops with no gate in between are where the cluster interpreter drops its barriers (deterministic
+    measurements) and prefetches rows: repeated rounds of all-qudit measurement (second round fully deterministic),
+    duplicates inside a run, RESETs and noise splitting runs, factor lists of several generators; bit-exact vs the C
+    oracle incl. the final tableau."""
+    import random
+    from oracle import c_oracle
+    from sdim_b200.circuit import Circuit
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    from make_cases import ONE, TWO
+    rng = random.Random(17 * n + d)
+    c = Circuit(n, d)
+    for _ in range(6 * n):
+        if rng.random() < 0.45:
+            a, b = rng.sample(range(n), 2)
+            c.add_gate(rng.choice(TWO), a, b)
+        else:
+            c.add_gate(rng.choice(ONE), rng.randrange(n))
+    order = list(range(n))
+    c.add_gate("M", order)                                   # random and deterministic outcomes interleaved
+    rng.shuffle(order)
+    c.add_gate("M", order)                                   # all deterministic now: long runs
+    c.add_gate("M", [order[0], order[0], order[1]])          # the same qudit twice in one run
+    for q in order[:10]:
+        c.add_gate("RESET", q)
+    c.add_gate("N1", order[3], prob=0.5, noise_channel="d")
+    c.add_gate("H", order[5])
+    c.add_gate("M", order[:40])
+    prog = compile_circuits([c])
+    shots, seed = 5, 77
+    want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
+                             channel=prog.noise_channel, want_final=True)
+    eng = TableauEngine(prog)
+    got = eng.run(shots, 0, seed, mode="cluster", keep_tableau=True).cpu().numpy()
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, shots - 1)
+    for key in ("x", "z", "p", "dx", "dz", "dp"):
+        assert np.array_equal(arrs[key], fin[key]), key
+
+
 def test_cluster_continue_from_store_and_stepped(monkeypatch):
     """!FRESH path and the unlayered stream of the cluster interpreter: stepping through the op stream in chunks on
     a persistent store gives the records and the store of one fused launch (and of the one-CTA kernel)."""
