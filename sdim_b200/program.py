@@ -144,8 +144,9 @@ class Program:
             from .dist import simulate_sharded
             rec = simulate_sharded(self, compiled, shots, seed, mode=mode)
         else:
-            rec = self._run_local(compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode)
-        table = RecordTable(values=rec & 0x7F, deterministic=(rec & 0x80) != 0,
+            rec = self._run_local(compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split=True)
+        values, det = rec if isinstance(rec, tuple) else (rec & 0x7F, (rec & 0x80) != 0)
+        table = RecordTable(values=values, deterministic=det,
                             meas_qudit=compiled.meas_qudit, meas_round=compiled.meas_round,
                             seed=seed, shot_offset=shot_offset)
         self.last_records = table
@@ -165,7 +166,11 @@ class Program:
         self._tableau_thunk = None
         return out
 
-    def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode) -> np.ndarray:
+    WAVE_RECORD_BYTES = 256 << 20      # records per launch when the shots do not need an HBM tableau each
+
+    def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split: bool = False):
+        """Packed record bytes uint8[shots, n_meas]; with `split`, (values, deterministic) instead — unpacked wave
+        by wave while the device is busy with the next wave."""
         import torch
         engine = self._get_engine(compiled)
         rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
@@ -179,16 +184,60 @@ class Program:
             per_shot = engine.layout.shot_bytes + 3 * compiled.n_meas + 2 * compiled.n_noise
             wave = max(1, min(shots, int(0.6 * free_bytes) // max(per_shot, 1)))
         elif shots > 0:
-            wave = max(1, min(shots, (4 << 30) // max(compiled.n_meas, 1)))       # <= 4 GiB of records per launch
+            wave = max(1, min(shots, self.WAVE_RECORD_BYTES // max(compiled.n_meas, 1)))
         out = np.empty((shots, compiled.n_meas), dtype=np.uint8)
-        for lo in range(0, shots, max(wave, 1)):
-            hi = min(shots, lo + wave)
-            store = self._initial_store(engine, hi - lo)
-            rec = engine.run(hi - lo, shot_offset + lo, seed,
-                             None if rm is None else rm[lo:hi], None if rn is None else rn[lo:hi],
-                             mode=mode, tableau=store, fresh=store is None)
-            out[lo:hi] = rec.cpu().numpy()
-            del store, rec
+        det = np.empty((shots, compiled.n_meas), dtype=bool) if split else None
+
+        def deliver(lo, hi, packed):
+            if split:
+                np.bitwise_and(packed, 0x7F, out=out[lo:hi])
+                np.not_equal(packed & 0x80, 0, out=det[lo:hi])
+            else:
+                out[lo:hi] = packed
+
+        n_waves = (shots + max(wave, 1) - 1) // max(wave, 1) if shots > 0 else 0
+        if n_waves <= 1:
+            if shots > 0:
+                store = self._initial_store(engine, shots)
+                rec = engine.run(shots, shot_offset, seed, rm, rn, mode=mode, tableau=store, fresh=store is None)
+                deliver(0, shots, rec.cpu().numpy())
+                del store, rec
+        else:
+            # Several waves: records leave the device through two pinned staging buffers on a copy stream, so the
+            # device-to-host transfer and the host-side copy of wave k overlap the simulation of wave k + 1.
+            dev = engine.device
+            with torch.cuda.device(dev):
+                compute, copier = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+                recs = [torch.empty((wave, compiled.n_meas), dtype=torch.uint8, device=dev) for _ in range(2)]
+                pins = [torch.empty((wave, compiled.n_meas), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+                copied = [None, None]                            # (event, lo, hi) of the copy in flight per buffer
+
+                def collect(slot):
+                    if copied[slot] is not None:
+                        ev, lo, hi = copied[slot]
+                        ev.synchronize()
+                        deliver(lo, hi, pins[slot][: hi - lo].numpy())
+                        copied[slot] = None
+
+                for k, lo in enumerate(range(0, shots, wave)):
+                    hi, slot = min(shots, lo + wave), k & 1
+                    collect(slot)                                # wave k - 2 has left both buffers of this slot
+                    store = self._initial_store(engine, hi - lo)
+                    engine.run(hi - lo, shot_offset + lo, seed,
+                               None if rm is None else rm[lo:hi], None if rn is None else rn[lo:hi],
+                               mode=mode, tableau=store, fresh=store is None, records=recs[slot][: hi - lo])
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                    with torch.cuda.stream(copier):
+                        copier.wait_event(done)
+                        pins[slot][: hi - lo].copy_(recs[slot][: hi - lo], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copier)
+                    copied[slot] = (ev, lo, hi)
+                    collect(slot ^ 1)                            # host-side copy of wave k - 1 while wave k runs
+                    del store
+                collect(0)
+                collect(1)
 
         def last_shot_tableau(last=shots - 1):
             one = engine.alloc_tableau(1)
@@ -200,7 +249,7 @@ class Program:
             return ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, engine.export(one, 0))
 
         self._tableau_thunk = last_shot_tableau if shots > 0 else None
-        return out
+        return (out, det) if split else out
 
     def simulate(self, shots: int = 1, show_measurement: bool = False, record_tableau: bool = False,
                  force_tableau: bool = False, verbose: bool = False, show_gate: bool = False, exact: bool = False,

@@ -253,3 +253,20 @@ def test_extended_tableau_gate_methods_match_oracle():
         for got, want in zip((t.x_block, t.z_block, t.phase_vector, t.destab_x_block, t.destab_z_block,
                               t.destab_phase_vector), o.arrays()):
             assert np.array_equal(got, want)
+
+
+def test_many_waves_pipeline_gives_the_same_records():
+    """Large shot counts run in waves whose records leave the device through pinned double buffers on a copy stream
+    (Program._run_local); forcing tiny waves must not change a single record, in resident and HBM-store modes."""
+    from sdim_b200 import Program
+    from make_cases import random_circuit
+    circ = random_circuit(seed=9, n=11, d=3, depth=150)
+    prog = Program(circ)
+    want = prog.simulate_records(1000, seed=4).values
+    want_det = prog.last_records.deterministic
+    small = Program(circ)
+    small.WAVE_RECORD_BYTES = 64 * small._compiled().n_meas          # 64 shots per wave: 16 waves, last one ragged
+    got = small.simulate_records(1000, seed=4)
+    assert np.array_equal(got.values, want) and np.array_equal(got.deterministic, want_det)
+    got = small.simulate_records(130, seed=4, shot_offset=870)
+    assert np.array_equal(got.values, want[870:])
