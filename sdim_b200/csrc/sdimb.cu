@@ -527,6 +527,11 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
   auto flush = [&]() {
     for (auto& layer : layers) {
       if (layer.empty()) continue;
+      // ops of a layer commute: order them by opcode, so that a warp (which takes every SDIMB_SCHED_WARPS-th op)
+      // runs gates of one kind back to back and stays in the same stretch of the interpreter's code
+      std::stable_sort(layer.begin(), layer.end(), [&](int64_t x, int64_t y) {
+        return (ops[4 * x] & SDIMB_OP_MASK) < (ops[4 * y] & SDIMB_OP_MASK);
+      });
       int k = 0;
       for (int64_t i : layer) {
         const int32_t* o = ops + 4 * i;
