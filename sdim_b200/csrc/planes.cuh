@@ -550,12 +550,16 @@ __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(c
     cta_sync();
     bool dirty = false;                    // some gate may have added to a private phase accumulator since the last fold
 
+    int4 ahead = make_int4(SDIMB_OP_I, 0, 0, 0);                // ops of the next batch, fetched one batch early
+    if (lane < p.n_ops) ahead = __ldg(p.ops + lane);
     for (int64_t i0 = 0; i0 < p.n_ops; i0 += 32) {
       // each warp fetches the same 32 ops, one per lane, and keeps the ones it has to execute: collective ops
       // (measurements, barriers) and its own share of the gates; the fetching lane resolves N1 events, so events
-      // that do not fire are never dispatched
-      int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
-      if (i0 + lane < p.n_ops) mine = __ldg(p.ops + i0 + lane);
+      // that do not fire are never dispatched.  The load of the following batch is issued now and lands while
+      // this batch executes.
+      int4 mine = ahead;
+      ahead = make_int4(SDIMB_OP_I, 0, 0, 0);
+      if (i0 + 32 + lane < p.n_ops) ahead = __ldg(p.ops + i0 + 32 + lane);
       const int owner = (mine.x >> SDIMB_OP_WARP_SHIFT) & 0xFF;
       mine.x &= SDIMB_OP_MASK;
       const bool collective = mine.x >= SDIMB_OP_M && mine.x != SDIMB_OP_N1;      // M, M_X, RESET, BARRIER
