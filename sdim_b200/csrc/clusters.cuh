@@ -17,15 +17,19 @@
 //                 dot products, x_p . z_p and the deterministic-branch sums are reduced with distributed-shared-
 //                 memory atomics into the CTA that owns the lane word (phases are lane-partitioned like gates).
 //
-// Synchronisation is the hardware cluster barrier (release/acquire at cluster scope, ~0.2 us):
+// Synchronisation is the hardware cluster barrier (release/acquire at cluster scope; 1 000 - 1 500 cycles here
+// with the L1 invalidate and the skew between CTAs), used only where ownership changes hands:
 //   A   before a measurement that follows gates (lane-partitioned writes -> row-partitioned reads)
 //   B1  random branch only: every CTA has read row q before its owner updates it
-//   B2  partial sums have arrived in their owners' shared memory
-// Nothing else: after B2 a CTA only writes phase words it owns, which no other CTA reads before the next B2
-// (the old pivot phase travels through shared memory), so back-to-back measurements cost one or two barriers
-// and gates after a measurement need none.  All cluster-shared accumulators are double-buffered by measurement
-// parity and zeroed by their owner when consumed: a CTA that races ahead into measurement k+1 adds into the
-// other buffer, and cannot reach measurement k+2 before every CTA has finished k.
+//   B2  random branch, and deterministic branch of a RESET (every CTA needs the outcome for the correction):
+//       the partial sums have arrived in their owners' shared memory
+// After B2 a CTA only writes phase words it owns, which no other CTA reads before the next B2 (the old pivot phase
+// travels through shared memory), so gates after a measurement need no barrier.  A deterministic M / M_X writes
+// nothing to the tableau and runs with NO cluster barrier: each CTA sends its partial sums to a ring slot in CTA 0
+// in one packed atomic and moves on, CTA 0 writes the record one measurement later; the row of the next
+// measurement is fetched with cp.async meanwhile.  The accumulators of the barrier-carrying measurements are
+// double-buffered by their parity and zeroed by their owner when consumed: a CTA that races ahead adds into the
+// other set, and cannot reach the measurement after that before every CTA has finished this one.
 //
 // Same arithmetic as lanes.cuh (its helpers are reused); same reference behaviour (file:line citations there).
 #pragma once
