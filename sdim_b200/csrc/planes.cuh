@@ -462,8 +462,15 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
 // per-CTA slab of caller-provided scratch (L2 / HBM) — the same bit planes for tableaus beyond the shared-memory
 // limit (d = 3: n > ~440, d = 2: n > ~630), 4x / 8x fewer bytes per gate than the uint8 lanes; phase accumulators and
 // measurement scratch stay in shared memory.  Two instantiations, so the resident one keeps LDS / STS.
+// The global-image variant is bounded by latency, not by shared memory: 8 CTAs (32 warps) per SM at 64 registers
+// measured best (7: -1 %, 9: -1 %, 10: -17 %, the default 80 registers / 6 CTAs: -12 %).  The resident variant keeps
+// the compiler's own register choice (0 = no minimum: small tableaus run a dozen CTAs per SM).
+#ifndef SDIMB_PLANES_GLOBAL_MIN_CTAS
+#define SDIMB_PLANES_GLOBAL_MIN_CTAS 8
+#endif
 template <int D, bool GLOBAL>
-__global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS) interp_planes_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS, GLOBAL ? SDIMB_PLANES_GLOBAL_MIN_CTAS : 0)
+interp_planes_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   Geo<D> G;

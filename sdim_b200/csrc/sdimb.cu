@@ -54,6 +54,10 @@ int check_dims(int n, int d) {
 int block_threads(int W) {
   int t = ((W / 4) + 31) / 32 * 32;
   if (t < 32) t = 32;
+  if (const char* env = std::getenv("SDIMB_LANES_MIN_THREADS")) {   // developer knob (A/B timings)
+    const int m = std::atoi(env);
+    if (m > t && m <= kMaxThreads) t = m / 32 * 32;
+  }
   if (t > kMaxThreads) t = t > kWideThreads ? kWideThreads : t;   // > 256 threads run interp_kernel_wide
   return t;
 }
@@ -80,8 +84,16 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
   if ((flags & SDIMB_FORCE_PLANES) && !planes_fit) return SDIMB_ETOOBIG;
   if ((flags & SDIMB_FORCE_RESIDENT) && !fits) return SDIMB_ETOOBIG;
   const bool free_choice = !(flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES | SDIMB_CLUSTER));
+  if (free_choice && !(flags & SDIMB_FORCE_PLANES) && planes_ok) {
+    // Shared memory holds few large images: at 3 or fewer resident CTAs per SM the same interpreter on an L2 image
+    // with 8 CTAs per SM is faster (d = 3: n = 224 +19 %, 256 +22 %; d = 2: n = 320 +21 %, 400 +52 %); at 4 it is a
+    // tie (d = 3, n = 200), above that shared memory wins (d = 3, n = 160: 5.0e9 against 3.7e9).
+    const size_t per_cta = planes::planes_smem_bytes(n, d) + 1024;
+    const int resident_ctas = planes_fit ? (int)((228u * 1024u) / per_cta) : 0;
+    if (resident_ctas >= 4 || !planes_global_ok) { if (planes_fit) return 2; }
+    else return 3;
+  }
   if (planes_fit && free_choice) return 2;
-  if (planes_global_ok && !fits && free_choice) return 3;
   return (fits && !(flags & SDIMB_FORCE_GLOBAL)) ? 1 : 0;
 }
 
@@ -244,6 +256,14 @@ int sdimb_run(const SdimbRunArgs* a) {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
+  // the global-image plane interpreter needs its slabs; a caller that brought none still gets the resident one
+  // where that fits (it was the only plane interpreter of this ABI's first version)
+  if (kernel == 3 && !(a->flags & SDIMB_FORCE_GLOBAL) && planes::planes_smem_bytes(a->n, a->d) <= (size_t)kSmemLimit &&
+      (!a->scratch || a->scratch_bytes < (int64_t)(256 + planes::planes_row_bytes(a->n, a->d)))) {
+    SdimbRunArgs b = *a;
+    b.flags |= SDIMB_FORCE_PLANES;
+    return sdimb_run(&b);
+  }
   if (kernel == 3) {
     // bit planes on a global image: 4 warps per shot, one slab of scratch per resident CTA, shots claimed dynamically
     size_t smem = 0;
@@ -417,10 +437,18 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   if (n_noise > 0 && !replay_noise && (!noise_thresh24 || !noise_channel)) return SDIMB_EINVAL;
   if (shots == 0) return SDIMB_OK;
 
-  const uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES |
-                                       SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER);
-  const int kernel = plan_kernel(n, d, mode_flags, L.np);
+  uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES |
+                                 SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER);
+  int kernel = plan_kernel(n, d, mode_flags, L.np);
   if (kernel < 0) return kernel;
+  // A few shots of a d = 2, 3 tableau too large for shared memory: one uint8 tableau per thread-block cluster beats
+  // one CTA per shot on bit planes (n = 2048, 8 shots: 12.8 ms against 30 ms), as long as every shot gets a cluster
+  if (kernel == 3 && !(mode_flags & SDIMB_FORCE_PLANES) && planes::planes_smem_bytes(n, d) > (size_t)kSmemLimit &&
+      plan_cluster(L, shots, mode_flags) > 0) {
+    mode_flags |= SDIMB_FORCE_LANES;
+    kernel = plan_kernel(n, d, mode_flags, L.np);
+    if (kernel < 0) return kernel;
+  }
   std::vector<int32_t> sched;
   const int32_t* up_ops = ops;
   int64_t up_n = n_ops;

@@ -192,27 +192,57 @@ def test_many_shots_multiple_waves_are_race_free():
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("d,n", [(3, 256), (2, 300), (3, 440)])
-def test_planes_kernel_large_resident(d, n):
-    """Bit-plane interpreter at the headline size and near the shared-memory limit, vs the C oracle; the plane
-    kernel is what `auto` picks for d in {2, 3}."""
+@pytest.mark.parametrize("d,n,auto", [(3, 256, "planes-global"), (2, 300, "planes-resident"), (3, 440, "planes-global"),
+                                      (3, 160, "planes-resident")])
+def test_planes_kernel_large_resident(d, n, auto):
+    """Bit-plane interpreter at the headline size and near the shared-memory limit, vs the C oracle, with the image
+    in shared memory ("planes") and in scratch memory ("planes-global"); `auto` picks the plane interpreter for d in
+    {2, 3}: resident while four or more CTAs fit per SM, on the global image below that."""
     from oracle import c_oracle
     from sdim_b200.engine import TableauEngine
     from sdim_b200.ir import compile_circuits
     from sdim_b200.workloads import noisy_random_clifford
     prog = compile_circuits([noisy_random_clifford(n, 2500, d, prob=0.02)])
     eng = TableauEngine(prog)
-    assert eng.plan(None)[0] == "planes-resident" and not eng.plan(None)[1]
+    assert eng.plan(None) == (auto, False) and eng.plan("planes") == ("planes-resident", False)
     shots, seed = 600, 11
-    got = eng.run(shots, 0, seed, keep_tableau=True).cpu().numpy()
     want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
                              channel=prog.noise_channel, want_final=True)
-    assert np.array_equal(got, want)
-    arrs = eng.export(eng.tableau, shots - 1)
-    for key in ("x", "z", "p", "dx", "dz", "dp"):
-        assert np.array_equal(arrs[key], fin[key]), key
+    for mode in ("planes", "planes-global", None):
+        got = eng.run(shots, 0, seed, keep_tableau=True, mode=mode).cpu().numpy()
+        assert np.array_equal(got, want), mode
+        arrs = eng.export(eng.tableau, shots - 1)
+        for key in ("x", "z", "p", "dx", "dz", "dp"):
+            assert np.array_equal(arrs[key], fin[key]), (mode, key)
     lanes = TableauEngine(prog).run(64, 0, seed, mode="lanes").cpu().numpy()
     assert np.array_equal(lanes, want[:64])
+
+
+def test_plane_interpreter_without_scratch_stays_resident():
+    """A C-ABI caller that passes no scratch (the slabs of the global image) still gets the resident plane interpreter
+    where it fits: same records."""
+    import ctypes as C
+    import torch
+    from sdim_b200 import _native as N
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.workloads import noisy_random_clifford
+    prog = compile_circuits([noisy_random_clifford(256, 300, 3, prob=0.05)])
+    eng = TableauEngine(prog)
+    want = eng.run(32, 0, 5).cpu().numpy()
+    rec = torch.zeros((32, prog.n_meas), dtype=torch.uint8, device="cuda")
+    a = N.SdimbRunArgs()
+    a.struct_size = C.sizeof(N.SdimbRunArgs)
+    a.flags = N.FRESH
+    a.n, a.d, a.shots, a.shot_offset = 256, 3, 32, 0
+    a.ops, a.n_ops = eng.ops.data_ptr(), prog.n_ops
+    a.records, a.n_meas, a.rec_stride = rec.data_ptr(), prog.n_meas, prog.n_meas
+    a.noise_thresh24, a.noise_channel, a.n_noise = eng.noise_thresh.data_ptr(), eng.noise_channel.data_ptr(), prog.n_noise
+    a.seed = 5
+    a.stream = torch.cuda.current_stream().cuda_stream
+    N.check(N.lib().sdimb_run(C.byref(a)))
+    torch.cuda.synchronize()
+    assert np.array_equal(rec.cpu().numpy(), want)
 
 
 @pytest.mark.parametrize("d,n,depth", [(3, 500, 4000), (2, 700, 6000)])
@@ -226,7 +256,7 @@ def test_planes_on_a_global_image_beyond_the_shared_memory_limit(d, n, depth):
     eng = TableauEngine(prog)
     assert eng.plan(None) == ("planes-global", False) and eng.plan("lanes")[0] == "lanes-global"
     shots, seed = 24, 31
-    got = eng.run(shots, 0, seed, keep_tableau=True).cpu().numpy()
+    got = eng.run(shots, 0, seed, keep_tableau=True, mode="planes-global").cpu().numpy()
     want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
                              channel=prog.noise_channel, want_final=True)
     assert np.array_equal(got, want)
@@ -234,6 +264,7 @@ def test_planes_on_a_global_image_beyond_the_shared_memory_limit(d, n, depth):
     for key in ("x", "z", "p", "dx", "dz", "dp"):
         assert np.array_equal(arrs[key], fin[key]), key
     assert np.array_equal(eng.run(shots, 0, seed, mode="lanes").cpu().numpy(), want)
+    assert np.array_equal(eng.run(shots, 0, seed).cpu().numpy(), want)      # auto: planes, or clusters for few shots
 
 
 def test_planes_continue_from_store_and_stepped():
@@ -403,6 +434,22 @@ def test_cluster_continue_from_store_and_stepped(monkeypatch):
                 records=rec, mode="cluster")
     assert np.array_equal(rec.cpu().numpy(), fused)
     assert torch.equal(store, fused_tab)
+
+
+def test_few_shots_of_a_large_qubit_tableau_take_the_cluster_path():
+    """d = 2, 3 beyond the shared-memory limit: many shots run bit planes on a global image, a few shots run one uint8
+    tableau per thread-block cluster (auto decides from the shot count); same records either way."""
+    from oracle import c_oracle
+    from sdim_b200 import generate_random_clifford_circuit
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    prog = compile_circuits([generate_random_clifford_circuit(1024, 3000, 3, measurement_rounds=1, seed=2)])
+    eng = TableauEngine(prog)
+    assert eng.plan(None)[0] == "planes-global"
+    assert eng._auto_mode(None, 2) == "lanes" and eng._auto_mode(None, 5000) is None
+    few = eng.run(2, 0, 9).cpu().numpy()
+    assert np.array_equal(few, eng.run(2, 0, 9, mode="planes-global").cpu().numpy())
+    assert np.array_equal(few, c_oracle.run_philox(prog, 2, 0, 9))
 
 
 def test_cluster_is_the_default_for_a_large_single_tableau():
