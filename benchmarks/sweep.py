@@ -16,8 +16,9 @@ from sdim_b200.workloads import noisy_random_clifford  # noqa: E402
 def point(n, d, shots, reps=2):
     prog = compile_circuits([noisy_random_clifford(n, 8 * n, d)])
     eng = TableauEngine(prog)
-    kernel, need_tab = eng.plan(None)
-    csize = eng.cluster_size(shots) if kernel == "lanes-global" else 0
+    mode = eng._auto_mode(None, shots)               # what `auto` resolves to for this shot count
+    kernel, need_tab = eng.plan(mode)
+    csize = eng.cluster_size(shots, mode) if kernel == "lanes-global" else 0
     tab = eng.alloc_tableau(shots) if need_tab else None
     rec = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device="cuda")
     eng.run(shots, 0, 1, tableau=tab, records=rec)

@@ -104,6 +104,12 @@ int planes_global_ctas(int n, int d, size_t* smem_out) {
   if (smem_out) *smem_out = smem;
   auto kern = (d == 2) ? planes::interp_planes_kernel<2, true> : planes::interp_planes_kernel<3, true>;
   int dev = 0, sms = 0, per_sm = 0;
+  // The image is read through L1: ask for no more shared memory per SM than the CTAs the register file admits need
+  // (headline: 20 % instead of the driver's choice, +1 %; a full carve-out, as a co-resident shared-memory kernel
+  // would force, costs 25 %).
+  int carve = (int)((100 * (size_t)SDIMB_PLANES_GLOBAL_MIN_CTAS * (smem + 1024) + 228 * 1024 - 1) / (228 * 1024));
+  if (carve > 100) carve = 100;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * SDIMB_SCHED_WARPS, smem) != cudaSuccess || per_sm < 1) {
