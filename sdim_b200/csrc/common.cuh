@@ -62,6 +62,11 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   return make_uint4(c0, c1, c2, c3);
 }
 
+struct PlaneGeo {   // bit-plane interpreter: geometry and shared-memory offsets computed once on the host (planes::make_plane_geo)
+  int np, Wb, RS, gpw, jstep, row_words, slab_words, acc_words;
+  int off_ops, off_f, off_dotw, off_cnt, off_ar, off_br, off_xz, off_next;   // bytes from the phase accumulators' base
+};
+
 struct KParams {
   uint8_t* tab;
   const int4* ops;
@@ -84,4 +89,5 @@ struct KParams {
   unsigned int* shot_counter;  // bit-plane kernel: next unclaimed shot (nullable: static grid-stride)
   int wpc;                     // cluster interpreter: lane words owned by each CTA of the cluster
   uint32_t* plane_slab;        // bit-plane interpreter on a global image: gridDim slabs of planes_row_bytes each
+  PlaneGeo pg;                 // bit-plane interpreter: host-computed geometry (constant-bank operands instead of per-use arithmetic)
 };

@@ -121,97 +121,30 @@ struct PScratch {
   int* next;         // [2] shot claimed from the global counter (double-buffered)
 };
 
+template <bool FOUR_WARPS = false>   // FOUR_WARPS: the CTA is known to be multi-warp (global image), no test
 __device__ __forceinline__ void cta_sync() {
+  if (FOUR_WARPS) { __syncthreads(); return; }
   if (blockDim.x == 32) __syncwarp(); else __syncthreads();
 }
 
-// ---- gates: lane j of the warp owns lane word j of every row ------------------------------------------
-template <int D>
-__device__ __forceinline__ void g_h(const Geo<D>& G, int a, bool inverse) {
-  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
-    const XZ v = G.ld(a, j);
-    E p = G.ldp(j);
-    if (D == 3) {
-      p = add3(p, neg3(mul3(v.x, v.z)));                                  // phase -= x*z
-      G.st(a, j, inverse ? XZ{v.z, neg3(v.x)} : XZ{neg3(v.z), v.x});     // H: (x,z)<-(-z,x); H^-1: (x,z)<-(z,-x)
-    } else {
-      p.h ^= v.x.l & v.z.l;                                               // phase += 2*x*z (mod 4); H == H^-1
-      G.st(a, j, XZ{v.z, v.x});
-    }
-    G.stp(j, p);
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void g_p(const Geo<D>& G, int a, bool inverse) {
-  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
-    const XZ v = G.ld(a, j);
-    E p = G.ldp(j);
-    if (D == 3) {
-      p = add3(p, inverse ? E{0u, v.x.h} : E{v.x.h, 0u});                 // phase +-= x(x-1)/2 = [x == 2]
-      G.stz(a, j, add3(v.z, inverse ? neg3(v.x) : v.x));                  // z +-= x
-    } else {
-      if (inverse) { const uint32_t borrow = ~p.l & v.x.l; p.l ^= v.x.l; p.h ^= borrow; }   // phase -= x (mod 4)
-      else { const uint32_t carry = p.l & v.x.l; p.l ^= v.x.l; p.h ^= carry; }              // phase += x^2 = x
-      G.stz(a, j, E{v.z.l ^ v.x.l, 0u});
-    }
-    G.stp(j, p);
-  }
-}
-
-// Pauli X^a Z^b on qudit q: phase += po*(b*x - a*z)
-template <int D>
-__device__ __forceinline__ void g_pauli(const Geo<D>& G, int q, uint32_t a, uint32_t b) {
-  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
-    const XZ v = G.ld(q, j);
-    E p = G.ldp(j);
-    if (D == 3) p = add3(p, add3(smul3(v.x, b), smul3(v.z, (3u - a) % 3u)));
-    else p.h ^= ((b & 1u) ? v.x.l : 0u) ^ ((a & 1u) ? v.z.l : 0u);
-    G.stp(j, p);
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void g_cnot(const Geo<D>& G, int a, int b, bool inverse) {
-  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
-    const XZ va = G.ld(a, j), vb = G.ld(b, j);
-    if (D == 3) {
-      G.stx(b, j, add3(vb.x, inverse ? neg3(va.x) : va.x));               // x[t] +-= x[c]
-      G.stz(a, j, add3(va.z, inverse ? vb.z : neg3(vb.z)));               // z[c] -+= z[t]
-    } else {
-      G.stx(b, j, E{vb.x.l ^ va.x.l, 0u});
-      G.stz(a, j, E{va.z.l ^ vb.z.l, 0u});
-    }
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void g_cz(const Geo<D>& G, int a, int b, bool inverse) {
-  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {
-    const XZ va = G.ld(a, j), vb = G.ld(b, j);
-    E p = G.ldp(j);
-    if (D == 3) {
-      const E prod = mul3(va.x, vb.x);
-      p = add3(p, inverse ? neg3(prod) : prod);                           // phase +-= x[a]*x[b]
-      G.stz(a, j, add3(va.z, inverse ? neg3(vb.x) : vb.x));
-      G.stz(b, j, add3(vb.z, inverse ? neg3(va.x) : va.x));
-    } else {
-      p.h ^= va.x.l & vb.x.l;
-      G.stz(a, j, E{va.z.l ^ vb.x.l, 0u});
-      G.stz(b, j, E{vb.z.l ^ va.x.l, 0u});
-    }
-    G.stp(j, p);
-  }
-}
-
-template <int D>
-__device__ __forceinline__ void g_swap(const Geo<D>& G, int a, int b) {
-  for (int j = threadIdx.x & 31; j < G.Wb; j += 32) {   // lane j swaps lane word j (lane ownership holds across gates)
-    const XZ va = G.ld(a, j), vb = G.ld(b, j);
-    G.st(a, j, vb);
-    G.st(b, j, va);
-  }
-}
+// COMPACT (global image): the interpreter's hot code (dispatch, 13 gate handlers, measurement: ~30 KB) sits at the
+// capacity of the 32 KB instruction-cache level, and the 32 warps of an SM are in different handlers at any time.  The
+// compact form keeps one handler per gate FAMILY (direction and Pauli exponents become run-time selects), does not
+// unroll the lane-word loops and drops the one-warp tests of the CTA barriers: 26 % less code, +6.5 % on the headline.
+// The shared-memory instantiation keeps the specialised handlers (its SASS is unchanged).
+#ifndef SDIMB_PG_COMPACT
+#define SDIMB_PG_COMPACT 1
+#endif
+#define SDIMB_GATES_NS gates_std
+#define SDIMB_GATE_LOOP
+#include "planes_gates.inc"
+#undef SDIMB_GATES_NS
+#undef SDIMB_GATE_LOOP
+#define SDIMB_GATES_NS gates_compact
+#define SDIMB_GATE_LOOP _Pragma("unroll 1")
+#include "planes_gates.inc"
+#undef SDIMB_GATES_NS
+#undef SDIMB_GATE_LOOP
 
 // N1 event -> (a | b << 8), 0 if it does not fire: replayed, or Philox with the distribution of
 // sdim/program.py:486-507.  Evaluated by the lane that fetched the op, so events that do not fire never reach
@@ -236,7 +169,11 @@ __device__ __forceinline__ uint32_t p_noise_event(const KParams& p, int64_t j, i
 }
 
 // ---- measurement (whole CTA: 1 or SDIMB_SCHED_WARPS warps) -----------------------------------------------------
-template <int D>
+#ifndef SDIMB_PG_SKIPLIST       // column walk: skip the list bookkeeping of a warp none of whose 32 rows is listed
+#define SDIMB_PG_SKIPLIST 0
+#endif
+// FW: the CTA is known to have four warps (global image), see cta_sync
+template <int D, bool FW = false>
 __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local,
                               bool fold, uint32_t draw) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -254,7 +191,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
   if (tid < 4) S.cnt[4 * (S.parity ^ 1u) + tid] = 0;
   S.parity ^= 1u;
   if (fold) {
-    cta_sync();
+    cta_sync<FW>();
     for (int j = tid; j < Wb && nw > 1; j += nt) {
       E acc = G.ldp(j);
       for (int w = 1; w < nw; ++w) {
@@ -265,7 +202,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       }
       G.stp(j, acc);
     }
-    cta_sync();
+    cta_sync<FW>();
   }
 
   // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283); every warp looks itself
@@ -285,11 +222,10 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     const uint32_t ps_old = G.getp(piv);
     // one pass down the pivot column AND the destabilizer-p column: support list, values, stale destab entries
     uint32_t sd_part = 0;
-    for (int base = 0; base < n; base += nt) {
-      const int r = base + tid;
+    // one row of the walk, entries already loaded (all lanes of the warp call it together: it ballots)
+    auto walk_row = [&](const int r, const bool in, const XZ& s, const XZ& dd) {
       uint32_t xr = 0, zr = 0, od = 0;
-      if (r < n) {
-        const XZ s = G.ld(r, jp), dd = G.ld(r, jd);
+      if (in) {
         const uint32_t bm = 1u << bp;
         od = (dd.x.l | dd.x.h | dd.z.l | dd.z.h) & bm;
         if ((s.x.l | s.x.h | s.z.l | s.z.h) & bm) {            // the pivot acts on few qudits: most rows stop here
@@ -301,11 +237,21 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       }
       const bool act = (xr | zr) != 0, stale = !act && od != 0;
       const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, stale);
+#if SDIMB_PG_SKIPLIST
+      if ((ma | mb) == 0) return;                        // warp-uniform: no row of these 32 is on either list (the usual case)
+#endif
       uint32_t both = 0;                                 // list lengths packed: support | stale << 16
       if (lane == 0 && (ma | mb)) both = atomicAdd(&cnt[0], (uint32_t)__popc(ma) | ((uint32_t)__popc(mb) << 16));
       both = __shfl_sync(FULL, both, 0);
       if (act) S.ar[(both & 0xFFFFu) + __popc(ma & lt)] = (uint16_t)r;
       if (stale) S.br[(both >> 16) + __popc(mb & lt)] = (uint16_t)r;
+    };
+    for (int base = 0; base < n; base += nt) {
+      const int r = base + tid;
+      const XZ zero{E{0u, 0u}, E{0u, 0u}};
+      XZ s = zero, dd = zero;
+      if (r < n) { s = G.ld(r, jp); dd = G.ld(r, jd); }
+      walk_row(r, r < n, s, dd);
     }
     sd_part = __reduce_add_sync(FULL, sd_part);
     if (lane == 0 && sd_part) atomicAdd(&cnt[2], sd_part);
@@ -315,7 +261,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       if (j == jp) { x.l &= ~(1u << bp); x.h &= ~(1u << bp); }
       S.f[j] = (D == 3) ? make_uint2(x.h, x.l) : make_uint2(x.l, 0u);
     }
-    cta_sync();
+    cta_sync<FW>();
     const int nr_a = (int)(cnt[0] & 0xFFFFu), nr_b = (int)(cnt[0] >> 16);
     const uint32_t sd_raw = cnt[2] % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
@@ -328,10 +274,8 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       const E f{fv.x, fv.y};
       E dot{0u, 0u};
       if (f.l | f.h) {
-        for (int ri = gid; ri < nr_a; ri += gtot) {
-          const int r = S.ar[ri];
-          const uint32_t c = S.xz[r], s = c & 3u, t = c >> 2;
-          const XZ v = G.ld(r, j);
+        auto update_row = [&](const int r, const uint32_t c, const XZ& v) {
+          const uint32_t s = c & 3u, t = c >> 2;
           if (D == 3) {
             dot = add3(dot, smul3(v.z, s));                               // Z[:,i] . x_p  (old Z)
             G.st(r, j, XZ{add3(v.x, smul3(f, s)), add3(v.z, smul3(f, t))});
@@ -339,6 +283,10 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
             if (s) dot.l ^= v.z.l;
             G.st(r, j, XZ{E{v.x.l ^ (s ? f.l : 0u), 0u}, E{v.z.l ^ (t ? f.l : 0u), 0u}});
           }
+        };
+        for (int ri = gid; ri < nr_a; ri += gtot) {
+          const int r = S.ar[ri];
+          update_row(r, S.xz[r], G.ld(r, j));
         }
       }
       for (int off = Wb; off < 32 && gpw > 1; off <<= 1) {
@@ -347,7 +295,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       }
       if (gpw == 1 || lane < Wb) S.dotw[warp * Wb + j] = make_uint2(dot.l, dot.h);
     }
-    cta_sync();
+    cta_sync<FW>();
     // phase_i += f_i*ps + po*(f_i*dot_i + sd*f_i(f_i-1)/2*po)      (tableau_prime.py:310-312,317-319)
     for (int j = tid; j < Wb; j += nt) {
       const uint2 fv = S.f[j];
@@ -369,7 +317,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       }
       G.stp(j, ph);
     }
-    cta_sync();
+    cta_sync<FW>();
     // destabilizer p <- old pivot; stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333).
     // Only rows where something changes are touched: the support (list ar) and stale destabilizer rows (br).
     for (int i = tid; i < nr_a; i += nt) {
@@ -427,7 +375,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       a1 = __reduce_add_sync(FULL, a1);
       if (lane == 0) { cnt[3] = (uint32_t)total; cnt[2] = a1 % ORDER; }
     }
-    cta_sync();
+    cta_sync<FW>();
     const int total = (int)cnt[3];
     uint32_t part = 0;
     for (int r = tid; r < n; r += nt) {
@@ -447,13 +395,13 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     }
     part = __reduce_add_sync(FULL, part);
     if (lane == 0 && part) atomicAdd(&cnt[0], part);
-    cta_sync();
+    cta_sync<FW>();
     const uint32_t ap = (cnt[2] + PO * (cnt[0] % D)) % ORDER;
     outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);        // (-ap // po) % d  (tableau_prime.py:362)
     rec = outcome | SDIMB_REC_DET;
   }
   if (tid == 0) p.records[shot_local * p.rec_stride + slot] = (uint8_t)rec;
-  cta_sync();
+  cta_sync<FW>();
   return outcome;
 }
 
@@ -468,24 +416,69 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
 #ifndef SDIMB_PLANES_GLOBAL_MIN_CTAS
 #define SDIMB_PLANES_GLOBAL_MIN_CTAS 8
 #endif
+#ifndef SDIMB_PG_NOPAD          // global image: rows without the bank-conflict padding entry
+#define SDIMB_PG_NOPAD 0
+#endif
+#ifndef SDIMB_PG_HOSTGEO        // geometry and shared-memory offsets as kernel parameters (both instantiations)
+#define SDIMB_PG_HOSTGEO 0
+#endif
+#ifndef SDIMB_PG_SHFLOPS        // global image: staged ops broadcast by shuffle instead of a shared-memory round trip
+#define SDIMB_PG_SHFLOPS 1
+#endif
 template <int D, bool GLOBAL>
 __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS, GLOBAL ? SDIMB_PLANES_GLOBAL_MIN_CTAS : 0)
 interp_planes_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr bool CP = GLOBAL && SDIMB_PG_COMPACT != 0;     // compact dispatch form (see COMPACT above)
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   Geo<D> G;
+  PScratch S;
+  uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
+#if SDIMB_PG_HOSTGEO
+  // geometry and scratch offsets come from the host as kernel parameters: constant-bank operands, nothing for the
+  // compiler to rematerialise inside the dispatch loop (the arithmetic below was 11 % of the executed instructions)
+  G.n = p.n;
+  G.np = p.pg.np;
+  G.Wb = p.pg.Wb;
+  G.RS = p.pg.RS;
+  G.gpw = p.pg.gpw;
+  G.jstep = p.pg.jstep;
+  G.gsub = G.gpw > 1 ? lane / G.Wb : 0;
+  G.j0 = G.gpw > 1 ? lane % G.Wb : lane;
+  const int row_words = p.pg.row_words, acc_words = p.pg.acc_words;
+  if (GLOBAL) {
+    G.tab = p.plane_slab + (int64_t)blockIdx.x * p.pg.slab_words;
+  } else {
+    G.tab = sm;
+    sm += row_words;
+  }
+  G.ph_base = reinterpret_cast<uint2*>(sm);
+  G.pacc = G.phase_of(warp);
+  uint8_t* const sb = reinterpret_cast<uint8_t*>(sm);
+  S.ops = reinterpret_cast<int4*>(sb + p.pg.off_ops);
+  S.f = reinterpret_cast<uint2*>(sb + p.pg.off_f);
+  S.dotw = reinterpret_cast<uint2*>(sb + p.pg.off_dotw);
+  S.cnt = reinterpret_cast<uint32_t*>(sb + p.pg.off_cnt);
+  S.ar = reinterpret_cast<uint16_t*>(sb + p.pg.off_ar);
+  S.parity = 0;
+  S.br = reinterpret_cast<uint16_t*>(sb + p.pg.off_br);
+  S.xz = sb + p.pg.off_xz;
+  S.next = reinterpret_cast<int*>(sb + p.pg.off_next);
+#else
   G.n = p.n;
   G.np = (p.n + 31) / 32 * 32;
   G.Wb = 2 * G.np / 32;
-  G.RS = Geo<D>::EW * (G.Wb + 1);
+  // the padding entry keeps shared-memory column walks off one bank; a global image may drop it so that rows start on
+  // sector (n = 256, d = 3: cache-line) boundaries — its slab keeps the padded size either way
+  G.RS = Geo<D>::EW * (G.Wb + ((GLOBAL && SDIMB_PG_NOPAD != 0) ? 0 : 1));
   G.gpw = (G.Wb <= 32 && (32 % G.Wb) == 0) ? 32 / G.Wb : 1;
   G.gsub = G.gpw > 1 ? lane / G.Wb : 0;
   G.j0 = G.gpw > 1 ? lane % G.Wb : lane;
   G.jstep = G.gpw > 1 ? G.Wb : 32;
   const int row_words = (p.n * G.RS + 3) & ~3;
-  uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
   if (GLOBAL) {
-    G.tab = p.plane_slab + (int64_t)blockIdx.x * row_words;
+    const int slab_words = (p.n * Geo<D>::EW * (G.Wb + 1) + 3) & ~3;       // = planes_row_bytes / 4, the host's stride
+    G.tab = p.plane_slab + (int64_t)blockIdx.x * slab_words;
   } else {
     G.tab = sm;
     sm += row_words;
@@ -493,7 +486,6 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
   G.ph_base = reinterpret_cast<uint2*>(sm);
   G.pacc = G.phase_of(warp);
   const int acc_words = (nw * 2 * G.Wb + 3) & ~3;
-  PScratch S;
   S.ops = reinterpret_cast<int4*>(sm + acc_words);
   S.f = reinterpret_cast<uint2*>(S.ops + 32 * nw);
   S.dotw = S.f + G.Wb;
@@ -503,21 +495,22 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
   S.br = S.ar + G.np;
   S.xz = reinterpret_cast<uint8_t*>(S.br + G.np);
   S.next = reinterpret_cast<int*>(S.xz + G.np + ((4 - (G.np & 3)) & 3));
-  int4* my_ops = S.ops + 32 * warp;
+#endif
+  int4* const my_ops = S.ops + 32 * warp;
 
   for (int round = 0;; ++round) {
     // claim the next shot: dynamic when the caller provided a counter (shots differ in cost, CTAs in speed),
     // static grid-stride otherwise
     if (tid == 0)
       S.next[round & 1] = p.shot_counter ? (int)atomicAdd(p.shot_counter, 1u) : (int)(blockIdx.x + round * gridDim.x);
-    cta_sync();
+    cta_sync<CP>();
     const int64_t shot = S.next[round & 1];
     if (shot >= p.shots) break;
     // ---- load: |0...0> or pack from the uint8 store ----
     for (int i = tid; i < row_words; i += nt) G.tab[i] = 0u;
     for (int i = tid; i < acc_words; i += nt) reinterpret_cast<uint32_t*>(G.ph_base)[i] = 0u;
     if (tid < 8) S.cnt[tid] = 0;
-    cta_sync();
+    cta_sync<CP>();
     uint8_t* T8 = p.tab ? p.tab + shot * p.shot_bytes : nullptr;
     G.pacc = G.phase_of(0);
     if (p.flags & SDIMB_FRESH) {
@@ -554,7 +547,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       }
     }
     G.pacc = G.phase_of(warp);
-    cta_sync();
+    cta_sync<CP>();
     bool dirty = false;                    // some gate may have added to a private phase accumulator since the last fold
 
     int4 ahead = make_int4(SDIMB_OP_I, 0, 0, 0);                // ops of the next batch, fetched one batch early
@@ -590,52 +583,85 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       uint32_t todo = __ballot_sync(0xFFFFFFFFu, live);
       // positions of ops (executed by ANY warp) that may touch a phase accumulator: identical in every warp
       const uint32_t gate_pos = __ballot_sync(0xFFFFFFFFu, mine.x != SDIMB_OP_I && !collective);
-      __syncwarp();
-      my_ops[lane] = mine;
-      __syncwarp();
+      if constexpr (!(GLOBAL && SDIMB_PG_SHFLOPS != 0)) {
+        __syncwarp();
+        my_ops[lane] = mine;
+        __syncwarp();
+      }
 #pragma unroll 1
       while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        const int4 op = my_ops[k];
-        switch (op.x) {
-          case SDIMB_OP_X: g_pauli<D>(G, op.y, 1u, 0u); break;
-          case SDIMB_OP_X_INV: g_pauli<D>(G, op.y, D - 1u, 0u); break;
-          case SDIMB_OP_Z: g_pauli<D>(G, op.y, 0u, 1u); break;
-          case SDIMB_OP_Z_INV: g_pauli<D>(G, op.y, 0u, D - 1u); break;
-          case SDIMB_OP_H: g_h<D>(G, op.y, false); break;
-          case SDIMB_OP_H_INV: g_h<D>(G, op.y, true); break;
-          case SDIMB_OP_P: g_p<D>(G, op.y, false); break;
-          case SDIMB_OP_P_INV: g_p<D>(G, op.y, true); break;
-          case SDIMB_OP_CNOT: g_cnot<D>(G, op.y, op.z, false); break;
-          case SDIMB_OP_CNOT_INV: g_cnot<D>(G, op.y, op.z, true); break;
-          case SDIMB_OP_CZ: g_cz<D>(G, op.y, op.z, false); break;
-          case SDIMB_OP_CZ_INV: g_cz<D>(G, op.y, op.z, true); break;
-          case SDIMB_OP_SWAP: g_swap<D>(G, op.y, op.z); break;
-          case SDIMB_OP_M_X:
-            cta_sync();
-            if (warp == 0) g_h<D>(G, op.y, true);
-            dirty = true;                                                  // row q changed: the measurement must sync
-            // fallthrough
-          case SDIMB_OP_M:
-          case SDIMB_OP_RESET: {
-            const bool fold = dirty || (gate_pos & ((1u << k) - 1u)) != 0;   // gates since the last measurement?
-            const uint32_t m = p_measure<D>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);
-            dirty = false;
-            if (op.x == SDIMB_OP_RESET) {
-              if (m && warp == 0) g_pauli<D>(G, op.y, D - m, 0u);      // program.py:335-339
-              cta_sync();
-            }
+        int4 op;
+        if constexpr (GLOBAL && SDIMB_PG_SHFLOPS != 0) {      // the warp is converged here: broadcast from the fetching lane
+          op = make_int4(__shfl_sync(0xFFFFFFFFu, mine.x, k), __shfl_sync(0xFFFFFFFFu, mine.y, k),
+                         __shfl_sync(0xFFFFFFFFu, mine.z, k), __shfl_sync(0xFFFFFFFFu, mine.w, k));
+        } else {
+          op = my_ops[k];
+        }
+        // the measurement cases, shared by the two dispatch forms below
+#define SDIMB_COLLECTIVE_CASES(NS)                                                                                      \
+          case SDIMB_OP_M_X:                                                                                            \
+            cta_sync<CP>();                                                                                             \
+            if (warp == 0) NS::g_h<D>(G, op.y, true);                                                                   \
+            dirty = true;                       /* row q changed: the measurement must sync */                         \
+            /* fallthrough */                                                                                           \
+          case SDIMB_OP_M:                                                                                              \
+          case SDIMB_OP_RESET: {                                                                                        \
+            const bool fold = dirty || (gate_pos & ((1u << k) - 1u)) != 0;   /* gates since the last measurement? */   \
+            const uint32_t m = p_measure<D, CP>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);                  \
+            dirty = false;                                                                                              \
+            if (op.x == SDIMB_OP_RESET) {                                                                               \
+              if (m && warp == 0) NS::g_pauli<D>(G, op.y, D - m, 0u);   /* program.py:335-339 */                     \
+              cta_sync<CP>();                                                                                           \
+            }                                                                                                           \
+            break;                                                                                                      \
+          }
+        if constexpr (CP) {
+          switch (op.x) {
+          case SDIMB_OP_X: case SDIMB_OP_X_INV: case SDIMB_OP_Z: case SDIMB_OP_Z_INV: case SDIMB_OP_N1: {
+            // X^a Z^b: X (1,0), X^-1 (d-1,0), Z (0,1), Z^-1 (0,d-1), N1 the event resolved at fetch
+            const uint32_t e = (op.x == SDIMB_OP_X || op.x == SDIMB_OP_Z) ? 1u : D - 1u;
+            uint32_t pa = (op.x <= SDIMB_OP_X_INV) ? e : 0u, pb = (op.x <= SDIMB_OP_X_INV) ? 0u : e;
+            if (op.x == SDIMB_OP_N1) { pa = (uint32_t)op.z & 0xFFu; pb = (uint32_t)op.z >> 8; }
+            gates_compact::g_pauli<D>(G, op.y, pa, pb);
             break;
           }
-          case SDIMB_OP_N1: g_pauli<D>(G, op.y, (uint32_t)op.z & 0xFFu, (uint32_t)op.z >> 8); break;
-          case SDIMB_OP_BARRIER: cta_sync(); break;
+          case SDIMB_OP_H: case SDIMB_OP_H_INV: gates_compact::g_h<D>(G, op.y, op.x == SDIMB_OP_H_INV); break;
+          case SDIMB_OP_P: case SDIMB_OP_P_INV: gates_compact::g_p<D>(G, op.y, op.x == SDIMB_OP_P_INV); break;
+          case SDIMB_OP_CNOT: case SDIMB_OP_CNOT_INV: gates_compact::g_cnot<D>(G, op.y, op.z, op.x == SDIMB_OP_CNOT_INV); break;
+          case SDIMB_OP_CZ: case SDIMB_OP_CZ_INV: gates_compact::g_cz<D>(G, op.y, op.z, op.x == SDIMB_OP_CZ_INV); break;
+          case SDIMB_OP_SWAP: gates_compact::g_swap<D>(G, op.y, op.z); break;
+          SDIMB_COLLECTIVE_CASES(gates_compact)
+          case SDIMB_OP_BARRIER: cta_sync<CP>(); break;
           default: break;
+          }
+        } else {
+          switch (op.x) {
+          case SDIMB_OP_X: gates_std::g_pauli<D>(G, op.y, 1u, 0u); break;
+          case SDIMB_OP_X_INV: gates_std::g_pauli<D>(G, op.y, D - 1u, 0u); break;
+          case SDIMB_OP_Z: gates_std::g_pauli<D>(G, op.y, 0u, 1u); break;
+          case SDIMB_OP_Z_INV: gates_std::g_pauli<D>(G, op.y, 0u, D - 1u); break;
+          case SDIMB_OP_H: gates_std::g_h<D>(G, op.y, false); break;
+          case SDIMB_OP_H_INV: gates_std::g_h<D>(G, op.y, true); break;
+          case SDIMB_OP_P: gates_std::g_p<D>(G, op.y, false); break;
+          case SDIMB_OP_P_INV: gates_std::g_p<D>(G, op.y, true); break;
+          case SDIMB_OP_CNOT: gates_std::g_cnot<D>(G, op.y, op.z, false); break;
+          case SDIMB_OP_CNOT_INV: gates_std::g_cnot<D>(G, op.y, op.z, true); break;
+          case SDIMB_OP_CZ: gates_std::g_cz<D>(G, op.y, op.z, false); break;
+          case SDIMB_OP_CZ_INV: gates_std::g_cz<D>(G, op.y, op.z, true); break;
+          case SDIMB_OP_SWAP: gates_std::g_swap<D>(G, op.y, op.z); break;
+          SDIMB_COLLECTIVE_CASES(gates_std)
+          case SDIMB_OP_N1: gates_std::g_pauli<D>(G, op.y, (uint32_t)op.z & 0xFFu, (uint32_t)op.z >> 8); break;
+          case SDIMB_OP_BARRIER: cta_sync<CP>(); break;
+          default: break;
+          }
         }
+#undef SDIMB_COLLECTIVE_CASES
       }
       dirty = dirty || gate_pos != 0;      // conservative: gates of this batch behind its last measurement
     }
-    cta_sync();
+    cta_sync<CP>();
     if (p.flags & SDIMB_WRITEBACK) {      // fold the accumulators, then unpack into the uint8 store
       G.pacc = G.phase_of(0);
       for (int j = tid; j < G.Wb && nw > 1; j += nt) {
@@ -646,7 +672,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
         }
         G.stp(j, acc);
       }
-      cta_sync();
+      cta_sync<CP>();
       for (int q = warp; q < p.n; q += nw) {
         uint8_t* row8 = T8 + (int64_t)q * p.row_bytes;
         for (int ln = lane; ln < p.W; ln += 32) {
@@ -662,8 +688,31 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       }
       G.pacc = G.phase_of(warp);
     }
-    cta_sync();
+    cta_sync<CP>();
   }
+}
+
+// what the kernel prologue computes from (n, d, warps per CTA), for KParams::pg
+inline PlaneGeo make_plane_geo(int n, int d, int nw, bool global) {
+  PlaneGeo g;
+  const int EW = (d == 2) ? 2 : 4;
+  g.np = (n + 31) / 32 * 32;
+  g.Wb = 2 * g.np / 32;
+  g.RS = EW * (g.Wb + ((global && SDIMB_PG_NOPAD != 0) ? 0 : 1));
+  g.gpw = (g.Wb <= 32 && (32 % g.Wb) == 0) ? 32 / g.Wb : 1;
+  g.jstep = g.gpw > 1 ? g.Wb : 32;
+  g.row_words = (n * g.RS + 3) & ~3;
+  g.slab_words = (n * EW * (g.Wb + 1) + 3) & ~3;
+  g.acc_words = (nw * 2 * g.Wb + 3) & ~3;
+  g.off_ops = 4 * g.acc_words;
+  g.off_f = g.off_ops + 16 * 32 * nw;
+  g.off_dotw = g.off_f + 8 * g.Wb;
+  g.off_cnt = g.off_dotw + 8 * nw * g.Wb;
+  g.off_ar = g.off_cnt + 4 * 8;
+  g.off_br = g.off_ar + 2 * g.np;
+  g.off_xz = g.off_br + 2 * g.np;
+  g.off_next = g.off_xz + g.np + ((4 - (g.np & 3)) & 3);
+  return g;
 }
 
 // bytes of the row image of one shot (shared memory of a resident CTA, or one global slab of an overflow CTA)

@@ -283,6 +283,7 @@ int sdimb_run(const SdimbRunArgs* a) {
     auto kern = (a->d == 2) ? planes::interp_planes_kernel<2, true> : planes::interp_planes_kernel<3, true>;
     p.shot_counter = (unsigned int*)a->scratch;
     p.plane_slab = (uint32_t*)((uint8_t*)a->scratch + 256);
+    p.pg = planes::make_plane_geo(a->n, a->d, SDIMB_SCHED_WARPS, true);
     if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
     kern<<<(unsigned)grid, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p);
     g_launches++;
@@ -310,6 +311,7 @@ int sdimb_run(const SdimbRunArgs* a) {
       if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess)
         return SDIMB_ECUDA;
     }
+    p.pg = planes::make_plane_geo(a->n, a->d, nw, false);
     kern<<<(unsigned)grid, 32 * nw, smem, (cudaStream_t)a->stream>>>(p);
     g_launches++;
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
