@@ -63,9 +63,46 @@ class RecordTable:
             raise ValueError(f"qudit {qudit} has no measurement round {meas_round}")
         return int(hit[0])
 
+    def to_structured(self, num_qudits: Optional[int] = None) -> np.ndarray:
+        """The reference's record array: structured `[n_qudits, rounds, shots]` of MEASUREMENT_DTYPE
+        (sdim/program.py:34-40, the layout `simulate_frame` returns, :57-61).  Cells a qudit never reached (fewer
+        rounds than the maximum) stay zero, as in the reference's `np.zeros` allocation."""
+        n = int(num_qudits if num_qudits is not None else (self.meas_qudit.max() + 1 if self.meas_qudit.size else 0))
+        rounds = int(self.meas_round.max() + 1) if self.meas_round.size else 0
+        out = np.zeros((n, rounds, self.shots), dtype=MEASUREMENT_DTYPE)
+        shot_ids = np.arange(self.shot_offset, self.shot_offset + self.shots, dtype=np.int64)
+        for k in range(self.meas_qudit.size):
+            cell = out[int(self.meas_qudit[k]), int(self.meas_round[k])]
+            cell["qudit_index"] = int(self.meas_qudit[k])
+            cell["meas_round"] = int(self.meas_round[k])
+            cell["shot"] = shot_ids
+            cell["deterministic"] = self.deterministic[:, k]
+            cell["measurement_value"] = self.values[:, k]
+        return out
+
+    def save(self, path: str) -> str:
+        """Write the table as one compressed `.npz` (the reference's TODO.md:12 asks for numpy-array results):
+        values uint8 [shots, n_meas], the deterministic flags bit-packed along the measurement axis, the
+        (qudit, round) of every column, seed and shot offset.  `RecordTable.load` reads it back."""
+        if not path.endswith(".npz"):
+            path += ".npz"
+        np.savez_compressed(path, values=self.values, deterministic_bits=np.packbits(self.deterministic, axis=1),
+                            meas_qudit=self.meas_qudit, meas_round=self.meas_round,
+                            seed=np.uint64(self.seed), shot_offset=np.int64(self.shot_offset))
+        return path
+
+    @classmethod
+    def load(cls, path: str) -> "RecordTable":
+        with np.load(path) as z:
+            values = z["values"]
+            det = np.unpackbits(z["deterministic_bits"], axis=1, count=values.shape[1]).astype(bool)
+            return cls(values=values, deterministic=det, meas_qudit=z["meas_qudit"], meas_round=z["meas_round"],
+                       seed=int(z["seed"]), shot_offset=int(z["shot_offset"]))
+
 
 class Program:
-    def __init__(self, circuit: Circuit, tableau: Optional[ExtendedTableau] = None, device=None):
+    def __init__(self, circuit: Circuit, tableau: Optional[ExtendedTableau] = None, device=None,
+                 fold_gates: bool = False):
         d = circuit.dimension
         if not is_prime(d):
             raise ValueError(f"dimension {d} is not prime: only the prime-dimension (ExtendedTableau) path of the "
@@ -82,10 +119,18 @@ class Program:
         self._engine = None
         self._engine_key = None
         self.last_records: Optional[RecordTable] = None
+        # Not in the reference: fold runs of self-cancelling gates before upload (sdim_b200/peephole.py).  Records,
+        # final tableaus and the shot*gates count are unchanged; host-stepped modes (verbose / show_gate /
+        # record_tableau) always run the stream as written.
+        self.fold_gates = fold_gates
 
     # ---- engine plumbing -------------------------------------------------------------------------
-    def _compiled(self) -> CompiledProgram:
-        return compile_circuits(self.circuits)
+    def _compiled(self, fold: bool = False) -> CompiledProgram:
+        compiled = compile_circuits(self.circuits)
+        if fold:
+            from .peephole import fold_program
+            compiled = fold_program(compiled)
+        return compiled
 
     def _get_engine(self, compiled: CompiledProgram):
         from .engine import TableauEngine          # imports torch; kept out of module import time
@@ -133,7 +178,7 @@ class Program:
         method="tableau" (default): one full stabilizer tableau per shot.
         method="frame": the reference's default multi-shot shortcut (sdim/program.py:244-265) — shot 0 is one
         noiseless reference tableau shot, shots 1.. are Pauli frames propagated on the GPU (sdimb_frames)."""
-        compiled = self._compiled()
+        compiled = self._compiled(fold=self.fold_gates)
         if seed is None:
             seed = random.getrandbits(63)       # follows the user's random.seed(), like the reference's draws
         if method not in ("tableau", "frame"):

@@ -238,3 +238,45 @@ def test_workload_builders():
     assert rc.num_qudits == 49 and p.n_meas == 625 and p.n_noise == 625     # config 4: 625 records per shot
     hl = compile_circuits([noisy_random_clifford(256, 2000, 3)])
     assert hl.n_meas == 256 and hl.n_ops == hl.n_user_gates == 2000 + hl.n_noise + 256
+
+
+def test_record_table_structured_view_and_npz_round_trip(tmp_path):
+    """RecordTable -> the reference's structured record array (sdim/program.py:34-40, [qudit, round, shot]) and a
+    lossless .npz round trip; no GPU involved (the table is built by hand)."""
+    import numpy as np
+    from sdim_b200.program import RecordTable
+    from sdim_b200.results import MEASUREMENT_DTYPE
+    rng = np.random.default_rng(0)
+    meas_qudit = np.array([0, 2, 0, 1, 2, 2], dtype=np.int32)          # qudit 2 is measured three times
+    meas_round = np.array([0, 0, 1, 0, 1, 2], dtype=np.int32)
+    values = rng.integers(0, 5, size=(7, 6)).astype(np.uint8)
+    det = rng.random((7, 6)) < 0.4
+    table = RecordTable(values, det, meas_qudit, meas_round, seed=2**63 - 5, shot_offset=100)
+    arr = table.to_structured(num_qudits=4)
+    assert arr.dtype == MEASUREMENT_DTYPE and arr.shape == (4, 3, 7)
+    for k in range(6):
+        cell = arr[meas_qudit[k], meas_round[k]]
+        assert np.array_equal(cell["measurement_value"], values[:, k])
+        assert np.array_equal(cell["deterministic"], det[:, k])
+        assert np.array_equal(cell["shot"], np.arange(100, 107))
+        assert set(cell["qudit_index"]) == {meas_qudit[k]} and set(cell["meas_round"]) == {meas_round[k]}
+    zero = np.zeros((), dtype=MEASUREMENT_DTYPE)
+    assert (arr[3] == zero).all() and (arr[1, 1:] == zero).all()       # never measured / fewer rounds: zeros
+    assert table.column(2, 2) == 5
+    path = table.save(str(tmp_path / "records"))
+    back = RecordTable.load(path)
+    assert np.array_equal(back.values, values) and np.array_equal(back.deterministic, det)
+    assert np.array_equal(back.meas_qudit, meas_qudit) and np.array_equal(back.meas_round, meas_round)
+    assert back.seed == 2**63 - 5 and back.shot_offset == 100 and back.shots == 7
+
+
+def test_program_fold_gates_compiles_a_shorter_equivalent_stream():
+    from sdim_b200 import Circuit, Program
+    c = Circuit(3, 3)
+    for _ in range(4):
+        c.add_gate("H", 0)
+    c.add_gate("CNOT", 0, 1); c.add_gate("CNOT_INV", 0, 1); c.add_gate("P", 2); c.add_gate("M", [0, 1, 2])
+    prog = Program(c, fold_gates=True)
+    full, slim = prog._compiled(), prog._compiled(fold=True)
+    assert full.n_ops == 10 and slim.n_ops == 4 and slim.n_user_gates == full.n_user_gates == 10
+    assert slim.ops[:, 0].tolist() == [7, 14, 14, 14]

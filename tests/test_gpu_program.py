@@ -270,3 +270,20 @@ def test_many_waves_pipeline_gives_the_same_records():
     assert np.array_equal(got.values, want) and np.array_equal(got.deterministic, want_det)
     got = small.simulate_records(130, seed=4, shot_offset=870)
     assert np.array_equal(got.values, want[870:])
+
+
+def test_fold_gates_gives_the_same_records():
+    """Program(fold_gates=True) uploads the peephole-folded stream (sdim_b200/peephole.py): same records, same
+    deterministic flags, same final tableau under the same seed."""
+    from sdim_b200 import Program
+    from test_peephole import _redundant_circuit
+    for d, n in ((2, 9), (3, 7), (5, 4)):
+        circ = _redundant_circuit(n, d, 200, 40 + d)
+        plain, folded = Program(circ), Program(circ, fold_gates=True)
+        assert folded._compiled(fold=True).n_ops < plain._compiled().n_ops
+        a = plain.simulate_records(300, seed=8)
+        b = folded.simulate_records(300, seed=8)
+        assert np.array_equal(a.values, b.values) and np.array_equal(a.deterministic, b.deterministic)
+        ta, tb = plain.stabilizer_tableau, folded.stabilizer_tableau
+        for key in ("x_block", "z_block", "phase_vector", "destab_x_block", "destab_z_block", "destab_phase_vector"):
+            assert np.array_equal(getattr(ta, key), getattr(tb, key)), key
