@@ -1,30 +1,33 @@
-// Bit-plane (bit-sliced) resident interpreter for d = 2 and d = 3.
+// Bit-plane (bit-sliced) interpreter for d = 2 and d = 3.
 //
 // For the two smallest primes an exponent needs 1 (d = 2) or 2 (d = 3) bits, so a tableau row is kept as
 // bit-planes over the generator lanes: one 32-bit word carries 32 generators, a Clifford gate on a qudit is a
-// handful of LOP3s per word, and a whole n = 256 qutrit tableau is 64 KiB — it fits in shared memory, where one
-// warp owns one shot for the entire circuit and HBM sees nothing but the record bytes.
+// handful of LOP3s per word, and a whole n = 256 qutrit tableau is 69.6 KB.  One CTA owns one shot for the entire
+// circuit; the image lives in shared memory (GLOBAL = false) or in a per-CTA slab of caller scratch that stays in
+// L2 / L1 (GLOBAL = true, what sdimb_plan picks when fewer than four images fit in one SM's shared memory).  HBM sees
+// the op stream, the record bytes and the write-back of slab lines.
 //
 //   d = 3  value v = 2*h + l, planes (l, h):  0 = (0,0), 1 = (1,0), 2 = (0,1);  negation swaps the planes
 //   d = 2  value v = l;  phases are mod 4 = 2*h + l                         
 //
-// Shared-memory image of one shot.  Lane word j (32 generators) of a qudit row is ONE vector entry holding
-// all planes of X and Z, so a gate is one LDS.128 + one STS.128 per lane (LDS.64 for d = 2):
+// Image of one shot.  Lane word j (32 generators) of a qudit row is ONE vector entry holding all planes of X and Z,
+// so a gate is one 128-bit load + one 128-bit store per lane (64-bit for d = 2):
 //   d = 3: entry = uint4 (x_l, x_h, z_l, z_h)        d = 2: entry = uint2 (x, z)
-//   row q:   entry[0..Wb) at q * (Wb + 1) entries    (+1 entry of padding: column walks — one entry per row,
-//                                                     32 rows per instruction — then hit distinct banks)
-//   phases:  uint2 (p_l, p_h) [Wb]                   after the n rows
+//   row q:   entry[0..Wb) at q * (Wb + 1) entries    (+1 entry of padding: shared-memory column walks — one entry per
+//                                                     row, 32 rows per instruction — then hit distinct banks)
+//   phases:  uint2 (p_l, p_h) [Wb]                   per-warp accumulators, always in shared memory
 // Lane numbering is that of the uint8 store (include/sdimb.h): stabilizer g -> lane g, destabilizer g -> lane
 // np + g, with np a multiple of 32 here so the two halves never share a word.
 //
-// One CTA owns one shot.  With an unscheduled op stream the CTA is a single warp.  With a SCHEDULED stream
-// (sdimb_schedule: layers of gates on pairwise disjoint qudits, separated by barriers) the CTA has
-// SDIMB_SCHED_WARPS warps: inside a layer each warp executes its share of the gates — every warp adds its phase
-// increments to a PRIVATE phase accumulator, so gates of one layer never touch the same word — and
-// measurements split their column walks and row updates over all warps.  The accumulators are folded into
-// accumulator 0 at the start of each measurement.
+// With an unscheduled op stream the CTA is a single warp.  With a SCHEDULED stream (sdimb_schedule: layers of gates
+// on pairwise disjoint qudits, separated by barriers) the CTA has SDIMB_SCHED_WARPS warps: inside a layer each warp
+// executes its share of the gates — every warp adds its phase increments to a PRIVATE phase accumulator, so gates of
+// one layer never touch the same word — and measurements split their column walks and row updates over all warps.
+// The accumulators are folded into accumulator 0 at the start of each measurement.
 //
-// Same reference behaviour as the uint8 interpreter in sdimb.cu (file:line citations there).
+// Gate handlers live in planes_gates.inc, included twice (specialised for the shared-memory instantiation, compact
+// for the global-image one: see COMPACT below).  Same reference behaviour as the uint8 interpreter in sdimb.cu
+// (file:line citations there).
 #pragma once
 
 namespace planes {
