@@ -138,6 +138,9 @@ __device__ __forceinline__ void cta_sync() {
 #ifndef SDIMB_PG_COMPACT
 #define SDIMB_PG_COMPACT 1
 #endif
+#ifndef SDIMB_PR_COMPACT        // the same dispatch form for the shared-memory instantiation: not measured yet (round 2)
+#define SDIMB_PR_COMPACT 0
+#endif
 #define SDIMB_GATES_NS gates_std
 #define SDIMB_GATE_LOOP
 #include "planes_gates.inc"
@@ -432,7 +435,8 @@ template <int D, bool GLOBAL>
 __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS, GLOBAL ? SDIMB_PLANES_GLOBAL_MIN_CTAS : 0)
 interp_planes_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  constexpr bool CP = GLOBAL && SDIMB_PG_COMPACT != 0;     // compact dispatch form (see COMPACT above)
+  constexpr bool FW = GLOBAL && SDIMB_PG_COMPACT != 0;     // the CTA is known to have four warps: barriers without the test
+  constexpr bool CP = FW || (!GLOBAL && SDIMB_PR_COMPACT != 0);   // compact dispatch form (see COMPACT above)
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   Geo<D> G;
   PScratch S;
@@ -506,14 +510,14 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
     // static grid-stride otherwise
     if (tid == 0)
       S.next[round & 1] = p.shot_counter ? (int)atomicAdd(p.shot_counter, 1u) : (int)(blockIdx.x + round * gridDim.x);
-    cta_sync<CP>();
+    cta_sync<FW>();
     const int64_t shot = S.next[round & 1];
     if (shot >= p.shots) break;
     // ---- load: |0...0> or pack from the uint8 store ----
     for (int i = tid; i < row_words; i += nt) G.tab[i] = 0u;
     for (int i = tid; i < acc_words; i += nt) reinterpret_cast<uint32_t*>(G.ph_base)[i] = 0u;
     if (tid < 8) S.cnt[tid] = 0;
-    cta_sync<CP>();
+    cta_sync<FW>();
     uint8_t* T8 = p.tab ? p.tab + shot * p.shot_bytes : nullptr;
     G.pacc = G.phase_of(0);
     if (p.flags & SDIMB_FRESH) {
@@ -550,7 +554,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       }
     }
     G.pacc = G.phase_of(warp);
-    cta_sync<CP>();
+    cta_sync<FW>();
     bool dirty = false;                    // some gate may have added to a private phase accumulator since the last fold
 
     int4 ahead = make_int4(SDIMB_OP_I, 0, 0, 0);                // ops of the next batch, fetched one batch early
@@ -605,18 +609,18 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
         // the measurement cases, shared by the two dispatch forms below
 #define SDIMB_COLLECTIVE_CASES(NS)                                                                                      \
           case SDIMB_OP_M_X:                                                                                            \
-            cta_sync<CP>();                                                                                             \
+            cta_sync<FW>();                                                                                             \
             if (warp == 0) NS::g_h<D>(G, op.y, true);                                                                   \
             dirty = true;                       /* row q changed: the measurement must sync */                         \
             /* fallthrough */                                                                                           \
           case SDIMB_OP_M:                                                                                              \
           case SDIMB_OP_RESET: {                                                                                        \
             const bool fold = dirty || (gate_pos & ((1u << k) - 1u)) != 0;   /* gates since the last measurement? */   \
-            const uint32_t m = p_measure<D, CP>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);                  \
+            const uint32_t m = p_measure<D, FW>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);                  \
             dirty = false;                                                                                              \
             if (op.x == SDIMB_OP_RESET) {                                                                               \
               if (m && warp == 0) NS::g_pauli<D>(G, op.y, D - m, 0u);   /* program.py:335-339 */                     \
-              cta_sync<CP>();                                                                                           \
+              cta_sync<FW>();                                                                                           \
             }                                                                                                           \
             break;                                                                                                      \
           }
@@ -636,7 +640,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
           case SDIMB_OP_CZ: case SDIMB_OP_CZ_INV: gates_compact::g_cz<D>(G, op.y, op.z, op.x == SDIMB_OP_CZ_INV); break;
           case SDIMB_OP_SWAP: gates_compact::g_swap<D>(G, op.y, op.z); break;
           SDIMB_COLLECTIVE_CASES(gates_compact)
-          case SDIMB_OP_BARRIER: cta_sync<CP>(); break;
+          case SDIMB_OP_BARRIER: cta_sync<FW>(); break;
           default: break;
           }
         } else {
@@ -656,7 +660,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
           case SDIMB_OP_SWAP: gates_std::g_swap<D>(G, op.y, op.z); break;
           SDIMB_COLLECTIVE_CASES(gates_std)
           case SDIMB_OP_N1: gates_std::g_pauli<D>(G, op.y, (uint32_t)op.z & 0xFFu, (uint32_t)op.z >> 8); break;
-          case SDIMB_OP_BARRIER: cta_sync<CP>(); break;
+          case SDIMB_OP_BARRIER: cta_sync<FW>(); break;
           default: break;
           }
         }
@@ -664,7 +668,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       }
       dirty = dirty || gate_pos != 0;      // conservative: gates of this batch behind its last measurement
     }
-    cta_sync<CP>();
+    cta_sync<FW>();
     if (p.flags & SDIMB_WRITEBACK) {      // fold the accumulators, then unpack into the uint8 store
       G.pacc = G.phase_of(0);
       for (int j = tid; j < G.Wb && nw > 1; j += nt) {
@@ -675,7 +679,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
         }
         G.stp(j, acc);
       }
-      cta_sync<CP>();
+      cta_sync<FW>();
       for (int q = warp; q < p.n; q += nw) {
         uint8_t* row8 = T8 + (int64_t)q * p.row_bytes;
         for (int ln = lane; ln < p.W; ln += 32) {
@@ -691,7 +695,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       }
       G.pacc = G.phase_of(warp);
     }
-    cta_sync<CP>();
+    cta_sync<FW>();
   }
 }
 

@@ -1,6 +1,7 @@
 """Same-box A/B of prebuilt library variants (tools/build_variants.sh) on the headline and two neighbours.
 
     python tools/ab_variants.py variants/libsdimb_base.so variants/libsdimb_mlp.so ...
+    AB_SET=resident python tools/ab_variants.py ...      # shapes that run the shared-memory instantiation
 
 One subprocess per library (SDIMB_LIB is read at import).  Each prints, per workload, the device time of a launch and
 whether the records equal the C oracle's on the first shots; results land in gpurun_out/ab_variants.json.
@@ -17,6 +18,8 @@ WORKLOADS = [  # (d, n, depth or None for 8n, shots, oracle_shots)
     (2, 400, None, 8192, 24),    # d = 2 on the slab image
     (3, 500, None, 2048, 12),    # beyond the shared-memory limit
 ]
+if os.environ.get("AB_SET") == "resident":   # shared-memory image: 1-warp CTAs (n = 64), 4-warp CTAs (n = 160, 192)
+    WORKLOADS = [(3, 64, None, 32768, 64), (2, 97, None, 32768, 64), (3, 160, None, 16384, 48), (2, 256, None, 8192, 32)]
 
 
 def worker():
