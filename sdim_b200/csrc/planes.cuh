@@ -175,6 +175,14 @@ __device__ __forceinline__ uint32_t p_noise_event(const KParams& p, int64_t j, i
 }
 
 // ---- measurement (whole CTA: 1 or SDIMB_SCHED_WARPS warps) -----------------------------------------------------
+#ifndef SDIMB_P_NOUNROLL        // measurement and shot-init loops left rolled (smaller code, both instantiations): not measured yet
+#define SDIMB_P_NOUNROLL 0
+#endif
+#if SDIMB_P_NOUNROLL
+#define SDIMB_P_LOOP _Pragma("unroll 1")
+#else
+#define SDIMB_P_LOOP
+#endif
 #ifndef SDIMB_PG_SKIPLIST       // column walk: skip the list bookkeeping of a warp none of whose 32 rows is listed
 #define SDIMB_PG_SKIPLIST 0
 #endif
@@ -198,8 +206,10 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
   S.parity ^= 1u;
   if (fold) {
     cta_sync<FW>();
+    SDIMB_P_LOOP
     for (int j = tid; j < Wb && nw > 1; j += nt) {
       E acc = G.ldp(j);
+      SDIMB_P_LOOP
       for (int w = 1; w < nw; ++w) {
         uint2* pw = G.phase_of(w) + j;
         const E o{pw->x, pw->y};
@@ -213,6 +223,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
 
   // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283); every warp looks itself
   uint32_t best = kNoPivot;
+  SDIMB_P_LOOP
   for (int j = lane; j < np / 32; j += 32) {
     const E x = G.ld(q, j).x;
     const uint32_t m = x.l | x.h;
@@ -252,6 +263,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       if (act) S.ar[(both & 0xFFFFu) + __popc(ma & lt)] = (uint16_t)r;
       if (stale) S.br[(both >> 16) + __popc(mb & lt)] = (uint16_t)r;
     };
+    SDIMB_P_LOOP
     for (int base = 0; base < n; base += nt) {
       const int r = base + tid;
       const XZ zero{E{0u, 0u}, E{0u, 0u}};
@@ -262,6 +274,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     sd_part = __reduce_add_sync(FULL, sd_part);
     if (lane == 0 && sd_part) atomicAdd(&cnt[2], sd_part);
     // factors f = -X[q,i] for every lane but the pivot itself
+    SDIMB_P_LOOP
     for (int j = tid; j < Wb; j += nt) {
       E x = G.ld(q, j).x;
       if (j == jp) { x.l &= ~(1u << bp); x.h &= ~(1u << bp); }
@@ -275,6 +288,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     // col_i += f_i * col_p on the pivot's support.  Threads form row groups: 32/Wb per warp when Wb divides 32
     // (geometry precomputed in Geo: the divisions cost more than the update of a sparse measurement).
     const int gpw = G.gpw, gtot = gpw * nw, gid = warp * gpw + G.gsub, jstep = G.jstep;
+    SDIMB_P_LOOP
     for (int j = G.j0; j < Wb; j += jstep) {
       const uint2 fv = S.f[j];
       const E f{fv.x, fv.y};
@@ -290,11 +304,13 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
             G.st(r, j, XZ{E{v.x.l ^ (s ? f.l : 0u), 0u}, E{v.z.l ^ (t ? f.l : 0u), 0u}});
           }
         };
+        SDIMB_P_LOOP
         for (int ri = gid; ri < nr_a; ri += gtot) {
           const int r = S.ar[ri];
           update_row(r, S.xz[r], G.ld(r, j));
         }
       }
+      SDIMB_P_LOOP
       for (int off = Wb; off < 32 && gpw > 1; off <<= 1) {
         const E o{__shfl_xor_sync(FULL, dot.l, off), __shfl_xor_sync(FULL, dot.h, off)};
         dot = (D == 3) ? add3(dot, o) : E{dot.l ^ o.l, 0u};
@@ -303,11 +319,13 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     }
     cta_sync<FW>();
     // phase_i += f_i*ps + po*(f_i*dot_i + sd*f_i(f_i-1)/2*po)      (tableau_prime.py:310-312,317-319)
+    SDIMB_P_LOOP
     for (int j = tid; j < Wb; j += nt) {
       const uint2 fv = S.f[j];
       const E f{fv.x, fv.y};
       if ((f.l | f.h) == 0) continue;
       E dot{0u, 0u};
+      SDIMB_P_LOOP
       for (int w = 0; w < nw; ++w) {
         const uint2 o = S.dotw[w * Wb + j];
         dot = (D == 3) ? add3(dot, E{o.x, o.y}) : E{dot.l ^ o.x, 0u};
@@ -326,6 +344,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     cta_sync<FW>();
     // destabilizer p <- old pivot; stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333).
     // Only rows where something changes are touched: the support (list ar) and stale destabilizer rows (br).
+    SDIMB_P_LOOP
     for (int i = tid; i < nr_a; i += nt) {
       const int r = S.ar[i];
       const uint32_t c = S.xz[r];
@@ -338,6 +357,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       dd.z = setbit2(dd.z, bp, c >> 2);
       G.st(r, jd, dd);
     }
+    SDIMB_P_LOOP
     for (int i = tid; i < nr_b; i += nt) {
       const int r = S.br[i];
       XZ dd = G.ld(r, jd);
@@ -355,6 +375,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     if (warp == 0) {
       uint32_t a1 = 0;
       int total = 0;
+      SDIMB_P_LOOP
       for (int base = 0; base < np / 32; base += 32) {
         const int j = base + lane;
         E f{0u, 0u}, ph{0u, 0u};
@@ -384,8 +405,10 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     cta_sync<FW>();
     const int total = (int)cnt[3];
     uint32_t part = 0;
+    SDIMB_P_LOOP
     for (int r = tid; r < n; r += nt) {
       uint32_t az = 0, cross = 0, sdg = 0;
+      SDIMB_P_LOOP
       for (int k = 0; k < total; ++k) {
         const int g = S.ar[k];
         const uint32_t f = S.xz[k];
@@ -514,7 +537,9 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
     const int64_t shot = S.next[round & 1];
     if (shot >= p.shots) break;
     // ---- load: |0...0> or pack from the uint8 store ----
+    SDIMB_P_LOOP
     for (int i = tid; i < row_words; i += nt) G.tab[i] = 0u;
+    SDIMB_P_LOOP
     for (int i = tid; i < acc_words; i += nt) reinterpret_cast<uint32_t*>(G.ph_base)[i] = 0u;
     if (tid < 8) S.cnt[tid] = 0;
     cta_sync<FW>();
