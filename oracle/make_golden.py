@@ -123,5 +123,33 @@ def main():
     print(f"wrote {path}")
 
 
+def main_large():
+    """Large primes (uint8-lane limit d = 127 included): pins the oracles where the GPU parity tests lean on the
+    C oracle alone.  Shallower circuits: the reference's lazy reduction multiplies entries by up to d per CNOT
+    (SURVEY Appendix B-1), cases it overflows in are dropped like above."""
+    plan, seed = [], 5000
+    for d in (17, 31, 61, 127):
+        for n, depth, reps in ((1, 20, 2), (2, 30, 3), (3, 45, 3), (5, 60, 3), (8, 80, 2)):
+            for _ in range(reps):
+                plan.append((seed, n, d, depth))
+                seed += 1
+    cases, dropped = [], 0
+    for seed, n, d, depth in plan:
+        case = make_case(seed, n, d, depth)
+        if case is None:
+            dropped += 1
+        else:
+            cases.append(case)
+    out = {"generator": "oracle/make_golden.py --large", "reference": "events555/sdim @ /root/reference",
+           "dropped_for_reference_int64_overflow": dropped, "cases": cases}
+    path = os.path.join(GOLDEN_DIR, "large_primes.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh, separators=(",", ":"))
+    print(f"wrote {len(cases)} cases ({dropped} dropped) -> {path} ({os.path.getsize(path)} bytes)")
+
+
 if __name__ == "__main__":
-    main()
+    if "--large" in sys.argv:
+        main_large()
+    else:
+        main()

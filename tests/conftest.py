@@ -25,3 +25,9 @@ def golden_random():
 def golden_shipped():
     with open(os.path.join(GOLDEN_DIR, "shipped_circuits.json")) as fh:
         return json.load(fh)["circuits"]
+
+
+@pytest.fixture(scope="session")
+def golden_large_primes():
+    with open(os.path.join(GOLDEN_DIR, "large_primes.json")) as fh:
+        return json.load(fh)["cases"]

@@ -51,6 +51,28 @@ def test_c_oracle_matches_reference_goldens(golden_random):
             assert np.array_equal(fin[key], np.array(case["final"][key])), (case["seed"], key)
 
 
+def test_oracles_match_reference_goldens_at_large_primes(golden_large_primes):
+    """d in {17, 31, 61, 127} (127 = the uint8-lane limit of the CUDA store): both restatements against outputs of the
+    unmodified reference (`oracle/make_golden.py --large`).  The GPU parity tests at these dimensions compare with the
+    C oracle, which this test pins."""
+    assert {c["d"] for c in golden_large_primes} == {17, 31, 61, 127} and len(golden_large_primes) >= 48
+    assert sum(1 for c in golden_large_primes for r in c["records"] if not r[1]) > 80
+    for case in golden_large_primes:
+        draws = [r[2] for r in case["records"]]
+        noise64 = np.array(case["noise_ab"], dtype=np.int64).reshape(-1, 2)
+        recs, t = run_shot(case["n"], case["d"], case["ops"], lambda k: draws[k], noise64)
+        assert recs == [(q, bool(det), m) for q, det, m in case["records"]], case["seed"]
+        for key, arr in zip(KEYS, t.arrays()):
+            assert np.array_equal(arr, np.array(case["final"][key])), (case["seed"], key)
+        if c_oracle.available():
+            want = _want(case)
+            rec, fin = c_oracle.run(case["n"], case["d"], case["ops"], 1, replay_meas=(want & 0x7F)[None, :],
+                                    replay_noise=noise64.astype(np.uint8).reshape(1, -1, 2), want_final=True)
+            assert np.array_equal(rec[0], want), case["seed"]
+            for key in KEYS:
+                assert np.array_equal(fin[key], np.array(case["final"][key])), (case["seed"], key)
+
+
 def test_shipped_circuit_goldens(golden_shipped):
     """circuits/css_steane_final.chp -> 1,1,0,1,1,0 all deterministic; circuits/epr.chp -> qudit 1 random."""
     st = golden_shipped["circuits/css_steane_final.chp"]
