@@ -84,3 +84,60 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|liboracle", text, flags=re.M), \
                     f"{f} imports or loads the oracle"
+
+
+def test_kernel_selection_rule_without_a_gpu():
+    """sdimb_plan is host logic: d = 2, 3 run the bit-plane interpreter — image in shared memory
+    while four or more fit per SM, else in a per-CTA global slab; other primes run uint8 lanes, resident while one
+    tableau fits in shared memory."""
+    from sdim_b200 import _native as N
+    fresh = N.FRESH
+    names = {k: N.KERNEL_NAMES[N.plan(*k, fresh)[0]] for k in
+             ((64, 3), (160, 3), (200, 3), (224, 3), (256, 3), (500, 3), (97, 2), (290, 2), (320, 2), (700, 2),
+              (64, 5), (200, 7), (256, 5), (4096, 7), (6, 127))}
+    assert names[(64, 3)] == names[(160, 3)] == names[(200, 3)] == "planes-resident"
+    assert names[(224, 3)] == names[(256, 3)] == names[(500, 3)] == "planes-global"
+    assert names[(97, 2)] == names[(290, 2)] == "planes-resident"
+    assert names[(320, 2)] == names[(700, 2)] == "planes-global"
+    assert names[(64, 5)] == names[(200, 7)] == names[(6, 127)] == "lanes-resident"
+    assert names[(256, 5)] == names[(4096, 7)] == "lanes-global"
+    # a fresh run that keeps nothing needs no HBM store unless the lanes run from global memory
+    assert N.plan(256, 3, fresh) == (3, False) and N.plan(64, 5, fresh) == (1, False)
+    assert N.plan(256, 5, fresh) == (0, True) and N.plan(256, 3, fresh | N.WRITEBACK)[1] is True
+    # forced modes
+    assert N.KERNEL_NAMES[N.plan(256, 3, fresh | N.FORCE_PLANES)[0]] == "planes-resident"
+    assert N.KERNEL_NAMES[N.plan(256, 3, fresh | N.FORCE_LANES)[0]] == "lanes-global"
+    assert N.KERNEL_NAMES[N.plan(64, 3, fresh | N.FORCE_PLANES | N.FORCE_GLOBAL)[0]] == "planes-global"
+    with pytest.raises(ValueError):
+        N.plan(500, 3, fresh | N.FORCE_PLANES)          # does not fit in shared memory
+    with pytest.raises(ValueError):
+        N.plan(256, 5, fresh | N.FORCE_RESIDENT)
+
+
+def test_host_entry_validates_before_touching_cuda():
+    """sdimb_simulate_host checks dimension, sizes and every op row first: the error a user gets for a bad stream
+    does not depend on a GPU being present ("Invalid gate value", sdim/program.py:381-382)."""
+    import numpy as np
+    from sdim_b200 import _native as N
+    L = N.lib()
+    rec = np.zeros((2, 4), dtype=np.uint8)
+
+    def call(n, d, ops, n_meas=0, n_noise=0, thr=None, ch=None, shots=2):
+        ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 4)
+        return L.sdimb_simulate_host(n, d, shots, 0, ops.ctypes.data if ops.size else None, ops.shape[0],
+                                     rec.ctypes.data, n_meas, None, None,
+                                     None if thr is None else thr.ctypes.data, None if ch is None else ch.ctypes.data,
+                                     n_noise, 1, 0, None)
+
+    assert call(4, 3, [[18, 0, -1, -1]]) == N.EOP                       # BARRIER is not a user opcode
+    assert call(4, 3, [[99, 0, -1, -1]]) == N.EOP
+    assert call(4, 3, [[5, 4, -1, -1]]) == N.EOP                        # qudit out of range
+    assert call(4, 3, [[9, 1, 1, -1]]) == N.EOP                         # control == target
+    assert call(4, 3, [[9, 1, 7, -1]]) == N.EOP
+    assert call(4, 3, [[14, 0, -1, 3]], n_meas=1) == N.EOP              # record slot out of range
+    assert call(4, 3, [[17, 0, -1, 0]], n_noise=0) == N.EOP             # noise slot out of range
+    assert call(4, 4, [[5, 0, -1, -1]]) == N.EDIM and call(4, 131, [[5, 0, -1, -1]]) == N.EDIM
+    assert call(0, 3, [[5, 0, -1, -1]]) == N.EINVAL and call(4, 3, [[5, 0, -1, -1]], shots=-1) == N.EINVAL
+    assert call(4, 3, [[17, 0, -1, 0]], n_noise=1) == N.EINVAL          # Philox mode without noise tables
+    assert call(4, 3, [[5, 0, -1, -1]], shots=0) == N.OK                # nothing to do
+    assert N.lib().sdimb_strerror(N.EOP).decode() == "Invalid gate value"
