@@ -29,6 +29,18 @@ from .results import MEASUREMENT_DTYPE, MeasurementResult
 from .tableau import ExtendedTableau
 
 
+def undo_reset_correction(arrays: dict, qudit: int, outcome: int, d: int) -> dict:
+    """Exported tableau arrays (keys x, z, p, dx, dz, dp; [qudit, generator]) AFTER a RESET op -> the tableau right
+    after its measurement, i.e. before the driver's X^((-m) mod d) correction (sdim/program.py:335-339).  X^k only
+    moves phases: phase -= phase_order * k * z[qudit] on both halves, so the inverse adds it."""
+    k = (-outcome) % d
+    po, order = (2, 2 * d) if d % 2 == 0 else (1, d)
+    out = dict(arrays)
+    out["p"] = (np.asarray(arrays["p"]) + po * k * np.asarray(arrays["z"])[qudit]) % order
+    out["dp"] = (np.asarray(arrays["dp"]) + po * k * np.asarray(arrays["dz"])[qudit]) % order
+    return out
+
+
 @dataclass
 class SimulationOptions:
     """Same fields as the reference (sdim/program.py:167-175)."""
@@ -374,10 +386,14 @@ class Program:
                            op_range=(i, i + 1), records=rec)
                 op, _, _, slot = (int(v) for v in compiled.ops[i])
                 if snaps is not None and op in MEASURE_OPS:
-                    # The reference snapshots right after measure(), before the RESET correction
-                    # (program.py:323-324 precede :335-339); here the snapshot is taken after the whole op.
-                    snaps[s][slot] = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
-                                                                 engine.export(store, 0))
+                    arrays = engine.export(store, 0)
+                    if op == OP_RESET:
+                        # The reference snapshots right after measure(), before the RESET correction
+                        # (program.py:323-324 precede :335-339); the device op does both, so the correction's
+                        # phase update is taken back out of the exported copy.
+                        outcome = int(rec[0, slot].item()) & 0x7F
+                        arrays = undo_reset_correction(arrays, int(compiled.ops[i][1]), outcome, compiled.dimension)
+                    snaps[s][slot] = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, arrays)
                 if options.show_gate:
                     g = user_ops[i]
                     info = g.target_index if g.target_index is not None else ""

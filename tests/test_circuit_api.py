@@ -280,3 +280,26 @@ def test_program_fold_gates_compiles_a_shorter_equivalent_stream():
     full, slim = prog._compiled(), prog._compiled(fold=True)
     assert full.n_ops == 10 and slim.n_ops == 4 and slim.n_user_gates == full.n_user_gates == 10
     assert slim.ops[:, 0].tolist() == [7, 14, 14, 14]
+
+
+def test_undo_reset_correction_recovers_the_post_measurement_tableau():
+    """record_tableau snapshots of a RESET are taken where the reference takes them: after measure(), before the
+    X^(-m) correction (sdim/program.py:323-324 vs :335-339).  Checked on the numpy oracle's tableau."""
+    import numpy as np
+    from oracle.tableau_oracle import run_shot
+    from make_cases import random_program
+    from sdim_b200.program import undo_reset_correction
+    keys = ("x", "z", "p", "dx", "dz", "dp")
+    for d in (2, 3, 5, 7):
+        prog = random_program(seed=90 + d, n=5, d=d, depth=70, p_meas=0.0)
+        for q in range(5):
+            for m in range(d):
+                _, t = run_shot(5, d, prog.ops.tolist(), lambda k: 0)
+                det, value = t.measure(q, lambda: m)
+                before = {k: a.copy() for k, a in zip(keys, t.arrays())}
+                t.pauli(q, (-value) % d, 0)
+                after = {k: a.copy() for k, a in zip(keys, t.arrays())}
+                got = undo_reset_correction(after, q, value, d)
+                for k in keys:
+                    assert np.array_equal(np.asarray(got[k]) % (2 * d if d == 2 else d) if k in ("p", "dp") else got[k],
+                                          before[k]), (d, q, m, k)

@@ -287,3 +287,27 @@ def test_fold_gates_gives_the_same_records():
         ta, tb = plain.stabilizer_tableau, folded.stabilizer_tableau
         for key in ("x_block", "z_block", "phase_vector", "destab_x_block", "destab_z_block", "destab_phase_vector"):
             assert np.array_equal(getattr(ta, key), getattr(tb, key)), key
+
+
+def test_record_tableau_snapshot_of_a_reset_precedes_its_correction():
+    """The reference snapshots a RESET right after measure(), before the X^(-m) correction
+    (sdim/program.py:323-324 vs :335-339): the snapshot must equal the oracle's tableau at that point."""
+    from oracle.tableau_oracle import run_shot
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.rng import measurement_draws
+    for d in (2, 3, 5):
+        c = Circuit(3, d)
+        c.add_gate("H", 0); c.add_gate("CNOT", 0, 1); c.add_gate("P", 1); c.add_gate("H", 2); c.add_gate("CZ", 2, 1)
+        head = compile_circuits([c])
+        c.add_gate("RESET", 1)
+        prog = compile_circuits([c])
+        for seed in range(6):
+            res = Program(c).simulate(shots=1, record_tableau=True, seed=seed)
+            md = measurement_draws(seed, d, [0], prog.n_meas)[0]
+            _, t = run_shot(3, d, head.ops, lambda k: 0)
+            det, value = t.measure(1, lambda: int(md[0]))
+            assert (res[0].deterministic, res[0].measurement_value) == (det, value)
+            snap = res[0].get_tableau()
+            for got, want in zip((snap.x_block, snap.z_block, snap.phase_vector, snap.destab_x_block,
+                                  snap.destab_z_block, snap.destab_phase_vector), t.arrays()):
+                assert np.array_equal(got, want), (d, seed)
