@@ -425,15 +425,15 @@ class Program:
         store = torch.from_numpy(current.pack(engine.layout.np)).to(engine.device).unsqueeze(0).contiguous()
         rec = engine.run(1, 0, random.getrandbits(63), keep_tableau=True, tableau=store, fresh=False)
         out = None
+        arrays = engine.export(store, 0)
         if compiled.n_meas:
             r = int(rec.cpu().numpy()[0, 0])
             out = MeasurementResult(int(compiled.meas_qudit[0]), bool(r & 0x80), r & 0x7F)
             if instruc.gate_id == OP_RESET:
-                # the reference's apply_reset only measures; its driver applies the X correction
-                # (program.py:335-339).  The device op does both, so undo nothing and document it.
-                pass
-        self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
-                                                              engine.export(store, 0))
+                # the reference's apply_reset only measures (tableau_gates.py:331-346); the X correction belongs to
+                # its shot loop (program.py:335-339).  The device op does both, so the correction is taken back out.
+                arrays = undo_reset_correction(arrays, int(compiled.meas_qudit[0]), r & 0x7F, compiled.dimension)
+        self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, arrays)
         return out
 
     # ---- reference helpers kept for drop-in compatibility -------------------------------------------
