@@ -8,7 +8,8 @@ import torch
 
 from oracle.tableau_oracle import OracleTableau, run_shot
 from sdim_b200 import _native as N
-from sdim_b200.rng import measurement_draws, noise_draws
+from oracle.frame_oracle import simulate_frames
+from sdim_b200.rng import frame_z0_draws, frame_zm_draws, measurement_draws, noise_draws
 from sdim_b200.tableau import ExtendedTableau
 
 
@@ -78,3 +79,14 @@ class FakeEngine:
         t = unpack(tableau[shot].numpy(), self.prog.num_qudits, self.prog.dimension, self.layout.np)
         x, z, p, dx, dz, dp = t.arrays()
         return {"x": x, "z": z, "p": p, "dx": dx, "dz": dz, "dp": dp}
+
+    def run_frames(self, shots, reference, shot_offset=1, seed=0, replay_z0=None, replay_zm=None, replay_noise=None):
+        prog, n, d = self.prog, self.prog.num_qudits, self.prog.dimension
+        ids = np.arange(shot_offset, shot_offset + shots)
+        z0 = replay_z0.numpy() if replay_z0 is not None else frame_z0_draws(seed, d, ids, n)
+        zm = replay_zm.numpy() if replay_zm is not None else frame_zm_draws(seed, d, ids, prog.n_meas)
+        nd = None
+        if prog.n_noise:
+            nd = replay_noise.numpy() if replay_noise is not None else \
+                noise_draws(seed, d, ids, prog.noise_thresh24, prog.noise_channel)
+        return torch.from_numpy(simulate_frames(n, d, prog.ops, reference.numpy(), z0, zm, nd))

@@ -144,3 +144,23 @@ def test_replayed_draws_and_record_table_columns():
     assert table.column(int(prog.meas_qudit[-1]), int(prog.meas_round[-1])) == prog.n_meas - 1
     with pytest.raises(ValueError):
         Program(circ).simulate_records(2, method="nope")
+
+
+def test_frame_method_takes_one_reference_shot_and_frames_for_the_rest():
+    """method="frame": shot 0 is a noiseless tableau shot, shots 1.. are Pauli frames (sdim/program.py:244-265);
+    force_tableau / shots == 1 stay on the tableau path."""
+    c = Circuit(3, 3)
+    c.add_gate("H", 0); c.add_gate("CNOT", 0, [1, 2]); c.add_gate("N1", 1, prob=1.0, noise_channel="f")
+    c.add_gate("M", [0, 1, 2])
+    P = Program(c)
+    res = P.simulate(shots=50, seed=3, method="frame")
+    assert len(res) == 3 and len(res[0][0]) == 50
+    ref = [res[q][0][0].measurement_value for q in range(3)]
+    assert ref[0] == ref[1] == ref[2]                        # the reference shot ignores N1 (program.py:31)
+    flips = sum(res[0][0][s].measurement_value != res[1][0][s].measurement_value for s in range(1, 50))
+    assert flips == 49                                       # every frame carries the certain flip on qudit 1
+    assert all(res[0][0][s].measurement_value == res[2][0][s].measurement_value for s in range(50))
+    assert {res[0][0][s].measurement_value for s in range(50)} == {0, 1, 2}
+    runs_before = len(P._engine.runs)
+    P.simulate(shots=50, seed=3, method="frame", force_tableau=True)
+    assert P._engine.runs[runs_before][0] == 50              # all 50 shots went through the tableau path
