@@ -148,8 +148,68 @@ def main_large():
     print(f"wrote {len(cases)} cases ({dropped} dropped) -> {path} ({os.path.getsize(path)} bytes)")
 
 
+def config_cases():
+    """(name, n, d, ops, noise_ab) of the BASELINE.json config-size shots: circuits from the product's workload
+    builders (sdim_b200/workloads.py, same constructions as SURVEY 8d), N1 events as the (a, b) draws of Philox
+    seed 2026, global shot 0 — i.e. exactly shot 0 of a free-running GPU run — except that configs 3 and 4 also get a
+    second shot drawn at 20x the noise probability so that several events fire."""
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.random_circuit import generate_random_clifford_circuit
+    from sdim_b200.rng import noise_draws, prob_to_thresh24
+    from sdim_b200.workloads import noisy_random_clifford, qudit_repetition_code, rotated_surface_code
+    out = []
+
+    def add(name, circ, boost=1.0, shot=0):
+        prog = compile_circuits([circ])
+        noise = np.zeros((0, 2), dtype=np.int64)
+        if prog.n_noise:
+            thr = prog.noise_thresh24 if boost == 1.0 else np.array(
+                [prob_to_thresh24(min(1.0, boost * p)) for p in prog.noise_prob], dtype=np.uint32)
+            noise = noise_draws(2026, prog.dimension, np.array([shot]), thr, prog.noise_channel)[0].astype(np.int64)
+        out.append((name, prog.num_qudits, prog.dimension, prog.ops.tolist(), noise))
+
+    add("config2_random_clifford_n64_d3", generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1))
+    add("config3_surface_code_d7_n97_d2", rotated_surface_code(7, 7, 1e-3))
+    add("config3_surface_code_d7_n97_d2_noisy", rotated_surface_code(7, 7, 1e-3), boost=20.0, shot=1)
+    add("config4_repetition_code_d25_n49_d3", qudit_repetition_code(25, 25, 3, 1e-2, "f"))
+    add("config4_repetition_code_d25_n49_d3_noisy", qudit_repetition_code(25, 25, 3, 1e-2, "f"), boost=20.0, shot=1)
+    add("headline_noisy_random_clifford_n256_d3", noisy_random_clifford(256, 2000, 3, seed=1, prob=1e-3, channel="d"))
+    return out
+
+
+def main_configs():
+    """One reference shot per BASELINE.json config size (n = 64, 97, 49, 256): pins both oracles, and through them
+    every GPU mode, where round 1's goldens (n <= 13) could not see — multi-word lane rows, the headline shape.
+    Stored compactly (uint8 / int32 arrays in one .npz); records rows are (qudit, deterministic, value)."""
+    import time
+    blob, names = {}, []
+    for name, n, d, ops, noise in config_cases():
+        t0 = time.time()
+        recs, arrs = rh.ref_run(n, d, ops, noise, draw_seed=2026)
+        recs2, arrs2 = rh.ref_run_eager_modulo(n, d, ops, noise, draw_seed=2026)
+        if recs != recs2 or any(not np.array_equal(arrs[k], arrs2[k]) for k in arrs):
+            raise SystemExit(f"{name}: reference int64 overflow (lazy vs eager modulo disagree)")
+        names.append(name)
+        blob[name + "/nd"] = np.array([n, d], dtype=np.int32)
+        blob[name + "/ops"] = np.array(ops, dtype=np.int32).reshape(-1, 4)
+        blob[name + "/noise_ab"] = noise.astype(np.uint8).reshape(-1, 2)
+        blob[name + "/records"] = np.array([[q, int(det), m] for q, det, m in recs], dtype=np.int16).reshape(-1, 3)
+        for k, v in arrs.items():
+            assert v.min() >= 0 and v.max() < 2 * d
+            blob[name + "/" + k] = v.astype(np.uint8)
+        n_rand = sum(1 for r in recs if not r[1])
+        print(f"{name}: n={n} d={d} ops={len(ops)} noise fired={int((noise.sum(axis=1) > 0).sum())} "
+              f"records={len(recs)} ({n_rand} random) {time.time() - t0:.1f}s")
+    blob["names"] = np.array(names)
+    path = os.path.join(GOLDEN_DIR, "config_sizes.npz")
+    np.savez_compressed(path, **blob)
+    print(f"wrote {path} ({os.path.getsize(path)} bytes)")
+
+
 if __name__ == "__main__":
-    if "--large" in sys.argv:
+    if "--configs" in sys.argv:
+        main_configs()
+    elif "--large" in sys.argv:
         main_large()
     else:
         main()

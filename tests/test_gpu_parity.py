@@ -44,6 +44,54 @@ def test_golden_random_circuits_replay(golden_random, mode):
     assert checked >= 40
 
 
+@pytest.mark.parametrize("mode", [None, "resident", "global", "planes", "planes-global", "cluster"])
+def test_golden_config_sizes_replay(golden_config_sizes, mode):
+    """Outputs of the UNMODIFIED reference at the BASELINE.json config sizes (config 2 n = 64, surface code n = 97,
+    repetition code n = 49, headline n = 256): records and all six final arrays in every kernel that can hold the
+    shape (tests/golden/config_sizes.npz, oracle/make_golden.py --configs)."""
+    import torch
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    checked = 0
+    for case in golden_config_sizes:
+        n, d, ops = case["n"], case["d"], case["ops"]
+        prog = compile_circuits([circuit_from_ops(n, d, ops)])
+        eng = TableauEngine(prog)
+        try:
+            eng.plan(mode)
+        except ValueError:
+            continue                      # this shape does not fit that kernel (n = 256 in shared memory)
+        want = np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+        shots = 5
+        rm = torch.from_numpy(np.tile((want & 0x7F)[None, :], (shots, 1)))
+        rn = torch.from_numpy(np.tile(case["noise_ab"][None], (shots, 1, 1))) if prog.n_noise else None
+        got = eng.run(shots, 0, 99, rm, rn, keep_tableau=True, mode=mode).cpu().numpy()
+        for s in range(shots):
+            assert np.array_equal(got[s], want), f"records differ: {case['name']} shot {s} mode {mode}"
+        arrs = eng.export(eng.tableau, shots - 1)
+        for key in ("x", "z", "p", "dx", "dz", "dp"):
+            assert np.array_equal(arrs[key], case["final"][key]), f"final {key} differs: {case['name']} mode {mode}"
+        checked += 1
+    assert checked >= (6 if mode in (None, "global", "planes-global", "cluster") else 5)
+
+
+def test_headline_free_running_shot0_equals_reference_golden(golden_config_sizes):
+    """The headline golden's N1 events are shot 0 of Philox seed 2026.  With only the measurement outcomes replayed
+    and the noise left to the device's own Philox draws, global shot 0 of the bench workload must reproduce the
+    reference's records: pins the device-side noise draws to the reference at the headline size."""
+    import torch
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.workloads import noisy_random_clifford
+    case = next(c for c in golden_config_sizes if c["name"].startswith("headline"))
+    prog = compile_circuits([noisy_random_clifford(256, 2000, 3, seed=1, prob=1e-3, channel="d")])
+    assert np.array_equal(prog.ops, case["ops"])
+    want = np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+    rm = torch.from_numpy((want & 0x7F)[None, :].copy())
+    got = TableauEngine(prog).run(1, 0, 2026, rm, None).cpu().numpy()      # noise: Philox seed 2026, global shot 0
+    assert np.array_equal(got[0], want)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Free-running (Philox) mode against the C oracle: same counters on both sides -> bit-exact records
 # ---------------------------------------------------------------------------------------------------

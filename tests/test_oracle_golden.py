@@ -73,6 +73,32 @@ def test_oracles_match_reference_goldens_at_large_primes(golden_large_primes):
                 assert np.array_equal(fin[key], np.array(case["final"][key])), (case["seed"], key)
 
 
+def test_oracles_match_reference_goldens_at_config_sizes(golden_config_sizes):
+    """One reference shot per BASELINE.json config size — config 2 (n = 64, d = 3), the distance-7 surface code
+    (n = 97, d = 2), the distance-25 qutrit repetition code (n = 49), the headline (n = 256, d = 3; N1 events = shot 0
+    of Philox seed 2026): records and all six final arrays of both restatements.  This is what pins the C oracle at the
+    sizes where the GPU parity tests lean on it (multi-word lane rows, 4-warp CTAs, the slab image)."""
+    names = [c["name"] for c in golden_config_sizes]
+    assert len(names) == 6 and {c["n"] for c in golden_config_sizes} == {49, 64, 97, 256}
+    assert sum(int((c["records"][:, 1] == 0).sum()) for c in golden_config_sizes) > 300
+    for case in golden_config_sizes:
+        n, d, ops = case["n"], case["d"], case["ops"]
+        want = np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+        noise = case["noise_ab"]
+        if c_oracle.available():
+            rec, fin = c_oracle.run(n, d, ops, 1, replay_meas=(want & 0x7F)[None, :],
+                                    replay_noise=noise.reshape(1, -1, 2), want_final=True)
+            assert np.array_equal(rec[0], want), case["name"]
+            for key in KEYS:
+                assert np.array_equal(fin[key], case["final"][key]), (case["name"], key)
+        if n <= 97:       # the numpy restatement at n = 256 is covered through the C oracle (pinned to it at n <= 33 and here)
+            draws = [int(r[2]) for r in case["records"]]
+            recs, t = run_shot(n, d, ops.tolist(), lambda k: draws[k], noise.astype(np.int64))
+            assert recs == [(int(q), bool(det), int(m)) for q, det, m in case["records"]], case["name"]
+            for key, arr in zip(KEYS, t.arrays()):
+                assert np.array_equal(arr, case["final"][key]), (case["name"], key)
+
+
 def test_shipped_circuit_goldens(golden_shipped):
     """circuits/css_steane_final.chp -> 1,1,0,1,1,0 all deterministic; circuits/epr.chp -> qudit 1 random."""
     st = golden_shipped["circuits/css_steane_final.chp"]
