@@ -39,10 +39,26 @@ def gather_records(local, shots: int, n_meas: int, group=None):
     return torch.cat(pieces, dim=0)
 
 
-def simulate_sharded(program, compiled, shots: int, seed: int, mode: Optional[str] = None,
-                     runner: Optional[Callable] = None, group=None) -> np.ndarray:
-    """Simulate this rank's shot range and return the gathered uint8[shots, n_meas] records.
+def broadcast_seed(seed: Optional[int], group=None) -> int:
+    """One seed for the whole job: rank 0's value (drawn there from `random` when the caller gave none) reaches every
+    rank, so that the gathered table is ONE run whose records depend on the global shot id only."""
+    import random
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return random.getrandbits(63) if seed is None else int(seed)
+    box = [random.getrandbits(63) if seed is None else int(seed)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return int(box[0])
 
+
+def simulate_sharded(program, compiled, shots: int, seed: int, mode: Optional[str] = None,
+                     runner: Optional[Callable] = None, group=None, shot_offset: int = 0,
+                     replay_meas=None, replay_noise=None) -> np.ndarray:
+    """Simulate this rank's shot range and return the gathered uint8[shots, n_meas] records (packed bytes).
+
+    The shard runs through `Program._run_local` — the same initial tableau, replay slices, global shot ids
+    (`shot_offset + lo + local`) and wave sizing as a single-process run — with the records left on the device, so the
+    only exchange is the NCCL all-gather over NVLink.  `seed` must already be the job-wide seed (`broadcast_seed`).
     runner(lo, hi) -> torch uint8 [hi-lo, n_meas] overrides the GPU engine (CPU tests).
     """
     import torch
@@ -51,12 +67,17 @@ def simulate_sharded(program, compiled, shots: int, seed: int, mode: Optional[st
         world, rank = 1, 0
     else:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+    for name, arr, width in (("replay_meas", replay_meas, compiled.n_meas), ("replay_noise", replay_noise, compiled.n_noise)):
+        if arr is not None and (np.asarray(arr).shape[0] != shots or np.asarray(arr).shape[1] != width):
+            raise ValueError(f"{name} must cover all {shots} shots of the job (every rank passes the full array)")
     lo, hi = shard_range(shots, rank, world)
     if runner is not None:
         local = runner(lo, hi)
     else:
-        engine = program._get_engine(compiled)
-        local = engine.run(hi - lo, lo, seed, mode=mode)
+        local = program._run_local(compiled, hi - lo, shot_offset + lo, seed,
+                                   None if replay_meas is None else np.asarray(replay_meas)[lo:hi],
+                                   None if replay_noise is None else np.asarray(replay_noise)[lo:hi],
+                                   mode, on_device=True)
     if world > 1:
         local = gather_records(local, shots, compiled.n_meas, group)
     return local.cpu().numpy() if isinstance(local, torch.Tensor) else np.asarray(local)

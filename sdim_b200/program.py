@@ -191,15 +191,22 @@ class Program:
         method="frame": the reference's default multi-shot shortcut (sdim/program.py:244-265) — shot 0 is one
         noiseless reference tableau shot, shots 1.. are Pauli frames propagated on the GPU (sdimb_frames)."""
         compiled = self._compiled(fold=self.fold_gates)
-        if seed is None:
-            seed = random.getrandbits(63)       # follows the user's random.seed(), like the reference's draws
         if method not in ("tableau", "frame"):
             raise ValueError("method must be 'tableau' or 'frame'")
+        if distributed:
+            from .dist import broadcast_seed
+            seed = broadcast_seed(seed)         # one seed for all ranks (rank 0's draw when none was given)
+        elif seed is None:
+            seed = random.getrandbits(63)       # follows the user's random.seed(), like the reference's draws
         if method == "frame":
+            if replay_meas is not None or replay_noise is not None or shot_offset != 0 or mode is not None or distributed:
+                raise ValueError("method='frame' takes none of replay_meas, replay_noise, shot_offset, mode, distributed: "
+                                 "frames are drawn per extra shot (ids 1..shots-1) around one reference tableau shot")
             rec = self._run_frames(compiled, shots, seed)
         elif distributed:
             from .dist import simulate_sharded
-            rec = simulate_sharded(self, compiled, shots, seed, mode=mode)
+            rec = simulate_sharded(self, compiled, shots, seed, mode=mode, shot_offset=shot_offset,
+                                   replay_meas=replay_meas, replay_noise=replay_noise)
         else:
             rec = self._run_local(compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split=True)
         values, det = rec if isinstance(rec, tuple) else (rec & 0x7F, (rec & 0x80) != 0)
@@ -215,19 +222,27 @@ class Program:
         # reference shot: N1 is the identity there (sdim/program.py:31,245-247)
         quiet = torch.zeros((1, compiled.n_noise, 2), dtype=torch.uint8) if compiled.n_noise else None
         store = self._initial_store(engine, 1)
-        ref = engine.run(1, 0, seed, None, quiet, tableau=store, fresh=store is None)
+        if store is None:
+            store = engine.alloc_tableau(1)
+            engine.init_tableau(store)
+        ref = engine.run(1, 0, seed, None, quiet, tableau=store, fresh=False, keep_tableau=True)
         out = np.empty((shots, compiled.n_meas), dtype=np.uint8)
         out[:1] = ref.cpu().numpy()
         if shots > 1:
             out[1:] = engine.run_frames(shots - 1, ref[0], 1, seed).cpu().numpy()
-        self._tableau_thunk = None
+        # like the reference, which leaves the reference shot's final tableau in self.stabilizer_tableau
+        # (sdim/program.py:245-247)
+        self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
+                                                              engine.export(store, 0))
         return out
 
     WAVE_RECORD_BYTES = 256 << 20      # records per launch when the shots do not need an HBM tableau each
 
-    def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split: bool = False):
+    def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split: bool = False,
+                   on_device: bool = False):
         """Packed record bytes uint8[shots, n_meas]; with `split`, (values, deterministic) instead — unpacked wave
-        by wave while the device is busy with the next wave."""
+        by wave while the device is busy with the next wave.  With `on_device` the packed records stay in ONE device
+        tensor (the sharded path gathers them over NCCL from there); waves then only bound the HBM tableau store."""
         import torch
         engine = self._get_engine(compiled)
         rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
@@ -242,6 +257,18 @@ class Program:
             wave = max(1, min(shots, int(0.6 * free_bytes) // max(per_shot, 1)))
         elif shots > 0:
             wave = max(1, min(shots, self.WAVE_RECORD_BYTES // max(compiled.n_meas, 1)))
+        if on_device:
+            full = torch.empty((shots, compiled.n_meas), dtype=torch.uint8, device=engine.device)
+            step = max(wave, 1) if need_tab else max(shots, 1)
+            for lo in range(0, shots, step):
+                hi = min(shots, lo + step)
+                store = self._initial_store(engine, hi - lo)
+                engine.run(hi - lo, shot_offset + lo, seed, None if rm is None else rm[lo:hi],
+                           None if rn is None else rn[lo:hi], mode=mode, tableau=store, fresh=store is None,
+                           records=full[lo:hi])
+                del store
+            self._set_last_shot_thunk(compiled, engine, shots, shot_offset, seed, rm, rn, mode)
+            return full
         out = np.empty((shots, compiled.n_meas), dtype=np.uint8)
         det = np.empty((shots, compiled.n_meas), dtype=bool) if split else None
 
@@ -296,6 +323,11 @@ class Program:
                 collect(0)
                 collect(1)
 
+        self._set_last_shot_thunk(compiled, engine, shots, shot_offset, seed, rm, rn, mode)
+        return (out, det) if split else out
+
+    def _set_last_shot_thunk(self, compiled, engine, shots, shot_offset, seed, rm, rn, mode):
+        """`stabilizer_tableau` of a batched run = the tableau of its last shot, re-simulated on demand."""
         def last_shot_tableau(last=shots - 1):
             one = engine.alloc_tableau(1)
             if self.initial_tableau is not None:
@@ -306,7 +338,6 @@ class Program:
             return ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, engine.export(one, 0))
 
         self._tableau_thunk = last_shot_tableau if shots > 0 else None
-        return (out, det) if split else out
 
     def simulate(self, shots: int = 1, show_measurement: bool = False, record_tableau: bool = False,
                  force_tableau: bool = False, verbose: bool = False, show_gate: bool = False, exact: bool = False,

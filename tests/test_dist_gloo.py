@@ -58,3 +58,63 @@ def test_two_rank_gather_equals_single_process(tmp_path, shots):
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), f"rank{r}.npy"))
         assert got.shape == (shots, n_meas) and np.array_equal(got, want)
+
+
+def _worker_program(rank, world, port, out_dir):
+    """The product's own distributed path (Program.simulate_records(distributed=True)) on the stand-in engine: initial
+    tableau, replayed draws, shot_offset and an unseeded call all have to behave as in a single process."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    import sdim_b200.engine as engine_mod
+    from fake_engine import FakeEngine
+    from make_cases import random_circuit
+    from sdim_b200 import Program
+    engine_mod.TableauEngine = FakeEngine
+    torch.cuda.mem_get_info = lambda device=None: (1 << 34, 1 << 34)
+    shots = 7
+    circ = random_circuit(5, 6, 3, 60)
+    # (a) plain: global shot ids, explicit seed and shot_offset
+    a = Program(circ).simulate_records(shots, seed=11, shot_offset=100, distributed=True)
+    # (b) unseeded: ranks seed `random` differently, rank 0's draw must win everywhere
+    random.seed(1000 + rank)
+    prog_b = Program(circ)
+    b = prog_b.simulate_records(shots, distributed=True)
+    # (c) replayed measurement outcomes + an initial tableau taken from a previous run
+    rm = (np.arange(shots * a.values.shape[1], dtype=np.uint8).reshape(shots, -1) % 3)
+    start = Program(circ)
+    start.simulate_records(1, seed=3)
+    c = Program(circ, tableau=start.stabilizer_tableau).simulate_records(shots, seed=11, replay_meas=rm, distributed=True)
+    np.savez(os.path.join(out_dir, f"prog_rank{rank}.npz"), a=a.values, a_det=a.deterministic, b=b.values,
+             b_seed=np.uint64(b.seed), c=c.values, a_off=a.shot_offset)
+    dist.destroy_process_group()
+
+
+def test_two_rank_program_path_equals_single_process(tmp_path, monkeypatch):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_program, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    import random
+    import sdim_b200.engine as engine_mod
+    from fake_engine import FakeEngine
+    from make_cases import random_circuit
+    from sdim_b200 import Program
+    monkeypatch.setattr(engine_mod, "TableauEngine", FakeEngine)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda device=None: (1 << 34, 1 << 34))
+    shots = 7
+    circ = random_circuit(5, 6, 3, 60)
+    got = [np.load(os.path.join(str(tmp_path), f"prog_rank{r}.npz")) for r in range(world)]
+    a = Program(circ).simulate_records(shots, seed=11, shot_offset=100)
+    for g in got:
+        assert np.array_equal(g["a"], a.values) and np.array_equal(g["a_det"], a.deterministic) and int(g["a_off"]) == 100
+    random.seed(1000)                                                      # rank 0's stream
+    b = Program(circ).simulate_records(shots)
+    assert int(got[0]["b_seed"]) == int(got[1]["b_seed"]) == b.seed
+    for g in got:
+        assert np.array_equal(g["b"], b.values)
+    rm = (np.arange(shots * a.values.shape[1], dtype=np.uint8).reshape(shots, -1) % 3)
+    start = Program(circ)
+    start.simulate_records(1, seed=3)
+    c = Program(circ, tableau=start.stabilizer_tableau).simulate_records(shots, seed=11, replay_meas=rm)
+    for g in got:
+        assert np.array_equal(g["c"], c.values)
+    assert not np.array_equal(c.values, Program(circ).simulate_records(shots, seed=11, replay_meas=rm).values)

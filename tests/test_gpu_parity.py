@@ -392,6 +392,30 @@ def test_config5_large_single_tableau():
             assert np.array_equal(arrs[key], fin[key]), key
 
 
+@pytest.mark.parametrize("d", [5, 7])
+def test_config5_at_full_size_n4096(d):
+    """BASELINE config 5 AT ITS STATED SIZE: generate_random_clifford_circuit(4096, 8192, d, measurement_rounds=1,
+    seed=1), one 64 MiB tableau, d = 5 and 7 — the cluster interpreter (what auto picks) and one CTA per shot, records
+    and all six final arrays against the C oracle (0.15 s per shot on one host core)."""
+    from oracle import c_oracle
+    from sdim_b200 import generate_random_clifford_circuit
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    n = 4096
+    prog = compile_circuits([generate_random_clifford_circuit(n, 2 * n, d, measurement_rounds=1, seed=1)])
+    assert prog.n_ops == 3 * n and prog.n_meas == n
+    want, fin = c_oracle.run(n, d, prog.ops, 1, 0, 3, want_final=True)
+    assert ((want & 0x80) != 0).any() and ((want & 0x80) == 0).any()
+    eng = TableauEngine(prog)
+    assert eng.plan(None)[0] == "lanes-global" and eng.cluster_size(1, None) >= 8
+    for mode in (None, "global-cta"):
+        got = eng.run(1, 0, 3, keep_tableau=True, mode=mode).cpu().numpy()
+        assert np.array_equal(got, want), mode
+        arrs = eng.export(eng.tableau, 0)
+        for key in ("x", "z", "p", "dx", "dz", "dp"):
+            assert np.array_equal(arrs[key], fin[key]), (mode, key)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Cluster interpreter (one shot per thread-block cluster, sdim_b200/csrc/clusters.cuh)
 # ---------------------------------------------------------------------------------------------------
