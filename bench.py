@@ -9,10 +9,16 @@ gate on the qudit(s) it touched, then M on all 256 qudits; one full stabilizer t
 2026.  A step = one pass of the whole circuit over `--shots` shots per GPU.  Metric: shot*gates/s with
 gates = len(circuit.operations) as the user wrote them.
 
-`value`  : device-timed (CUDA events on the launch stream), op stream already resident in HBM.
-`e2e`    : the same metric through the host-buffer C-ABI call sdimb_simulate_host (host op stream in,
-           host records out; H2D/D2H and scratch allocation inside the timed region).
-`--impl reference` times the CPU oracle port of the reference algorithm (oracle/) on the host cores.
+`value`  : device-timed (CUDA events on the launch stream), op stream already resident in HBM.  At N > 1 a step is
+           this rank's shots + the NCCL all-gather of the packed records (the path's one collective).
+`e2e`    : N = 1: the same metric through the host-buffer C-ABI call sdimb_simulate_host (host op stream in,
+           host records out; H2D/D2H inside the timed region).  N > 1: op stream uploaded from pinned host memory,
+           simulation, all-gather, gathered records copied to pinned host memory on rank 0; wall clock, max over ranks.
+`configs`: short timed runs of BASELINE.json configs 2, 3, 4 with their TOTAL shot count split over the N ranks
+           (strong scaling), gather included, each with an oracle check; config 5 (replicas only) at N = 1.
+`--impl reference` times the C/OpenMP restatement of the reference algorithm (oracle/) on all host cores
+(`cpu_baseline.kind` "port"); the line of the GPU arm at N = 1 also carries `cpu_baseline_reference`: the reference
+ITSELF (unmodified events555/sdim from baseline/_ref or /root/reference, pure Python) on one core.
 """
 from __future__ import annotations
 
@@ -168,6 +174,53 @@ def cpu_sample_size(prog, seed: int, target_s: float, requested: int) -> int:
     return int(min(max(probe, target_s / per_shot), 1 << 16))
 
 
+def shared_config(prog, world: int) -> dict:
+    """`config` of BOTH arms (the driver compares them): the workload and nothing arm-specific."""
+    return {"workload": workload_name(), "gates_per_shot": prog.n_user_gates, "ops_in_stream": prog.n_ops,
+            "n_meas": prog.n_meas, "n_noise": prog.n_noise,
+            "clifford_gates_per_shot": prog.n_user_gates - prog.n_noise - prog.n_meas,
+            "l2": "GPU arm: L2 flushed (256 MiB fill) between timed steps, outside the timed region; CPU arm: n/a",
+            "parallelism": f"shots sharded over {world} GPU(s); one NCCL all-gather of the records per step at N > 1"}
+
+
+def time_reference_itself(prog, seed: int, target_s: float = 12.0, max_shots: int = 8):
+    """SURVEY 8d's primary CPU baseline: the UNMODIFIED reference, `Program(circuit).simulate(shots=1,
+    force_tableau=True)` (sdim/program.py:206-365), one shot at a time on ONE core, each N1 replaced by the explicit
+    Pauli its Philox draw stands for (the reference's tableau path ignores N1, program.py:31).  Returns None when no
+    copy of the reference is reachable (baseline/_ref travels to the GPU box; /root/reference exists in the build
+    container only).  Also returns the reference's records so the GPU can be checked against them under replay."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        return None
+    import random as _random
+    from sdim_b200.rng import noise_draws
+    sdim = rh.load_reference()
+    import sdim.tableau.tableau_prime as tp
+    n, d = prog.num_qudits, prog.dimension
+    ops = prog.ops.tolist()
+    spent, recs, shots = 0.0, [], 0
+    while shots < max_shots and (shots == 0 or spent + spent / shots <= target_s):
+        noise = noise_draws(seed, d, [shots], prog.noise_thresh24, prog.noise_channel)[0] if prog.n_noise else None
+        circ = rh.build_reference_circuit(sdim, n, d, ops, noise)
+        saved, tp.random = tp.random, rh._ChoiceFeed(_random.Random(seed + shots))
+        try:
+            program = sdim.Program(circ)
+            t0 = time.perf_counter()
+            program.simulate(shots=1, force_tableau=True)
+            spent += time.perf_counter() - t0
+        finally:
+            tp.random = saved
+        chron = rh._chronological(ops, program.measurement_results)
+        recs.append(np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in chron], dtype=np.uint8))
+        shots += 1
+    return {"value": shots * prog.n_user_gates / spent, "unit": UNIT, "cores": 1, "kind": "reference",
+            "host_cores_available": len(os.sched_getaffinity(0)),
+            "sample": f"first {shots} shots of the same circuit, one Program.simulate(shots=1, force_tableau=True) per "
+                      f"shot with that shot's N1 events as explicit Paulis ({spent:.1f} s); unmodified events555/sdim "
+                      f"1.2.0 from {os.path.relpath(rh.REFERENCE_ROOT, ROOT) if rh.REFERENCE_ROOT.startswith(ROOT) else rh.REFERENCE_ROOT}",
+            "seconds_per_shot": spent / shots}, np.stack(recs)
+
+
 def bench_reference(args):
     """--impl reference: the CPU restatement of the reference algorithm on the host cores (rank 0 only)."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -188,7 +241,11 @@ def bench_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(), "shots_per_step": sample, "gates_per_shot": gates},
+        "config": shared_config(prog, args.gpus),
+        "impl_detail": "reference-port: C/OpenMP restatement of the reference algorithm (oracle/oracle.c), all host "
+                       "cores; the reference itself is pure Python, see cpu_baseline_reference in the GPU arm's line",
+        "run": {"shots_per_step": sample},
+        "clifford_only_value": value * (gates - prog.n_noise - prog.n_meas) / gates,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{sample} shots x {gates} ops per step, {args.steps} steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,6 +259,129 @@ def workload_name():
     return (f"noisy random Clifford d={w['d']} n={w['n']}: generate_random_clifford_circuit({w['n']},{w['gates']},"
             f"{w['d']},seed={w['circuit_seed']}) + N1(p={w['noise_prob']},'{w['noise_channel']}') after every gate "
             f"+ M on all qudits; one tableau per shot")
+
+
+def _device_ms(fn, stream, reps: int, before=None):
+    """Mean device time of `reps` calls of fn, CUDA events on `stream`; `before` runs untimed ahead of each call."""
+    import torch
+    evs = []
+    for _ in range(reps):
+        if before is not None:
+            before()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return [e0.elapsed_time(e1) for e0, e1 in evs]
+
+
+def bench_configs(args, dev, world, rank, barrier, reduce_max):
+    """BASELINE.json configs 2, 3, 4 at their stated TOTAL shot counts, split over the N ranks (strong scaling), the
+    record gather inside the timed region; config 5 (one tableau: replicas only) at N = 1.  Every entry carries an
+    oracle check of a sample of the (gathered) records."""
+    import torch
+    import torch.distributed as dist
+    from oracle import c_oracle
+    from sdim_b200 import generate_random_clifford_circuit
+    from sdim_b200.dist import gather_records, shard_range
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.workloads import qudit_repetition_code, rotated_surface_code
+    scale = args.config_scale
+    jobs = [
+        ("config2: random Clifford d=3 n=64, depth 2000 + M on all qudits",
+         generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1), max(8 * world, int(10 ** 4 * scale))),
+        ("config3: rotated surface code distance 7, d=2, 97 qubits, 7 rounds, N1 'd' p=1e-3, RESET ancillas",
+         rotated_surface_code(7, 7, 1e-3), max(8 * world, int(10 ** 6 * scale))),
+        ("config4: qutrit repetition code distance 25, 25 rounds, N1 'f' p=1e-2, RESET ancillas",
+         qudit_repetition_code(25, 25, 3, 1e-2, "f"), max(8 * world, int(10 ** 7 * scale))),
+    ]
+    out = []
+    stream = torch.cuda.current_stream(dev)
+    pin = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+    for name, circ, total in jobs:
+        prog = compile_circuits([circ])
+        eng = TableauEngine(prog, dev)
+        kernel, need_tab = eng.plan(None)
+        lo, hi = shard_range(total, rank, world)
+        local = torch.empty((hi - lo, prog.n_meas), dtype=torch.uint8, device=dev)
+        tab = eng.alloc_tableau(hi - lo) if need_tab else None
+        gathered = [local]
+
+        def sim():
+            eng.run(hi - lo, lo, 7, tableau=tab, records=local)
+
+        def sim_gather():
+            sim()
+            if world > 1:
+                gathered[0] = gather_records(local, total, prog.n_meas)
+
+        sim_gather()                                   # warm-up (NCCL channels, scratch)
+        barrier()
+        sim_ms = float(np.mean(_device_ms(sim, stream, 2)))
+        barrier()
+        step_ms = float(np.mean(_device_ms(sim_gather, stream, 2)))
+        # end to end: + the gathered records to host memory on rank 0 through a pinned staging buffer
+        barrier()
+        t0 = time.perf_counter()
+        sim_gather()
+        if rank == 0:
+            flat = gathered[0].reshape(-1)
+            for off in range(0, flat.numel(), pin.numel()):
+                m = min(pin.numel(), flat.numel() - off)
+                pin[:m].copy_(flat[off:off + m], non_blocking=True)
+            torch.cuda.synchronize(dev)
+        barrier()
+        e2e_s = reduce_max(time.perf_counter() - t0)
+        sim_ms, step_ms = reduce_max(sim_ms), reduce_max(step_ms)
+        entry = None
+        if rank == 0:
+            full = gathered[0]
+            ok = True
+            per = 32
+            for r in range(world):                     # first shots of every rank's range against the C oracle
+                rlo, rhi = shard_range(total, r, world)
+                k = min(per, rhi - rlo)
+                if k > 0 and c_oracle.available():
+                    want = c_oracle.run_philox(prog, k, rlo, 7)
+                    ok = ok and bool(np.array_equal(full[rlo:rlo + k].cpu().numpy(), want))
+            gates = prog.n_user_gates
+            entry = {"name": name, "n": prog.num_qudits, "d": prog.dimension, "kernel": kernel, "scaling": "strong",
+                     "shots_total": total, "shots_per_gpu": hi - lo, "gates_per_shot": gates, "n_meas": prog.n_meas,
+                     "value": total * gates / (step_ms * 1e-3), "unit": UNIT, "ms_per_pass": step_ms,
+                     "simulate_ms": sim_ms, "gather_ms": max(step_ms - sim_ms, 0.0),
+                     "gather_bytes_received_per_gpu": int(total * prog.n_meas * (world - 1) / world),
+                     "e2e": {"value": total * gates / e2e_s, "unit": UNIT, "seconds": e2e_s,
+                             "d2h_bytes_rank0": int(total * prog.n_meas)},
+                     "records_match_oracle": ok if c_oracle.available() else None,
+                     "oracle_sample": f"first {per} shots of each rank's range, C restatement, Philox seed 7"}
+        out.append(entry)
+        del local, tab, gathered, eng
+        torch.cuda.empty_cache()
+    if world == 1:                                     # config 5: one 64 MiB tableau; it does not shard (replicas only)
+        for d in (5, 7):
+            n = args.config5_n
+            prog = compile_circuits([generate_random_clifford_circuit(n, 2 * n, d, measurement_rounds=1, seed=1)])
+            eng = TableauEngine(prog, dev)
+            tab = eng.alloc_tableau(1)
+            rec = torch.empty((1, prog.n_meas), dtype=torch.uint8, device=dev)
+
+            def one():
+                eng.run(1, 0, 3, tableau=tab, records=rec)
+
+            one()
+            ms = float(np.min(_device_ms(one, stream, 3)))
+            want = c_oracle.run_philox(prog, 1, 0, 3) if c_oracle.available() else None
+            out.append({"name": f"config5: single tableau random Clifford d={d} n={n}, {prog.n_ops} ops, 1 shot "
+                                f"(replicas only: does not shard)", "n": n, "d": d,
+                        "kernel": f"{eng.plan(None)[0]}, {eng.cluster_size(1)}-CTA cluster", "shots_total": 1,
+                        "gates_per_shot": prog.n_user_gates, "ms_per_pass": ms, "unit": UNIT,
+                        "value": prog.n_user_gates / (ms * 1e-3),
+                        "records_match_oracle": None if want is None else bool(np.array_equal(rec.cpu().numpy(), want))})
+            del tab, eng
+    return out
 
 
 def bench_ours(args):
@@ -227,16 +407,26 @@ def bench_ours(args):
     kernel_name, need_tab = engine.plan(args.mode)
     tab = engine.alloc_tableau(shots) if need_tab else None
     records = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world * shots, prog.n_meas), dtype=torch.uint8, device=dev) if world > 1 else records
     lo = rank * shots                       # global shot ids of this rank
     stream = torch.cuda.current_stream(dev)
 
     def step():
         engine.run(shots, lo, seed, mode=args.mode, tableau=tab, records=records)
+        if world > 1:                       # the path's one collective: all ranks end with every record
+            dist.all_gather_into_tensor(gathered, records)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def reduce_max(v: float) -> float:
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -248,45 +438,82 @@ def bench_ours(args):
     barrier()
     launches0 = N.lib().sdimb_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
         barrier()
-        for e0, e1 in ev:
+        for (e0, e1), em in zip(ev, mid):
             flush_l2()                      # untimed: evict the previous step's lines from L2
             e0.record(stream)
-            step()
+            engine.run(shots, lo, seed, mode=args.mode, tableau=tab, records=records)
+            em.record(stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, records)
             e1.record(stream)
         barrier()
         time.sleep(0.25)
     launches = N.lib().sdimb_launch_count() - launches0
-    kernel_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
-    total_ms = float(sum(kernel_ms))        # exactly K timed steps, device time on the launch stream
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    kernel_ms = [e0.elapsed_time(em) for (e0, _e1), em in zip(ev, mid)]
+    total_ms = reduce_max(float(sum(step_ms)))       # exactly K timed steps, device time on the launch stream
     value = world * shots * args.steps * gates / (total_ms * 1e-3)
+    gather_ms = reduce_max(float(np.mean(step_ms)) - float(np.mean(kernel_ms)))
 
-    # ---- end to end through the host-buffer C ABI call -------------------------------------------
+    # ---- the gathered matrix against the oracle (N > 1): a sample of every rank's rows ---------------------------
+    gather_ok = None
+    if world > 1 and rank == 0:
+        from oracle import c_oracle
+        if c_oracle.available():
+            gather_ok = True
+            g = gathered.cpu().numpy()
+            for r in range(world):
+                want = c_oracle.run_philox(prog, 16, r * shots, seed)
+                gather_ok = gather_ok and bool(np.array_equal(g[r * shots: r * shots + 16], want))
+
+    # ---- end to end ---------------------------------------------------------------------------------------------
     e2e_shots = shots
     e2e_times = []
-    simulate_host(prog, e2e_shots, lo, seed, mode=args.mode)   # warm-up: sizes the library's reusable workspace
-    for _ in range(max(1, min(args.steps, 3))):
-        barrier()
-        t0 = time.perf_counter()
-        rec_host, _ms = simulate_host(prog, e2e_shots, lo, seed, mode=args.mode)
-        e2e_times.append(time.perf_counter() - t0)
-    e2e_t = float(np.mean(e2e_times))
-    if world > 1:
-        t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_t = float(t.item())
-    e2e_value = world * e2e_shots * gates / e2e_t
     up_rows = N.schedule(prog.num_qudits, prog.ops).shape[0] if kernel_name.startswith("planes") else prog.n_ops
-    h2d = up_rows * 16 + prog.noise_thresh24.nbytes + prog.noise_channel.nbytes      # what the call uploads
-    d2h = e2e_shots * prog.n_meas
+    if world == 1:
+        # through the host-buffer C ABI call: host op stream in, host records out
+        simulate_host(prog, e2e_shots, lo, seed, mode=args.mode)   # warm-up: sizes the library's reusable workspace
+        for _ in range(max(1, args.steps)):
+            barrier()
+            t0 = time.perf_counter()
+            rec_host, _ms = simulate_host(prog, e2e_shots, lo, seed, mode=args.mode)
+            e2e_times.append(time.perf_counter() - t0)
+        h2d = up_rows * 16 + prog.noise_thresh24.nbytes + prog.noise_channel.nbytes      # what the call uploads
+        d2h = e2e_shots * prog.n_meas
+        e2e_how = "sdimb_simulate_host (C ABI, host buffers)"
+    else:
+        # op stream from pinned host memory -> device, simulate, all-gather, gathered records -> pinned host (rank 0)
+        host_ops = engine.ops_sched.cpu().pin_memory() if engine.ops_sched is not None else None
+        host_out = torch.empty((world * shots, prog.n_meas), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        for it in range(1 + max(1, args.steps)):
+            barrier()
+            t0 = time.perf_counter()
+            if host_ops is not None:
+                engine.ops_sched.copy_(host_ops, non_blocking=True)
+            step()
+            if rank == 0:
+                host_out.copy_(gathered, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            if it > 0:
+                e2e_times.append(time.perf_counter() - t0)
+        rec_host = records.cpu().numpy()
+        h2d = (host_ops.numel() * 4 if host_ops is not None else 0)
+        d2h = world * shots * prog.n_meas
+        e2e_how = "pinned op stream -> device, simulate, NCCL all_gather_into_tensor, gathered records -> pinned host on rank 0"
+    e2e_t = reduce_max(float(np.mean(e2e_times)))
+    e2e_value = world * e2e_shots * gates / e2e_t
 
     # the device-buffer path and the host-buffer path must agree bit for bit (same Philox counters)
     same = bool(np.array_equal(records.cpu().numpy(), rec_host))
+
+    configs = None
+    if not args.no_configs:
+        configs = bench_configs(args, dev, world, rank, barrier, reduce_max)
 
     if rank != 0:
         if world > 1:
@@ -302,19 +529,39 @@ def bench_ours(args):
     alg_bytes_dense = algorithmic_bytes_per_shot(prog, det_flags, None) * shots
     launch_s = float(np.mean(kernel_ms)) * 1e-3
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    sm_max_mhz = 1965.0
     if os.path.exists(peaks_path):
         with open(peaks_path) as fh:
-            peak, peak_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            pj = json.load(fh)
+        peak, peak_src = float(pj["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        sm_max_mhz = float(pj.get("sm_max_mhz", sm_max_mhz))
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / launch_s / 1e9
-    traffic = None
+    # counters of the SAME kernel from the committed ncu capture of this build (profiles/traffic.json, written by
+    # tools/summarise_profiles.py): DRAM bytes and executed warp instructions per launch, scaled by the shot count
+    traffic = inst = None
+    capture = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
         if tj.get("shots"):
             traffic = tj["dram_bytes_per_launch"] * (shots / tj["shots"])
+            if tj.get("inst_executed_per_launch"):
+                inst = tj["inst_executed_per_launch"] * (shots / tj["shots"])
+            capture = {k: tj.get(k) for k in ("capture", "duration_ms", "issue_active_pct", "warps_active_pct",
+                                               "l2_hit_pct", "l1_hit_pct", "top_stalls") if k in tj}
+    clk = clocks.summary()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue = None
+    if inst:
+        sm_hz = (clk.get("sm_mhz") or sm_max_mhz) * 1e6
+        slots = sms * 4 * sm_hz * launch_s            # one warp instruction per scheduler per cycle
+        issue = {"warp_instructions_per_launch": inst, "issue_slots_per_launch": slots, "frac": inst / slots,
+                 "warp_instructions_per_shot_op": inst / (shots * prog.n_ops),
+                 "note": "executed warp instructions (ncu smsp__inst_executed.sum) / (SMs x 4 schedulers x SM clock "
+                         "under load x launch time)"}
 
     # ---- BASELINE.json's second metric: gate-update HBM GB/s vs peak.  The gates of the same circuit (no noise,
     # no measurement) streamed over one uint8 tableau per shot in HBM by the lane interpreter ("global" mode):
@@ -342,16 +589,24 @@ def bench_ours(args):
                 gtimes.append(g0.elapsed_time(g1))
         gbytes = algorithmic_bytes_per_shot(gprog, [], None) * gshots
         gms = float(np.mean(gtimes))
+        gdram = None
+        if os.path.exists(tpath) and tj.get("all", {}).get("gates_stream", {}).get("shots"):
+            gs = tj["all"]["gates_stream"]
+            gdram = gs["dram_bytes_per_launch"] * (gshots / gs["shots"]) / (gms * 1e-3) / 1e9
         gate_update = {"kernel": "interp_kernel_stream (uint8 lanes, 16 lanes per thread, one tableau per shot in HBM)",
                        "workload": f"{gprog.n_ops} gates of the headline circuit, {gshots} shots, "
                                    f"{gshots * L.shot_bytes / 2**30:.2f} GiB store, tableaus evolve across launches",
                        "achieved": gbytes / (gms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                        "frac": gbytes / (gms * 1e-3) / 1e9 / peak, "launch_ms": gms,
+                       "achieved_dram": gdram, "frac_dram": (gdram / peak) if gdram else None,
+                       "reading": "achieved = SURVEY 8d algorithmic bytes / time (effective); achieved_dram = DRAM bytes "
+                                  "of the committed ncu capture / time (the rest are L2 hits, phases kept in "
+                                  "registers and unchanged words not rewritten)",
                        "shot_gates_per_sec": gshots * gprog.n_ops / (gms * 1e-3)}
         del gtab
 
-    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----------------------------------------
-    cpu = None
+    # ---- CPU baselines on bounded samples (rank 0, N = 1 only) ----------------------------------------
+    cpu = cpu_ref = None
     if world == 1 and not args.no_cpu:
         cpu_shots = min(cpu_sample_size(prog, seed, 15.0, args.cpu_shots), shots)     # ~15 s of CPU work
         dt, cores, kind, cpu_rec = run_cpu_oracle(prog, cpu_shots, seed)
@@ -360,29 +615,47 @@ def bench_ours(args):
                "sample": f"first {cpu_shots} shots of the same circuit/seed, C restatement of the reference "
                          f"algorithm with OpenMP over shots ({dt:.1f} s)",
                "records_match_gpu": cpu_ok}
+        ref = time_reference_itself(prog, seed, target_s=args.reference_seconds)
+        if ref is not None:
+            cpu_ref, ref_rec = ref
+            k = ref_rec.shape[0]
+            # the reference drew its own outcomes: replay them into the GPU (noise stays on Philox, same events)
+            rm = torch.from_numpy(ref_rec & 0x7F)
+            got = engine.run(k, 0, seed, rm, None, mode=args.mode).cpu().numpy()
+            cpu_ref["records_match_gpu_under_replay"] = bool(np.array_equal(got, ref_rec))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(), "shots_per_gpu_per_step": shots, "gates_per_shot": gates,
-                   "ops_in_stream": prog.n_ops, "n_meas": prog.n_meas, "n_noise": prog.n_noise,
-                   "mode": args.mode or "auto", "kernel": kernel_name,
-                   "l2": "L2 flushed (256 MiB fill) between timed steps, outside the timed region",
-                   "tableau_store_mib_per_step": (shots * L.shot_bytes / 2**20) if need_tab else 0.0,
-                   "parallelism": f"shots sharded over {world} GPU(s), no data-path collective"},
+        "config": shared_config(prog, world),
+        "run": {"shots_per_gpu_per_step": shots, "mode": args.mode or "auto", "kernel": kernel_name,
+                "tableau_store_mib_per_step": (shots * L.shot_bytes / 2**20) if need_tab else 0.0,
+                "gather_ms_per_step": gather_ms if world > 1 else 0.0,
+                "gather_bytes_received_per_gpu_per_step": (world - 1) * shots * prog.n_meas},
+        "clifford_only_value": value * (gates - prog.n_noise - prog.n_meas) / gates,
+        "gather_matches_oracle": gather_ok,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "records_match_device_path": same},
+                "calls_timed": len(e2e_times), "how": e2e_how, "records_match_device_path": same},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "interp_planes_kernel" if kernel_name.startswith("planes") else "interp_kernel", "peak_source": peak_src,
+                     "traffic": traffic,
+                     "achieved_dram": (traffic / launch_s / 1e9) if traffic else None,
+                     "frac_dram": (traffic / launch_s / 1e9 / peak) if traffic else None,
+                     "limiter": "warp issue + latency, not DRAM: the state of a shot lives in L1/L2 (see issue, "
+                                "frac_dram and DESIGN.md section 4); `achieved` is the contract's algorithmic-bytes "
+                                "reading (effective GB/s)",
+                     "issue": issue, "ncu_capture": capture,
+                     "kernel": "interp_planes_kernel" if kernel_name.startswith("planes") else "interp_kernel", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_s * 1e3,
                      "accounting": "SURVEY 8d per-op bytes; measurements count only generators with non-zero factor "
                                    "(the reference's own skip rule), see DESIGN.md section 4",
                      "achieved_dense": alg_bytes_dense / launch_s / 1e9},
         "gate_update_hbm": gate_update,
         "cpu_baseline": cpu,
-        "clocks": clocks.summary(),
+        "cpu_baseline_reference": cpu_ref,
+        "configs": configs,
+        "clocks": clk,
     }
     print(json.dumps(line))
     if world > 1:
@@ -400,6 +673,11 @@ def main():
     ap.add_argument("--mode", default=None, choices=[None, "auto", "global", "resident", "lanes", "planes"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gate-update", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 2-5 block")
+    ap.add_argument("--config-scale", type=float, default=1.0, help="fraction of the configs' stated shot counts")
+    ap.add_argument("--config5-n", type=int, default=4096)
+    ap.add_argument("--reference-seconds", type=float, default=12.0,
+                    help="budget of the reference-itself CPU leg (0 shots beyond the first once exceeded)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # launched bare with --gpus N: become the torchrun launch the contract describes (one rank per GPU)

@@ -16,7 +16,8 @@
  *     NULL = legacy default stream) and never synchronise; pointers marked [device]
  *     are plain CUDA device addresses owned by the caller (PyTorch in this repo)
  *   - the device entry points keep no global mutable state: calls on distinct (stream, buffer) sets may run
- *     concurrently.  Only sdimb_simulate_host owns state (its reusable workspace) and serialises its callers
+ *     concurrently.  Only sdimb_simulate_host owns state (one reusable workspace per device) and serialises its
+ *     callers per device: host threads driving different GPUs run concurrently
  *   - there is NO CPU fallback: without a CUDA device every launch returns SDIMB_ECUDA
  *
  * Tableau store (one tableau per shot; replaces the six int64 arrays of
@@ -142,8 +143,8 @@ int sdimb_export(const void* tableau, int n, int d, int64_t shot,
 
 /* Same job as sdimb_run with HOST buffers only: schedules the op stream (sdimb_schedule), copies it and the noise
  * tables in, simulates from |0...0>, copies the records out through pinned staging and synchronises.  Device
- * scratch, the staging buffer, the stream and the events live in a grow-only workspace that later calls reuse
- * (calls are serialised internally; sdimb_release_workspace frees it).  This is the call a non-PyTorch host
+ * scratch, the staging buffer, the stream and the events live in a grow-only workspace of the CURRENT DEVICE that
+ * later calls reuse (calls on one device are serialised internally; sdimb_release_workspace frees all of them).  This is the call a non-PyTorch host
  * (e.g. the reference itself through ctypes) makes; `elapsed_ms` (nullable) receives the device time of the
  * whole call measured with CUDA events. */
 int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,

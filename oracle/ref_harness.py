@@ -18,7 +18,20 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SDIM_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference() -> str:
+    """$SDIM_REFERENCE_ROOT, else the read-only checkout of this container, else the offline install that travels to
+    the GPU box (baseline/_ref, made by baseline/install_reference.sh; git-ignored)."""
+    cands = [os.environ.get("SDIM_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "sdim")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference()
 
 _NAMES = ["I", "X", "X_INV", "Z", "Z_INV", "H", "H_INV", "P", "P_INV", "CNOT", "CNOT_INV",
           "CZ", "CZ_INV", "SWAP", "M", "M_X", "RESET", "N1"]

@@ -371,9 +371,10 @@ int sdimb_export(const void* tableau, int n, int d, int64_t shot, int64_t* x, in
   return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
 }
 
-// Workspace of the host-buffer entry: one grow-only device arena, one grow-only pinned staging buffer, a stream
-// and two events, created on first use and reused by later calls (cudaMalloc/cudaFree per call cost more than
-// the simulation of a small batch).  Calls are serialised by a mutex; sdimb_release_workspace() frees it.
+// Workspace of the host-buffer entry, ONE PER DEVICE: a grow-only device arena, a grow-only pinned staging buffer, a
+// stream and two events, created on first use and reused by later calls (cudaMalloc/cudaFree per call cost more than
+// the simulation of a small batch).  Calls on the same device are serialised by that workspace's mutex; host threads
+// driving different GPUs do not touch each other's workspace.  sdimb_release_workspace() frees all of them.
 namespace {
 struct HostWorkspace {
   std::mutex mu;
@@ -392,10 +393,8 @@ struct HostWorkspace {
     if (stream) cudaStreamDestroy(stream);
     dev = pin = nullptr; dev_cap = pin_cap = 0; stream = nullptr; e0 = e1 = nullptr; device = -1;
   }
-  bool prepare(size_t dev_bytes, size_t pin_bytes) {
-    int cur = 0;
-    if (cudaGetDevice(&cur) != cudaSuccess) return false;
-    if (cur != device) { release(); device = cur; }
+  bool prepare(int cur, size_t dev_bytes, size_t pin_bytes) {   // caller holds mu and has `cur` as current device
+    device = cur;
     if (!stream && cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (!e0 && cudaEventCreate(&e0) != cudaSuccess) return false;
     if (!e1 && cudaEventCreate(&e1) != cudaSuccess) return false;
@@ -414,13 +413,23 @@ struct HostWorkspace {
     return true;
   }
 };
-HostWorkspace g_ws;
+constexpr int kMaxDevices = 64;
+HostWorkspace g_ws_by_device[kMaxDevices];
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
 
 int sdimb_release_workspace(void) {
-  std::lock_guard<std::mutex> lock(g_ws.mu);
-  g_ws.release();
+  int cur = 0;
+  const bool have = cudaGetDevice(&cur) == cudaSuccess;
+  for (int dv = 0; dv < kMaxDevices; ++dv) {
+    HostWorkspace& ws = g_ws_by_device[dv];
+    std::lock_guard<std::mutex> lock(ws.mu);
+    if (ws.device < 0) continue;
+    cudaSetDevice(ws.device);
+    ws.release();
+  }
+  if (have) cudaSetDevice(cur);
+  cudaGetLastError();
   return SDIMB_OK;
 }
 
@@ -481,8 +490,11 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_scr = align256((size_t)sdimb_scratch_bytes(n, d, mode_flags));
   const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_scr + 256;
 
+  int cur_dev = 0;
+  if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= kMaxDevices) { cudaGetLastError(); return SDIMB_ECUDA; }
+  HostWorkspace& g_ws = g_ws_by_device[cur_dev];
   std::lock_guard<std::mutex> lock(g_ws.mu);
-  if (!g_ws.prepare(total, b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
+  if (!g_ws.prepare(cur_dev, total, b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
   cudaStream_t st = g_ws.stream;
   uint8_t* base = (uint8_t*)g_ws.dev;
   uint8_t* d_ops = base; base += b_ops;
