@@ -66,7 +66,9 @@ enum {
 #define SDIMB_OP_MASK 0xFF
 #define SDIMB_OP_WARP_SHIFT 8
 #define SDIMB_OP_INDEX_SHIFT 16
+#ifndef SDIMB_SCHED_WARPS          /* compile-time knob of A/B builds; the shipped library uses 4 */
 #define SDIMB_SCHED_WARPS 4
+#endif
 
 /* Record byte: low 7 bits = measured value, bit 7 = deterministic flag
  * (MeasurementResult.measurement_value / .deterministic, sdim/tableau/dataclasses.py:166-180). */

@@ -63,16 +63,31 @@ __device__ __forceinline__ E setbit2(E w, int b, uint32_t v) {
   return E{(w.l & ~m) | ((v & 1u) << b), (w.h & ~m) | (((v >> 1) & 1u) << b)};
 }
 
-template <int D>
+// IL (global image of large tableaus): the entries of a row are stored INTERLEAVED — stabilizer lane word j at entry
+// 2j, destabilizer lane word j (lane word np/32 + j) at entry 2j + 1 — and rows carry no padding entry, so that the two
+// entries a measurement's column walk and column writes touch per row (pivot lane p and its destabilizer lane np + p)
+// share one 32-byte sector (d = 3; half a sector for d = 2).  Gates loop over all lane words and do not care.
+template <int D, bool IL = false>
 struct Geo {
   static constexpr int EW = (D == 2) ? 2 : 4;   // words per entry
-  uint32_t* tab;                                // shared-memory image of the n rows
+  uint32_t* tab;                                // image of the n rows: shared memory, or this CTA's slab
   uint2* ph_base;                               // [NW][Wb] phase accumulators, always in shared memory
   uint2* pacc;                                  // phase accumulator used by ldp/stp (this warp's, or #0 in measure)
   int n, np, Wb, RS;                            // RS = row stride in words = EW * (Wb + 1)
   int gpw, gsub, j0, jstep;                     // rank-1 update: row groups per warp (32 / Wb when Wb divides 32), this
                                                 // lane's group inside the warp, its first lane word and its word stride
-  __device__ __forceinline__ uint32_t* entry(int q, int j) const { return tab + q * RS + j * EW; }
+  __device__ __forceinline__ uint32_t* entry(int q, int j) const {
+    if (IL) { const int h = np >> 5; j = (j < h) ? 2 * j : 2 * (j - h) + 1; }
+    return tab + q * RS + j * EW;
+  }
+  __device__ __forceinline__ XZ ld_at(const uint32_t* e) const {      // entry address computed by the caller
+    if (D == 3) {
+      const uint4 v = *reinterpret_cast<const uint4*>(e);
+      return XZ{E{v.x, v.y}, E{v.z, v.w}};
+    }
+    const uint2 v = *reinterpret_cast<const uint2*>(e);
+    return XZ{E{v.x, 0u}, E{v.y, 0u}};
+  }
   __device__ __forceinline__ uint2* phase() const { return pacc; }
   __device__ __forceinline__ uint2* phase_of(int w) const { return ph_base + w * Wb; }
   __device__ __forceinline__ XZ ld(int q, int j) const {
@@ -186,9 +201,11 @@ __device__ __forceinline__ uint32_t p_noise_event(const KParams& p, int64_t j, i
 #ifndef SDIMB_PG_SKIPLIST       // column walk: skip the list bookkeeping of a warp none of whose 32 rows is listed
 #define SDIMB_PG_SKIPLIST 0
 #endif
-// FW: the CTA is known to have four warps (global image), see cta_sync
-template <int D, bool FW = false>
-__device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local,
+// FW: the CTA is known to have four warps (global image), see cta_sync.
+// MERGE (used with the interleaved image): the column writes of the random branch happen inside the rank-1 pass and the
+// two pivot phases inside the phase pass — one pass over the support and one block barrier less per measurement.
+template <int D, bool FW, bool MERGE, class GEO>
+__device__ uint32_t p_measure(GEO G, const KParams& p, PScratch& S, int q, int64_t slot, int64_t shot_local,
                               bool fold, uint32_t draw) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO;
@@ -237,6 +254,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     const int jp = piv >> 5, bp = piv & 31, jd = np / 32 + jp;          // stab word / bit, destab word of lane p
     const uint32_t e = (D == 3) ? G.getx(q, piv) : 1u;                  // inverse of v mod 3 is v itself
     const uint32_t ps_old = G.getp(piv);
+    if (MERGE && tid == 0) cnt[1] = draw;                               // only warp 0 resolved the draw: publish it
     // one pass down the pivot column AND the destabilizer-p column: support list, values, stale destab entries
     uint32_t sd_part = 0;
     // one row of the walk, entries already loaded (all lanes of the warp call it together: it ballots)
@@ -263,12 +281,15 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       if (act) S.ar[(both & 0xFFFFu) + __popc(ma & lt)] = (uint16_t)r;
       if (stale) S.br[(both >> 16) + __popc(mb & lt)] = (uint16_t)r;
     };
+    const uint32_t* const col_s = G.entry(0, jp);        // entries of lane p / of its destabilizer in row 0: the walk
+    const uint32_t* const col_d = G.entry(0, jd);        // strides by rows (interleaved image: one 32-byte sector)
     SDIMB_P_LOOP
     for (int base = 0; base < n; base += nt) {
       const int r = base + tid;
       const XZ zero{E{0u, 0u}, E{0u, 0u}};
       XZ s = zero, dd = zero;
-      if (r < n) { s = G.ld(r, jp); dd = G.ld(r, jd); }
+      if (MERGE) { if (r < n) { s = G.ld_at(col_s + r * G.RS); dd = G.ld_at(col_d + r * G.RS); } }
+      else if (r < n) { s = G.ld(r, jp); dd = G.ld(r, jd); }
       walk_row(r, r < n, s, dd);
     }
     sd_part = __reduce_add_sync(FULL, sd_part);
@@ -285,6 +306,7 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
     const uint32_t sd_raw = cnt[2] % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
+    if (MERGE) draw = cnt[1];
     // col_i += f_i * col_p on the pivot's support.  Threads form row groups: 32/Wb per warp when Wb divides 32
     // (geometry precomputed in Geo: the divisions cost more than the update of a sparse measurement).
     const int gpw = G.gpw, gtot = gpw * nw, gid = warp * gpw + G.gsub, jstep = G.jstep;
@@ -293,16 +315,24 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       const uint2 fv = S.f[j];
       const E f{fv.x, fv.y};
       E dot{0u, 0u};
-      if (f.l | f.h) {
+      // MERGE: the words of lane p and of its destabilizer are always visited, and the column writes
+      // (destabilizer p <- old pivot, stabilizer p <- Z_q, tableau_prime.py:323-333) ride on the same store
+      if ((f.l | f.h) || (MERGE && (j == jp || j == jd))) {
         auto update_row = [&](const int r, const uint32_t c, const XZ& v) {
           const uint32_t s = c & 3u, t = c >> 2;
+          XZ nv;
           if (D == 3) {
             dot = add3(dot, smul3(v.z, s));                               // Z[:,i] . x_p  (old Z)
-            G.st(r, j, XZ{add3(v.x, smul3(f, s)), add3(v.z, smul3(f, t))});
+            nv = XZ{add3(v.x, smul3(f, s)), add3(v.z, smul3(f, t))};
           } else {
             if (s) dot.l ^= v.z.l;
-            G.st(r, j, XZ{E{v.x.l ^ (s ? f.l : 0u), 0u}, E{v.z.l ^ (t ? f.l : 0u), 0u}});
+            nv = XZ{E{v.x.l ^ (s ? f.l : 0u), 0u}, E{v.z.l ^ (t ? f.l : 0u), 0u}};
           }
+          if (MERGE) {
+            if (j == jp) { nv.x = setbit2(nv.x, bp, 0u); nv.z = setbit2(nv.z, bp, (r == q) ? 1u : 0u); }
+            else if (j == jd) { nv.x = setbit2(nv.x, bp, s); nv.z = setbit2(nv.z, bp, t); }
+          }
+          G.st(r, j, nv);
         };
         SDIMB_P_LOOP
         for (int ri = gid; ri < nr_a; ri += gtot) {
@@ -317,13 +347,24 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       }
       if (gpw == 1 || lane < Wb) S.dotw[warp * Wb + j] = make_uint2(dot.l, dot.h);
     }
+    if (MERGE) {            // rows outside the support (untouched above): clear their stale destabilizer-p entry
+      SDIMB_P_LOOP
+      for (int i = tid; i < nr_b; i += nt) {
+        const int r = S.br[i];
+        XZ dd = G.ld(r, jd);
+        dd.x = setbit2(dd.x, bp, 0u);
+        dd.z = setbit2(dd.z, bp, 0u);
+        G.st(r, jd, dd);
+      }
+    }
     cta_sync<FW>();
     // phase_i += f_i*ps + po*(f_i*dot_i + sd*f_i(f_i-1)/2*po)      (tableau_prime.py:310-312,317-319)
+    // MERGE: and, in the same store, destabilizer p <- old pivot phase, stabilizer p <- -m*po
     SDIMB_P_LOOP
     for (int j = tid; j < Wb; j += nt) {
       const uint2 fv = S.f[j];
       const E f{fv.x, fv.y};
-      if ((f.l | f.h) == 0) continue;
+      if ((f.l | f.h) == 0 && !(MERGE && (j == jp || j == jd))) continue;
       E dot{0u, 0u};
       SDIMB_P_LOOP
       for (int w = 0; w < nw; ++w) {
@@ -339,8 +380,13 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
         ph = add4(ph, E{(ps & 1u) ? f.l : 0u, (ps & 2u) ? f.l : 0u});
         ph.h ^= dot.l & f.l;
       }
+      if (MERGE) {
+        if (j == jd) ph = setbit2(ph, bp, ps);
+        if (j == jp) ph = setbit2(ph, bp, (ORDER - draw * PO) % ORDER);
+      }
       G.stp(j, ph);
     }
+    if (!MERGE) {
     cta_sync<FW>();
     // destabilizer p <- old pivot; stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333).
     // Only rows where something changes are touched: the support (list ar) and stale destabilizer rows (br).
@@ -365,9 +411,12 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
       dd.z = setbit2(dd.z, bp, 0u);
       G.st(r, jd, dd);
     }
+    }
     outcome = draw;        // replayed or Philox, resolved when the op was fetched (reference: random.choice, :332)
-    if (tid == 0) G.setp(np + piv, ps);
-    if (tid == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
+    if (!MERGE) {
+      if (tid == 0) G.setp(np + piv, ps);
+      if (tid == 1) G.setp(piv, (ORDER - outcome * PO) % ORDER);
+    }
     rec = outcome;
   } else {
     // ---- deterministic branch (tableau_prime.py:336-363) ----
@@ -454,14 +503,22 @@ __device__ uint32_t p_measure(Geo<D> G, const KParams& p, PScratch& S, int q, in
 #ifndef SDIMB_PG_SHFLOPS        // global image: staged ops broadcast by shuffle instead of a shared-memory round trip
 #define SDIMB_PG_SHFLOPS 1
 #endif
-template <int D, bool GLOBAL>
+// IL: global image with interleaved entries and merged measurement passes (Geo, p_measure MERGE) — what sdimb_run
+// launches for tableaus of SDIMB_PG_IL_MIN_NP padded qudits and more (round-2 A/B, profiles/r2_ab_measurement.json:
+// d = 3 n = 500 18.0 -> 13.3 ms, d = 2 n = 400 19.6 -> 19.0 ms, but d = 3 n = 256 19.8 -> 20.8 ms, so the headline
+// shape keeps the plain image).
+#ifndef SDIMB_PG_IL_MIN_NP
+#define SDIMB_PG_IL_MIN_NP 384
+#endif
+template <int D, bool GLOBAL, bool IL = false>
 __global__ void __launch_bounds__(32 * SDIMB_SCHED_WARPS, GLOBAL ? SDIMB_PLANES_GLOBAL_MIN_CTAS : 0)
 interp_planes_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
+  static_assert(GLOBAL || !IL, "the interleaved image exists for the global placement only");
   constexpr bool FW = GLOBAL && SDIMB_PG_COMPACT != 0;     // the CTA is known to have four warps: barriers without the test
   constexpr bool CP = FW || (!GLOBAL && SDIMB_PR_COMPACT != 0);   // compact dispatch form (see COMPACT above)
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  Geo<D> G;
+  Geo<D, IL> G;
   PScratch S;
   uint32_t* sm = reinterpret_cast<uint32_t*>(smem);
 #if SDIMB_PG_HOSTGEO
@@ -500,7 +557,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
   G.Wb = 2 * G.np / 32;
   // the padding entry keeps shared-memory column walks off one bank; a global image may drop it so that rows start on
   // sector (n = 256, d = 3: cache-line) boundaries — its slab keeps the padded size either way
-  G.RS = Geo<D>::EW * (G.Wb + ((GLOBAL && SDIMB_PG_NOPAD != 0) ? 0 : 1));
+  G.RS = Geo<D>::EW * (G.Wb + ((IL || (GLOBAL && SDIMB_PG_NOPAD != 0)) ? 0 : 1));
   G.gpw = (G.Wb <= 32 && (32 % G.Wb) == 0) ? 32 / G.Wb : 1;
   G.gsub = G.gpw > 1 ? lane / G.Wb : 0;
   G.j0 = G.gpw > 1 ? lane % G.Wb : lane;
@@ -641,7 +698,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
           case SDIMB_OP_M:                                                                                              \
           case SDIMB_OP_RESET: {                                                                                        \
             const bool fold = dirty || (gate_pos & ((1u << k) - 1u)) != 0;   /* gates since the last measurement? */   \
-            const uint32_t m = p_measure<D, FW>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);                  \
+            const uint32_t m = p_measure<D, FW, IL>(G, p, S, op.y, op.w, shot, fold, (uint32_t)op.z);              \
             dirty = false;                                                                                              \
             if (op.x == SDIMB_OP_RESET) {                                                                               \
               if (m && warp == 0) NS::g_pauli<D>(G, op.y, D - m, 0u);   /* program.py:335-339 */                     \

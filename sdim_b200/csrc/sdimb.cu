@@ -97,12 +97,25 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
   return (fits && !(flags & SDIMB_FORCE_GLOBAL)) ? 1 : 0;
 }
 
+// The global-image plane interpreter for (d, interleaved image or not): see SDIMB_PG_IL_MIN_NP in planes.cuh.
+// The environment variable of the same name moves the threshold (tests run the goldens through both images).
+bool planes_interleaved(int n) {
+  int min_np = SDIMB_PG_IL_MIN_NP;
+  if (const char* env = std::getenv("SDIMB_PG_IL_MIN_NP")) min_np = std::atoi(env);
+  return (n + 31) / 32 * 32 >= min_np;
+}
+using PlaneKernel = void (*)(const KParams);
+PlaneKernel planes_global_kernel(int d, bool il) {
+  if (il) return (d == 2) ? planes::interp_planes_kernel<2, true, true> : planes::interp_planes_kernel<3, true, true>;
+  return (d == 2) ? planes::interp_planes_kernel<2, true, false> : planes::interp_planes_kernel<3, true, false>;
+}
+
 // CTAs of the bit-plane interpreter on a global image that the current device keeps resident (its grid never
 // exceeds this), and the shared memory one of them needs.
 int planes_global_ctas(int n, int d, size_t* smem_out) {
   const size_t smem = planes::planes_scratch_bytes(n, SDIMB_SCHED_WARPS);
   if (smem_out) *smem_out = smem;
-  auto kern = (d == 2) ? planes::interp_planes_kernel<2, true> : planes::interp_planes_kernel<3, true>;
+  auto kern = planes_global_kernel(d, planes_interleaved(n));
   int dev = 0, sms = 0, per_sm = 0;
   // The image is read through L1: ask for no more shared memory per SM than the CTAs the register file admits need
   // (headline: 20 % instead of the driver's choice, +1 %; a full carve-out, as a co-resident shared-memory kernel
@@ -280,7 +293,7 @@ int sdimb_run(const SdimbRunArgs* a) {
     int64_t grid = (a->scratch_bytes - 256) / (int64_t)slab;
     if (grid > max_ctas) grid = max_ctas;
     if (grid > a->shots) grid = a->shots;
-    auto kern = (a->d == 2) ? planes::interp_planes_kernel<2, true> : planes::interp_planes_kernel<3, true>;
+    auto kern = planes_global_kernel(a->d, planes_interleaved(a->n));
     p.shot_counter = (unsigned int*)a->scratch;
     p.plane_slab = (uint32_t*)((uint8_t*)a->scratch + 256);
     p.pg = planes::make_plane_geo(a->n, a->d, SDIMB_SCHED_WARPS, true);

@@ -315,6 +315,56 @@ def test_planes_on_a_global_image_beyond_the_shared_memory_limit(d, n, depth):
     assert np.array_equal(eng.run(shots, 0, seed).cpu().numpy(), want)      # auto: planes, or clusters for few shots
 
 
+@pytest.mark.parametrize("min_np", ["0", "100000"])
+def test_both_global_images_on_the_reference_goldens(golden_random, golden_config_sizes, monkeypatch, min_np):
+    """The global-image plane interpreter exists twice: plain rows (the headline shape) and the interleaved image with
+    merged measurement passes that sdimb_run picks for np >= 384.  SDIMB_PG_IL_MIN_NP = 0 / huge forces every
+    planes-global run through one of them: reference goldens (all d = 2, 3 cases incl. the config sizes), records and
+    all six final arrays."""
+    import torch
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    monkeypatch.setenv("SDIMB_PG_IL_MIN_NP", min_np)
+    cases = [(c["n"], c["d"], c["ops"], np.array(c["noise_ab"], dtype=np.uint8).reshape(-1, 2),
+              np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in c["records"]], dtype=np.uint8),
+              {k: np.array(v) for k, v in c["final"].items()}) for c in golden_random if c["d"] <= 3]
+    cases += [(c["n"], c["d"], c["ops"], c["noise_ab"],
+               np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in c["records"]], dtype=np.uint8), c["final"])
+              for c in golden_config_sizes]
+    assert len(cases) >= 40
+    for n, d, ops, noise, want, final in cases:
+        prog = compile_circuits([circuit_from_ops(n, d, ops)])
+        eng = TableauEngine(prog)
+        shots = 3
+        rm = torch.from_numpy(np.tile((want & 0x7F)[None, :], (shots, 1)))
+        rn = torch.from_numpy(np.tile(noise[None], (shots, 1, 1))) if prog.n_noise else None
+        got = eng.run(shots, 0, 5, rm, rn, keep_tableau=True, mode="planes-global").cpu().numpy()
+        assert all(np.array_equal(got[s], want) for s in range(shots)), (n, d, min_np)
+        arrs = eng.export(eng.tableau, shots - 1)
+        for key in ("x", "z", "p", "dx", "dz", "dp"):
+            assert np.array_equal(arrs[key], final[key]), (n, d, key, min_np)
+
+
+@pytest.mark.parametrize("d,n,depth", [(2, 33, 900), (3, 97, 2500), (3, 256, 4000), (2, 700, 6000), (3, 450, 5000)])
+def test_interleaved_image_matches_c_oracle_free_running(monkeypatch, d, n, depth):
+    """Interleaved image forced at every size: all opcodes incl. M_X / RESET / SWAP and the three noise channels,
+    ragged n, Philox draws; records of all shots and the final tableau vs the C oracle."""
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine
+    monkeypatch.setenv("SDIMB_PG_IL_MIN_NP", "0")
+    prog = random_program(seed=700 * d + n, n=n, d=d, depth=depth)
+    eng = TableauEngine(prog)
+    shots, seed = 40, 77
+    got = eng.run(shots, 0, seed, keep_tableau=True, mode="planes-global").cpu().numpy()
+    want, fin = c_oracle.run(n, d, prog.ops, shots, 0, seed, thresh24=prog.noise_thresh24,
+                             channel=prog.noise_channel, want_final=True)
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, shots - 1)
+    for key in ("x", "z", "p", "dx", "dz", "dp"):
+        assert np.array_equal(arrs[key], fin[key]), key
+
+
 def test_planes_continue_from_store_and_stepped():
     """!FRESH path of the plane kernel (pack from / unpack to the uint8 store): op-by-op stepping on a persistent
     store gives the same records and final tableau as one fused launch."""
