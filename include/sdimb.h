@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SDIMB_VERSION 1
+#define SDIMB_VERSION 2
 
 enum {
   SDIMB_OK = 0,
@@ -63,6 +63,13 @@ enum {
  * executes the op inside its layer (index in the layer mod SDIMB_SCHED_WARPS) and bits 16..30 the index in the
  * layer itself (mod 2^15; the cluster interpreter deals layers over its own number of gate groups); bits 0..7
  * are the opcode.  An unscheduled stream has those bits 0. */
+/* On an M op bits 8..15 carry the marks of a measurement RUN instead (sdimb_schedule: consecutive M ops with no
+ * other op between): the bit-plane interpreter on a global image may execute such a run on a generator-major copy
+ * of its image (sdim_b200/csrc/planes_gm.cuh); every other interpreter ignores them. */
+#define SDIMB_GM_IN 1      /* this M belongs to a marked run */
+#define SDIMB_GM_FIRST 2   /* first M of the run */
+#define SDIMB_GM_LAST 4    /* last M of the run */
+#define SDIMB_GM_FOLLOW 8  /* (with LAST) the stream has further ops behind the run */
 #define SDIMB_OP_MASK 0xFF
 #define SDIMB_OP_WARP_SHIFT 8
 #define SDIMB_OP_INDEX_SHIFT 16
@@ -119,6 +126,11 @@ typedef struct SdimbRunArgs {
   void* stream;
   void* scratch;                 /* [device] nullable, sdimb_scratch_bytes() bytes: shot counter of the bit-plane */
   int64_t scratch_bytes;         /* interpreter (CTAs then claim shots dynamically instead of grid-striding)      */
+  int64_t tail_run_len;          /* sdimb_tail_run(ops) of a SCHEDULED stream, or 0: the last tail_run_len ops are a marked
+                                    run of M ops.  With scratch of sdimb_scratch_bytes_shots(.., shots) bytes and no
+                                    WRITEBACK the global-image bit-plane interpreter hands that run to a second kernel
+                                    (one warp per shot on a generator-major image, sdim_b200/csrc/planes_gm.cuh).
+                                    Callers built against the struct without this field are accepted (struct_size). */
 } SdimbRunArgs;
 
 int sdimb_version(void);
@@ -190,6 +202,14 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
  * grid-striding.  Global-image interpreter (d = 2, 3 beyond the shared-memory limit; REQUIRED): the counter plus
  * one bit-plane image per CTA the current device keeps resident. */
 int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags);
+
+/* Scratch for a call over `shots` shots whose stream ends in a marked measurement run (SdimbRunArgs.tail_run_len > 0):
+ * at least sdimb_scratch_bytes(); for the global-image bit-plane interpreter with n <= 512 additionally one image per
+ * shot plus the second kernel's slabs.  shots = 0 gives sdimb_scratch_bytes(). */
+int64_t sdimb_scratch_bytes_shots(int n, int d, uint32_t flags, int64_t shots);
+
+/* Length of the marked run of M ops (SDIMB_GM_*) that ends a scheduled HOST stream, 0 if it does not end in one. */
+int64_t sdimb_tail_run(const int32_t* ops, int64_t n_ops);
 
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store (one CTA or
  * one thread-block cluster per shot, chosen per call from n and shots), 1 uint8 lanes resident in shared memory,

@@ -14,7 +14,8 @@ KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident", 3:
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
-                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes", "sdimb_cluster_size")
+                    "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes", "sdimb_cluster_size",
+                    "sdimb_scratch_bytes_shots", "sdimb_tail_run")
 
 
 class SdimbLayout(C.Structure):
@@ -29,7 +30,8 @@ class SdimbRunArgs(C.Structure):
                 ("ops", C.c_void_p), ("n_ops", C.c_int64), ("records", C.c_void_p), ("n_meas", C.c_int64),
                 ("rec_stride", C.c_int64), ("replay_meas", C.c_void_p), ("replay_noise", C.c_void_p),
                 ("noise_thresh24", C.c_void_p), ("noise_channel", C.c_void_p), ("n_noise", C.c_int64),
-                ("seed", C.c_uint64), ("stream", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
+                ("seed", C.c_uint64), ("stream", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
+                ("tail_run_len", C.c_int64)]
 
 
 class NativeError(RuntimeError):
@@ -68,6 +70,10 @@ def lib() -> C.CDLL:
                                C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]
     L.sdimb_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_uint32]
     L.sdimb_scratch_bytes.restype = C.c_int64
+    L.sdimb_scratch_bytes_shots.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int64]
+    L.sdimb_scratch_bytes_shots.restype = C.c_int64
+    L.sdimb_tail_run.argtypes = [C.c_void_p, C.c_int64]
+    L.sdimb_tail_run.restype = C.c_int64
     L.sdimb_cluster_size.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint32]
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
@@ -106,3 +112,10 @@ def schedule(n: int, ops):
     check(lib().sdimb_schedule(n, ops.ctypes.data if ops.size else None, ops.shape[0], out.ctypes.data,
                                out.shape[0], C.byref(count)))
     return out[: count.value].copy()
+
+
+def tail_run(sched) -> int:
+    """Length of the marked run of M ops that ends a scheduled stream (sdimb_tail_run), 0 if there is none."""
+    import numpy as np
+    sched = np.ascontiguousarray(sched, dtype=np.int32).reshape(-1, 4)
+    return int(lib().sdimb_tail_run(sched.ctypes.data if sched.size else None, sched.shape[0]))

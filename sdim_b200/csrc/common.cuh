@@ -90,4 +90,12 @@ struct KParams {
   int wpc;                     // cluster interpreter: lane words owned by each CTA of the cluster
   uint32_t* plane_slab;        // bit-plane interpreter on a global image: gridDim slabs of planes_row_bytes each
   PlaneGeo pg;                 // bit-plane interpreter: host-computed geometry (constant-bank operands instead of per-use arithmetic)
+  // trailing measurement run on a generator-major image (planes_gm.cuh): the interpreter keeps the image of shot s at
+  // plane_slab + s * img_stride_words (phase planes behind the rows) instead of one slab per CTA, run_tail_kernel
+  // picks it up there
+  int img_per_shot;
+  int64_t img_stride_words;
+  int64_t tail_start;          // run_tail_kernel: index of the first op of the run (ops [tail_start, n_ops) are M ops)
+  uint32_t* gm_slab;           // run_tail_kernel: one B + QX slab per resident warp
+  int64_t gm_slab_words;
 };

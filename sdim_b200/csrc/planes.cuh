@@ -593,6 +593,7 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
     cta_sync<FW>();
     const int64_t shot = S.next[round & 1];
     if (shot >= p.shots) break;
+    if (GLOBAL && p.img_per_shot) G.tab = p.plane_slab + shot * p.img_stride_words;   // the image outlives this kernel
     // ---- load: |0...0> or pack from the uint8 store ----
     SDIMB_P_LOOP
     for (int i = tid; i < row_words; i += nt) G.tab[i] = 0u;
@@ -751,6 +752,18 @@ interp_planes_kernel(const __grid_constant__ KParams p) {
       dirty = dirty || gate_pos != 0;      // conservative: gates of this batch behind its last measurement
     }
     cta_sync<FW>();
+    if (GLOBAL && p.img_per_shot) {       // folded phase planes behind the rows, for run_tail_kernel
+      uint2* const out = reinterpret_cast<uint2*>(G.tab + row_words);
+      for (int j = tid; j < G.Wb; j += nt) {
+        uint2 o = G.phase_of(0)[j];
+        E acc{o.x, o.y};
+        for (int w = 1; w < nw; ++w) {
+          o = G.phase_of(w)[j];
+          acc = (D == 3) ? add3(acc, E{o.x, o.y}) : add4(acc, E{o.x, o.y});
+        }
+        out[j] = make_uint2(acc.l, acc.h);
+      }
+    }
     if (p.flags & SDIMB_WRITEBACK) {      // fold the accumulators, then unpack into the uint8 store
       G.pacc = G.phase_of(0);
       for (int j = tid; j < G.Wb && nw > 1; j += nt) {
@@ -819,5 +832,12 @@ inline size_t planes_scratch_bytes(int n, int nw) {
 inline size_t planes_smem_bytes(int n, int d, int nw = SDIMB_SCHED_WARPS) {
   return planes_row_bytes(n, d) + planes_scratch_bytes(n, nw);
 }
+// words between the per-shot images of a run that hands its tail to run_tail_kernel: rows, then Wb phase entries
+inline size_t planes_img_stride_words(int n, int d) {
+  const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32;
+  return (planes_row_bytes(n, d) / 4 + 2 * Wb + 7) & ~(size_t)7;
+}
+
+#include "planes_gm.cuh"
 
 }  // namespace planes

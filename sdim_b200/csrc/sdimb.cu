@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -132,6 +133,35 @@ int planes_global_ctas(int n, int d, size_t* smem_out) {
   return sms * per_sm;
 }
 
+// Trailing measurement run on a generator-major image (planes_gm.cuh): kernel, resident CTAs, scratch layout.
+PlaneKernel run_tail_kernel_for(int d, bool il) {
+  if (il) return (d == 2) ? planes::run_tail_kernel<2, true> : planes::run_tail_kernel<3, true>;
+  return (d == 2) ? planes::run_tail_kernel<2, false> : planes::run_tail_kernel<3, false>;
+}
+bool tail_run_shape_ok(int n, int d) { return (d == 2 || d == 3) && (n + 31) / 32 * 32 <= 512; }   // Wb <= 32
+int run_tail_ctas(int n, int d) {
+  auto kern = run_tail_kernel_for(d, planes_interleaved(n));
+  const size_t smem = planes::run_smem_bytes(n);
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * planes::kRunWarps, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (const char* env = std::getenv("SDIMB_RUN_CTAS_PER_SM")) {     // developer knob (A/B timings)
+    const int m = std::atoi(env);
+    if (m >= 1 && m < per_sm) per_sm = m;
+  }
+  return sms * per_sm;
+}
+// scratch of a call that hands its tail run to run_tail_kernel: 256 bytes of counters, one image per SHOT, one
+// B + QX slab per resident warp of run_tail_kernel
+size_t tail_run_scratch_bytes(int n, int d, int64_t shots, int run_ctas) {
+  return 256 + (size_t)shots * 4 * planes::planes_img_stride_words(n, d) +
+         (size_t)run_ctas * planes::kRunWarps * 4 * planes::run_slab_words(n, d);
+}
+
 // Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
 // one CTA per shot.  By default only tableaus with rows wider than one 256-thread CTA (n > 512), and the largest
 // cluster size (16 = the non-portable maximum, then 8, 4, 2) of which the GPU can keep one per shot resident at the
@@ -231,8 +261,15 @@ int sdimb_init(void* tableau, int n, int d, int64_t shots, void* stream) {
   return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
 }
 
-int sdimb_run(const SdimbRunArgs* a) {
-  if (!a || a->struct_size != sizeof(SdimbRunArgs)) return SDIMB_EINVAL;
+int sdimb_run(const SdimbRunArgs* caller) {
+  // version 1 callers pass the struct without its last field (tail_run_len)
+  if (!caller || (caller->struct_size != sizeof(SdimbRunArgs) && caller->struct_size != offsetof(SdimbRunArgs, tail_run_len)))
+    return SDIMB_EINVAL;
+  SdimbRunArgs args;
+  std::memset(&args, 0, sizeof(args));
+  std::memcpy(&args, caller, caller->struct_size);
+  args.struct_size = sizeof(SdimbRunArgs);
+  const SdimbRunArgs* a = &args;
   SdimbLayout L;
   const int rc = sdimb_layout(a->n, a->d, &L);
   if (rc) return rc;
@@ -297,6 +334,33 @@ int sdimb_run(const SdimbRunArgs* a) {
     p.shot_counter = (unsigned int*)a->scratch;
     p.plane_slab = (uint32_t*)((uint8_t*)a->scratch + 256);
     p.pg = planes::make_plane_geo(a->n, a->d, SDIMB_SCHED_WARPS, true);
+    // The run of M ops that ends the stream goes to run_tail_kernel (one warp per shot on a generator-major image)
+    // when the caller says where it starts, does not want the tableau back and brought scratch for one image per shot.
+    const int64_t tail = (a->flags & SDIMB_SCHEDULED) && !(a->flags & SDIMB_WRITEBACK) && tail_run_shape_ok(a->n, a->d) &&
+                                 a->tail_run_len > 0 && a->tail_run_len <= a->n_ops ? a->tail_run_len : 0;
+    const int run_ctas_max = tail ? run_tail_ctas(a->n, a->d) : 0;
+    if (tail && run_ctas_max >= 1 && a->scratch_bytes >= (int64_t)tail_run_scratch_bytes(a->n, a->d, a->shots, run_ctas_max)) {
+      if (cudaMemsetAsync(a->scratch, 0, 256, (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
+      p.img_per_shot = 1;
+      p.img_stride_words = (int64_t)planes::planes_img_stride_words(a->n, a->d);
+      KParams p1 = p;
+      p1.n_ops = a->n_ops - tail;
+      int64_t grid1 = max_ctas < a->shots ? max_ctas : a->shots;
+      kern<<<(unsigned)grid1, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p1);
+      g_launches++;
+      if (cudaGetLastError() != cudaSuccess) return SDIMB_ECUDA;
+      KParams p2 = p;
+      p2.tail_start = a->n_ops - tail;
+      p2.shot_counter = (unsigned int*)a->scratch + 1;
+      p2.gm_slab = p.plane_slab + (int64_t)a->shots * p.img_stride_words;
+      p2.gm_slab_words = (int64_t)planes::run_slab_words(a->n, a->d);
+      int64_t grid2 = (a->shots + planes::kRunWarps - 1) / planes::kRunWarps;
+      if (grid2 > run_ctas_max) grid2 = run_ctas_max;
+      auto kern2 = run_tail_kernel_for(a->d, planes_interleaved(a->n));
+      kern2<<<(unsigned)grid2, 32 * planes::kRunWarps, planes::run_smem_bytes(a->n), (cudaStream_t)a->stream>>>(p2);
+      g_launches++;
+      return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+    }
     if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
     kern<<<(unsigned)grid, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p);
     g_launches++;
@@ -500,7 +564,8 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_th = (n_noise && noise_thresh24) ? align256((size_t)n_noise * 4) : 0;
   const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
   const size_t b_tab = kernel == 0 ? align256((size_t)shots * L.shot_bytes) : 0;
-  const size_t b_scr = align256((size_t)sdimb_scratch_bytes(n, d, mode_flags));
+  const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
+  const size_t b_scr = align256((size_t)sdimb_scratch_bytes_shots(n, d, mode_flags, tail_len ? shots : 0));
   const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_scr + 256;
 
   int cur_dev = 0;
@@ -538,6 +603,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     a.noise_thresh24 = (const uint32_t*)d_th; a.noise_channel = d_ch; a.n_noise = n_noise;
     a.seed = seed; a.stream = st;
     a.scratch = d_scr; a.scratch_bytes = (int64_t)b_scr;
+    a.tail_run_len = tail_len;
     rc = sdimb_run(&a);
     if (rc) break;
     rc = SDIMB_ECUDA;
@@ -585,6 +651,36 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
   std::vector<int> lw(n, 0), lr(n, 0);
   std::vector<std::vector<int64_t>> layers;
   int64_t w = 0;
+  // Runs of consecutive M ops (nothing but I / BARRIER between them) of at least min_run measurements are marked
+  // SDIMB_GM_*: the global-image bit-plane interpreter runs them on a generator-major copy of its image, which costs
+  // two transpositions (~n^2 / 8 bits each way) and saves a column walk over n rows per measurement.
+  int64_t min_run = n / 8 > 4 ? n / 8 : 4;
+  if (const char* env = std::getenv("SDIMB_GM_MIN_RUN")) min_run = std::atoll(env) > 2 ? std::atoll(env) : 2;
+  std::vector<uint8_t> gm_mark(n_ops, 0);
+  {
+    int64_t run_first = -1, run_last = -1, run_len = 0;
+    auto close_run = [&](bool follow) {
+      if (run_len >= min_run) {
+        for (int64_t i = run_first; i <= run_last; ++i)
+          if ((ops[4 * i] & SDIMB_OP_MASK) == SDIMB_OP_M) gm_mark[i] = SDIMB_GM_IN;
+        gm_mark[run_first] |= SDIMB_GM_FIRST;
+        gm_mark[run_last] |= SDIMB_GM_LAST | (follow ? SDIMB_GM_FOLLOW : 0);
+      }
+      run_len = 0;
+    };
+    for (int64_t i = 0; i < n_ops; ++i) {
+      const int op = ops[4 * i] & SDIMB_OP_MASK;
+      if (op == SDIMB_OP_I || op == SDIMB_OP_BARRIER) continue;
+      if (op == SDIMB_OP_M) {
+        if (run_len == 0) run_first = i;
+        run_last = i;
+        ++run_len;
+      } else {
+        close_run(true);
+      }
+    }
+    close_run(false);
+  }
   auto flush = [&]() {
     for (auto& layer : layers) {
       if (layer.empty()) continue;
@@ -617,7 +713,7 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
     if (op >= SDIMB_OP_M && op <= SDIMB_OP_RESET) {     // collective: everything before it completes first
       flush();
       int32_t* r = out + 4 * w++;
-      r[0] = op; r[1] = a; r[2] = -1; r[3] = o[3];
+      r[0] = op | ((int32_t)gm_mark[i] << SDIMB_OP_WARP_SHIFT); r[1] = a; r[2] = -1; r[3] = o[3];
       continue;
     }
     const bool two = op >= SDIMB_OP_CNOT && op <= SDIMB_OP_SWAP;
@@ -677,6 +773,29 @@ int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags) {
     int ctas = planes_global_ctas(n, d, nullptr);
     if (ctas < 1) ctas = 148 * 8;
     return 256 + (int64_t)ctas * (int64_t)planes::planes_row_bytes(n, d);
+  }
+  return 0;
+}
+
+int64_t sdimb_scratch_bytes_shots(int n, int d, uint32_t flags, int64_t shots) {
+  const int64_t base = sdimb_scratch_bytes(n, d, flags);
+  SdimbLayout L;
+  if (shots <= 0 || sdimb_layout(n, d, &L) || plan_kernel(n, d, flags, L.np) != 3 || !tail_run_shape_ok(n, d)) return base;
+  int ctas = run_tail_ctas(n, d);
+  if (ctas < 1) ctas = 148 * planes::kRunCtasPerSm;
+  const int64_t need = (int64_t)tail_run_scratch_bytes(n, d, shots, ctas);
+  return need > base ? need : base;
+}
+
+int64_t sdimb_tail_run(const int32_t* ops, int64_t n_ops) {
+  if (!ops || n_ops < 1) return 0;
+  auto mark = [&](int64_t i) { return (ops[4 * i] >> SDIMB_OP_WARP_SHIFT) & 0xFF; };
+  auto code = [&](int64_t i) { return ops[4 * i] & SDIMB_OP_MASK; };
+  const int64_t last = n_ops - 1;
+  if (code(last) != SDIMB_OP_M || !(mark(last) & SDIMB_GM_LAST) || (mark(last) & SDIMB_GM_FOLLOW)) return 0;
+  for (int64_t i = last; i >= 0; --i) {
+    if (code(i) != SDIMB_OP_M || !(mark(i) & SDIMB_GM_IN)) return 0;
+    if (mark(i) & SDIMB_GM_FIRST) return n_ops - i;
   }
   return 0;
 }

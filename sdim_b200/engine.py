@@ -50,7 +50,10 @@ class TableauEngine:
         dev = self.device
         self.ops = torch.from_numpy(np.ascontiguousarray(prog.ops)).to(dev)
         # layered stream for the multi-warp bit-plane interpreter (same ops, commuting reorder + barriers)
-        self.ops_sched = torch.from_numpy(N.schedule(prog.num_qudits, prog.ops)).to(dev) if prog.n_ops else None
+        sched = N.schedule(prog.num_qudits, prog.ops) if prog.n_ops else None
+        self.ops_sched = torch.from_numpy(sched).to(dev) if prog.n_ops else None
+        # the run of M ops that ends the stream ("measure every qudit"): the library may hand it to a second kernel
+        self.tail_run_len = N.tail_run(sched) if prog.n_ops else 0
         self.noise_thresh = torch.from_numpy(prog.noise_thresh24.astype(np.int64)).to(dev).to(torch.int32) \
             if prog.n_noise else None
         if prog.n_noise:
@@ -59,7 +62,7 @@ class TableauEngine:
         else:
             self.noise_channel = None
         self._planes_fit: Optional[bool] = None          # do the bit planes of one shot fit in shared memory?
-        self._scratch: Dict[int, torch.Tensor] = {}     # per mode flags: counter + overflow slabs of the plane kernel
+        self._scratch: Dict[tuple, torch.Tensor] = {}   # per (mode flags, tail-run shots): counter, images, slabs
         self.tableau: Optional[torch.Tensor] = None     # uint8 [shots, shot_bytes] of the last run that kept it
         self.tableau_shots = 0
 
@@ -92,11 +95,14 @@ class TableauEngine:
         with torch.cuda.device(self.device):
             return int(self.lib.sdimb_cluster_size(self.prog.num_qudits, self.prog.dimension, shots, self.MODES[mode]))
 
-    def _scratch_for(self, mode_flags: int) -> Optional[torch.Tensor]:
-        if mode_flags not in self._scratch:
-            nbytes = int(self.lib.sdimb_scratch_bytes(self.prog.num_qudits, self.prog.dimension, mode_flags))
-            self._scratch[mode_flags] = torch.empty(nbytes, dtype=torch.uint8, device=self.device) if nbytes else None
-        return self._scratch[mode_flags]
+    def _scratch_for(self, mode_flags: int, shots: int = 0) -> Optional[torch.Tensor]:
+        """Scratch of the plane kernels; `shots` > 0: room for one image per shot (tail run in a second kernel)."""
+        have = self._scratch.get(mode_flags)
+        nbytes = int(self.lib.sdimb_scratch_bytes_shots(self.prog.num_qudits, self.prog.dimension, mode_flags, shots))
+        if have is None or have.numel() < nbytes:
+            have = torch.empty(nbytes, dtype=torch.uint8, device=self.device) if nbytes else None
+            self._scratch[mode_flags] = have
+        return have
 
     def fits_resident(self, mode: Optional[str] = None) -> bool:
         return not self.plan(mode)[1]
@@ -169,8 +175,10 @@ class TableauEngine:
             a.n_noise = prog.n_noise
             a.seed = seed & 0xFFFFFFFFFFFFFFFF
             a.stream = torch.cuda.current_stream(dev).cuda_stream
-            scratch = self._scratch_for(self.MODES[mode])
+            tail = self.tail_run_len if (use_sched and not keep_tableau) else 0
+            scratch = self._scratch_for(self.MODES[mode], shots if tail else 0)
             a.scratch, a.scratch_bytes = _ptr(scratch), (scratch.numel() if scratch is not None else 0)
+            a.tail_run_len = tail
             N.check(self.lib.sdimb_run(C.byref(a)))
         if keep_tableau:
             self.tableau, self.tableau_shots = tableau, shots

@@ -8,12 +8,14 @@ ONE = ["I", "X", "X_INV", "Z", "Z_INV", "H", "H_INV", "P", "P_INV"]
 TWO = ["CNOT", "CNOT_INV", "CZ", "CZ_INV", "SWAP"]
 
 
-def random_circuit(seed, n, d, depth, p_meas=0.08, p_noise=0.1, final_measure=True, noise_prob=None):
+def random_circuit(seed, n, d, depth, p_meas=0.08, p_noise=0.1, final_measure=True, noise_prob=None, p_burst=0.0):
     rng = random.Random(seed)
     c = Circuit(n, d)
     for _ in range(depth):
         u = rng.random()
-        if u < p_meas:
+        if p_burst and rng.random() < p_burst:        # a run of plain M ops on a random subset, mid-circuit
+            c.add_gate("M", rng.sample(range(n), rng.randint(2, n)))
+        elif u < p_meas:
             c.add_gate(rng.choice(["M", "M", "M_X", "RESET"]), rng.randrange(n))
         elif u < p_meas + p_noise:
             prob = noise_prob if noise_prob is not None else rng.choice([0.05, 0.3, 0.9, 1.0])

@@ -365,6 +365,69 @@ def test_interleaved_image_matches_c_oracle_free_running(monkeypatch, d, n, dept
         assert np.array_equal(arrs[key], fin[key]), key
 
 
+def _launches():
+    from sdim_b200 import _native as N
+    return int(N.lib().sdimb_launch_count())
+
+
+@pytest.mark.parametrize("min_run", ["2", "1000000"])
+def test_tail_run_kernel_on_the_reference_goldens(golden_random, golden_config_sizes, monkeypatch, min_run):
+    """The run of M ops that ends a stream executes in run_tail_kernel (one warp per shot on a generator-major copy
+    of the image, planes_gm.cuh) when it is at least SDIMB_GM_MIN_RUN long and the tableau is not kept.  2 sends the
+    tail of every reference golden there (d = 2, 3, incl. the config sizes), a huge value none: the records must equal
+    the reference's either way, and the launch count tells which path ran."""
+    import torch
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    monkeypatch.setenv("SDIMB_GM_MIN_RUN", min_run)
+    cases = [(c["n"], c["d"], c["ops"], np.array(c["noise_ab"], dtype=np.uint8).reshape(-1, 2),
+              np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in c["records"]], dtype=np.uint8))
+             for c in golden_random if c["d"] <= 3]
+    cases += [(c["n"], c["d"], c["ops"], c["noise_ab"],
+               np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in c["records"]], dtype=np.uint8))
+              for c in golden_config_sizes]
+    two_kernels = 0
+    for n, d, ops, noise, want in cases:
+        prog = compile_circuits([circuit_from_ops(n, d, ops)])
+        eng = TableauEngine(prog)
+        shots = 37
+        rm = torch.from_numpy(np.tile((want & 0x7F)[None, :], (shots, 1)))
+        rn = torch.from_numpy(np.tile(noise[None], (shots, 1, 1))) if prog.n_noise else None
+        before = _launches()
+        got = eng.run(shots, 0, 5, rm, rn, mode="planes-global").cpu().numpy()
+        two_kernels += int(_launches() - before == 2)
+        assert (_launches() - before == 2) == (eng.tail_run_len > 0)
+        assert all(np.array_equal(got[s], want) for s in range(shots)), (n, d, min_run)
+    assert (two_kernels >= 20) if min_run == "2" else (two_kernels == 0)
+
+
+@pytest.mark.parametrize("il", ["0", "100000"])
+@pytest.mark.parametrize("d,n,depth", [(2, 33, 900), (3, 97, 2500), (3, 256, 3000), (2, 300, 3000), (3, 500, 3000),
+                                       (2, 512, 2500), (3, 17, 600), (3, 1, 40), (2, 2, 60)])
+def test_tail_run_kernel_matches_c_oracle_free_running(monkeypatch, d, n, depth, il):
+    """All opcodes incl. mid-circuit M / M_X / RESET and the three noise channels in front of the final all-qudit
+    measurement, ragged n up to the 512-qudit limit of the generator-major path, both global images, Philox draws,
+    more shots than one wave of warps: the records of every shot vs the C oracle; the same records without the
+    second kernel (tableau kept) and from the host-buffer entry."""
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine, simulate_host
+    monkeypatch.setenv("SDIMB_GM_MIN_RUN", "2")
+    monkeypatch.setenv("SDIMB_PG_IL_MIN_NP", il)
+    prog = random_program(seed=900 * d + n, n=n, d=d, depth=depth)
+    eng = TableauEngine(prog)
+    assert eng.tail_run_len >= n or n < 2          # a single M is not a run
+    shots, seed = (5000 if n <= 97 else 300), 78
+    before = _launches()
+    got = eng.run(shots, 3, seed, mode="planes-global").cpu().numpy()
+    assert _launches() - before == (2 if eng.tail_run_len else 1)
+    want, _ = c_oracle.run(n, d, prog.ops, shots, 3, seed, thresh24=prog.noise_thresh24, channel=prog.noise_channel)
+    assert np.array_equal(got, want)
+    assert np.array_equal(eng.run(64, 3, seed, keep_tableau=True, mode="planes-global").cpu().numpy(), want[:64])
+    rec, _ = simulate_host(prog, 64, 3, seed, mode="planes-global")
+    assert np.array_equal(rec, want[:64])
+
+
 def test_planes_continue_from_store_and_stepped():
     """!FRESH path of the plane kernel (pack from / unpack to the uint8 store): op-by-op stepping on a persistent
     store gives the same records and final tableau as one fused launch."""

@@ -36,8 +36,26 @@ def test_schedule_structure_and_equivalence(d, n, depth):
     a = sorted(map(tuple, np.column_stack((ops_only[:, 0] & 0xFF, ops_only[:, 1:])).tolist()))
     b = sorted(map(tuple, prog.ops.tolist()))
     assert a == b
-    coll = [tuple(r) for r in ops_only.tolist() if (r[0] & 0xFF) in (14, 15, 16)]
+    coll = [(r[0] & 0xFF,) + tuple(r[1:]) for r in ops_only.tolist() if (r[0] & 0xFF) in (14, 15, 16)]
     assert coll == [tuple(r) for r in prog.ops.tolist() if r[0] in (14, 15, 16)]
+    # marks of measurement runs (SDIMB_GM_*): only on M ops, FIRST ... LAST bracket at least min_run marked ops with
+    # nothing but marked M ops between them, FOLLOW iff the stream goes on behind the run
+    min_run = max(n // 8, 4)
+    marks = [((int(r[0]) >> 8) & 0xFF, int(r[0]) & 0xFF) for r in ops_only.tolist()]
+    inside, length = False, 0
+    for k, (mk, op) in enumerate(marks):
+        if op != 14 or not (mk & 1):
+            assert not inside and (op != 14 or mk == 0)
+            continue
+        if mk & 2:
+            assert not inside
+            inside, length = True, 0
+        assert inside
+        length += 1
+        if mk & 4:
+            assert length >= min_run and bool(mk & 8) == (k + 1 < len(marks))
+            inside = False
+    assert not inside
     # inside a layer: a written row is touched by exactly one op; warps are balanced
     for layer in _layers(sched):
         written, touched = set(), {}
