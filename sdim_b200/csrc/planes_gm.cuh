@@ -55,8 +55,8 @@ struct GMImg {
   uint8_t* ph8;
   uint16_t* list;                                // [2np] scratch: compacted generator / row lists
   int n, np, Wq, Wb, gs_shift;                   // group of lanes per B row = 1 << gs_shift >= Wq
-  __device__ __forceinline__ uint32_t* bent(int g, int w) const { return B + ((size_t)g * Wq + w) * EW; }
-  __device__ __forceinline__ uint32_t* qent(int r, int j) const { return QX + ((size_t)r * Wb + j) * EX; }
+  __device__ __forceinline__ uint32_t* bent(int g, int w) const { return B + (uint32_t)((g * Wq + w) * EW); }
+  __device__ __forceinline__ uint32_t* qent(int r, int j) const { return QX + (uint32_t)((r * Wb + j) * EX); }
   __device__ __forceinline__ XZ ldB(int g, int w) const {
     if (D == 3) { const uint4 v = *reinterpret_cast<const uint4*>(bent(g, w)); return XZ{E{v.x, v.y}, E{v.z, v.w}}; }
     const uint2 v = *reinterpret_cast<const uint2*>(bent(g, w));
@@ -73,6 +73,15 @@ struct GMImg {
   __device__ __forceinline__ E ldqx(int r, int j) const {
     if (D == 3) { const uint2 v = *reinterpret_cast<const uint2*>(qent(r, j)); return E{v.x, v.y}; }
     return E{qent(r, j)[0], 0u};
+  }
+  // lane words j (even) and j + 1 of row r in one access
+  __device__ __forceinline__ void ldqx2(int r, int j, E& a, E& b) const {
+    if (D == 3) { const uint4 v = *reinterpret_cast<const uint4*>(qent(r, j)); a = E{v.x, v.y}; b = E{v.z, v.w}; }
+    else { const uint2 v = *reinterpret_cast<const uint2*>(qent(r, j)); a = E{v.x, 0u}; b = E{v.y, 0u}; }
+  }
+  __device__ __forceinline__ void stqx2(int r, int j, E a, E b) const {
+    if (D == 3) *reinterpret_cast<uint4*>(qent(r, j)) = make_uint4(a.l, a.h, b.l, b.h);
+    else *reinterpret_cast<uint2*>(qent(r, j)) = make_uint2(a.l, b.l);
   }
   __device__ __forceinline__ void stqx(int r, int j, E x) const {
     if (D == 3) *reinterpret_cast<uint2*>(qent(r, j)) = make_uint2(x.l, x.h);
@@ -112,113 +121,201 @@ __device__ __noinline__ void gm_transpose(const GEO G, const GMImg<D> M, const b
   }
 }
 
-// set bits of m (this lane's word of a 32-lane-wide mask) -> list entries (32 * lane + bit) | value << 12, in order;
-// returns the total.  One warp.
-__device__ __forceinline__ int gm_compact(uint16_t* list, int lane, uint32_t m, E val) {
-  const int cnt = __popc(m);
+// ---- one shot per TILE of LPS lanes ---------------------------------------------------------------------------
+// At n = 256 a row of QX has 16 lane words and a row of B 8 entries: half a warp holds everything a measurement
+// touches at once.  A shot therefore belongs to a tile of LPS = 4..32 lanes (the power of two >= Wb); the tiles of a
+// warp run different shots in lock step (the control flow of a measurement depends on the X/Z blocks only, which are
+// the same in every shot of a fresh batch; where shots do differ the hardware diverges the tiles, all collectives
+// below are restricted to the tile's member mask).  Per shot this halves the instructions that do not scale with the
+// data (pivot search, scans, loop control) and doubles the shots in flight per SM.
+template <int LPS>
+struct Tile {
+  uint32_t mask;   // member mask of this tile inside its warp
+  int base;        // first warp lane of the tile
+  int lane;        // rank inside the tile
+  __device__ __forceinline__ Tile() {
+    const int wl = threadIdx.x & 31;
+    base = wl & ~(LPS - 1);
+    lane = wl & (LPS - 1);
+    mask = (LPS == 32) ? 0xFFFFFFFFu : (((1u << LPS) - 1u) << base);
+  }
+  template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, LPS); }
+  template <class T> __device__ __forceinline__ T shfl_xor(T v, int m) const { return __shfl_xor_sync(mask, v, m, LPS); }
+  template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(mask, v, d, LPS); }
+  template <class T> __device__ __forceinline__ T shfl_down(T v, int d) const { return __shfl_down_sync(mask, v, d, LPS); }
+  __device__ __forceinline__ uint32_t ballot(bool pr) const { return (__ballot_sync(mask, pr) & mask) >> base; }
+  __device__ __forceinline__ uint32_t min(uint32_t v) const { return __reduce_min_sync(mask, v); }
+  __device__ __forceinline__ uint32_t max(uint32_t v) const { return __reduce_max_sync(mask, v); }
+  __device__ __forceinline__ uint32_t sum(uint32_t v) const { return __reduce_add_sync(mask, v); }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+// Set bits of up to two mask words per lane (word indices w0 < w1 ascending with the lane) -> list entries
+// (32 * w + bit) | value << 12, in ascending order; returns the total (tile-uniform).
+template <int LPS>
+__device__ __forceinline__ int gm_compact(const Tile<LPS>& T, uint16_t* list, uint32_t m0, E v0, int w0, uint32_t m1, E v1,
+                                          int w1) {
+  const int c0 = __popc(m0), cnt = c0 + __popc(m1);
   int incl = cnt;
 #pragma unroll
-  for (int d2 = 1; d2 < 32; d2 <<= 1) {
-    const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d2);
-    if (lane >= d2) incl += o;
+  for (int d2 = 1; d2 < LPS; d2 <<= 1) {
+    const int o = T.shfl_up(incl, d2);
+    if (T.lane >= d2) incl += o;
   }
   int pos = incl - cnt;
-  while (m) {
-    const int b = __ffs(m) - 1;
-    m &= m - 1;
-    list[pos++] = (uint16_t)((32 * lane + b) | (bit2(val, b) << 12));
+  while (m0) {
+    const int b = __ffs(m0) - 1;
+    m0 &= m0 - 1;
+    list[pos++] = (uint16_t)((32 * w0 + b) | (bit2(v0, b) << 12));
   }
-  const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-  __syncwarp();
+  while (m1) {
+    const int b = __ffs(m1) - 1;
+    m1 &= m1 - 1;
+    list[pos++] = (uint16_t)((32 * w1 + b) | (bit2(v1, b) << 12));
+  }
+  const int total = T.shfl(incl, LPS - 1);
+  T.sync();
   return total;
 }
 
-// Measurement of qudit q on the generator-major image, one warp (tableau_prime.py:262-363; same closed forms as
-// p_measure).  Needs Wb <= 32: lane j holds lane word j of row q, lane w holds qudit word w of a generator row.
-template <int D>
-__device__ __noinline__ uint32_t gm_measure(const GMImg<D> M, const int q, const uint32_t draw) {
-  constexpr uint32_t FULL = 0xFFFFFFFFu;
+// Measurement of qudit q on the generator-major image by one tile (tableau_prime.py:262-363; same closed forms as
+// p_measure).  Needs Wb <= LPS.  Row q of QX is held one lane word per lane (pivot search, factors); rows of B and the
+// rows of QX that get updated are held TWO entries per lane, so a B row occupies gb = pow2 >= Wq/2 lanes and LPS / gb
+// rows are in flight per pass.  The shot's state lives in L2 / HBM, so the loads of a batch of passes are issued
+// together, the generator rows together with the pivot row (they depend on row q only), and row q of the NEXT
+// measurement (known from the op stream) is prefetched meanwhile.
+#ifndef SDIMB_GM_UNROLL_B
+#define SDIMB_GM_UNROLL_B 2        // passes over B rows whose loads are in flight together
+#endif
+#ifndef SDIMB_GM_UNROLL_Q
+#define SDIMB_GM_UNROLL_Q 2        // passes over QX rows whose loads are in flight together
+#endif
+template <int D, int LPS>
+__device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D>& M, const int q, const int q_next,
+                                               const uint32_t draw) {
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO;
-  const int lane = threadIdx.x & 31;
+  constexpr int UB = SDIMB_GM_UNROLL_B, UQ = SDIMB_GM_UNROLL_Q;
+  const int lane = T.lane;
   const int Wq = M.Wq, Wb = M.Wb, np = M.np;
   const XZ zero{E{0u, 0u}, E{0u, 0u}};
-  E xq{0u, 0u};
+  const E ezero{0u, 0u};
+  E xq = ezero;
   if (lane < Wb) xq = M.ldqx(q, lane);
+  if (q_next >= 0 && lane < Wb) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.qent(q_next, lane)));
   const uint32_t nz = xq.l | xq.h;
   // pivot: first stabilizer lane with an X component on q (tableau_prime.py:273-283)
-  const uint32_t best = (lane < Wq && nz) ? 32u * lane + (uint32_t)(__ffs(nz) - 1) : kNoPivot;
-  const uint32_t piv = __reduce_min_sync(FULL, best);
+  const uint32_t piv = T.min((lane < Wq && nz) ? 32u * lane + (uint32_t)(__ffs(nz) - 1) : kNoPivot);
+  // B rows: gb lanes per row, lane `sub` of a group holds entries 2 sub and 2 sub + 1
+  const int gb = 1 << M.gs_shift, sub = lane & (gb - 1), grp = lane >> M.gs_shift, ng = LPS >> M.gs_shift;
+  const int w0 = 2 * sub, w1 = 2 * sub + 1;
+  const bool has0 = w0 < Wq, has1 = w1 < Wq;
   uint32_t rec;
   if (piv != kNoPivot) {
     // ---- random branch (tableau_prime.py:294-334, exponentiate :365-380 folded in) ----
     const int jp = piv >> 5, bp = piv & 31;
-    const uint32_t e = (D == 3) ? bit2(E{__shfl_sync(FULL, xq.l, jp), __shfl_sync(FULL, xq.h, jp)}, bp) : 1u;
+    XZ pv0 = zero, pv1 = zero;                           // the pivot row, replicated in every group
+    E dx0 = ezero, dx1 = ezero;                          // X support of the destabilizer that is about to be overwritten
+    if (has0) { pv0 = M.ldB(piv, w0); dx0 = M.ldBx(np + piv, w0); }
+    if (has1) { pv1 = M.ldB(piv, w1); dx1 = M.ldBx(np + piv, w1); }
+    const uint32_t e = (D == 3) ? bit2(E{T.shfl(xq.l, jp), T.shfl(xq.h, jp)}, bp) : 1u;
     E f = negD<D>(xq);                                   // f_i = -X[q,i]; the pivot and its destabilizer are replaced below
     if (lane == jp || lane == Wq + jp) { f.l &= ~(1u << bp); f.h &= ~(1u << bp); }
-    XZ pv = zero;
-    E dxo{0u, 0u};                                       // X support of the destabilizer that is about to be overwritten
-    if (lane < Wq) { pv = M.ldB(piv, lane); dxo = M.ldBx(np + piv, lane); }
-    const uint32_t sd_raw = __reduce_add_sync(FULL, popsum<D>(mulD<D>(pv.x, pv.z))) % D;
+    const int total = gm_compact<LPS>(T, M.list, f.l | f.h, f, lane, 0u, ezero, 0);
+    // first batch of generator rows: requested before anything waits for the pivot row
+    XZ va[UB], vb[UB];
+    uint32_t ent[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int k = u * ng + grp;
+      ent[u] = (k < total) ? (uint32_t)M.list[k] | 0x8000u : 0u;
+      va[u] = vb[u] = zero;
+      if ((ent[u] & 0x8000u) && has0) va[u] = M.ldB(ent[u] & 0xFFFu, w0);
+      if ((ent[u] & 0x8000u) && has1) vb[u] = M.ldB(ent[u] & 0xFFFu, w1);
+    }
+    uint32_t sdp = popsum<D>(mulD<D>(pv0.x, pv0.z)) + popsum<D>(mulD<D>(pv1.x, pv1.z));
+    for (int off = 1; off < gb; off <<= 1) sdp += T.shfl_xor(sdp, off);
+    const uint32_t sd_raw = sdp % D;
     const uint32_t ps_old = M.ph8[piv];
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
-    if (D == 3 && e == 2u) { pv.x = neg3(pv.x); pv.z = neg3(pv.z); }    // pivot <- pivot^e: (xs, zs, ps)
-    // row_i += f_i * pivot for every generator with a factor; 32 >> gs_shift generators per pass
-    {
-      const int total = gm_compact(M.list, lane, f.l | f.h, f);
-      const int gs = 1 << M.gs_shift, sub = lane & (gs - 1), grp = lane >> M.gs_shift, ng = 32 >> M.gs_shift;
-      const XZ pvs{E{__shfl_sync(FULL, pv.x.l, sub), __shfl_sync(FULL, pv.x.h, sub)},
-                   E{__shfl_sync(FULL, pv.z.l, sub), __shfl_sync(FULL, pv.z.h, sub)}};
-      for (int k0 = 0; k0 < total; k0 += ng) {
-        const int k = k0 + grp;
-        const bool act = k < total && sub < Wq;
-        const uint32_t ent = act ? (uint32_t)M.list[k] : 0u;
-        const int i = ent & 0xFFFu;
-        const uint32_t fi = ent >> 12;
-        XZ v = zero;
-        if (act) v = M.ldB(i, sub);
-        uint32_t dot = popsum<D>(mulD<D>(v.z, pvs.x));                   // Z[:,i] . xs (old Z)
-        if (act) M.stB(i, sub, XZ{addD<D>(v.x, smulD<D>(pvs.x, fi)), addD<D>(v.z, smulD<D>(pvs.z, fi))});
-        for (int off = 1; off < gs; off <<= 1) dot += __shfl_xor_sync(FULL, dot, off);
+    if (D == 3 && e == 2u) { pv0.x = neg3(pv0.x); pv0.z = neg3(pv0.z); pv1.x = neg3(pv1.x); pv1.z = neg3(pv1.z); }
+    // row_i += f_i * pivot for every generator with a factor; ng generators per pass   (pivot <- pivot^e = (xs, zs, ps))
+    for (int k0 = 0;;) {
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (k0 + u * ng >= total) break;                                  // tile-uniform
+        const bool act = (ent[u] & 0x8000u) != 0u;
+        const int i = ent[u] & 0xFFFu;
+        const uint32_t fi = (ent[u] >> 12) & 3u;
+        uint32_t dot = popsum<D>(mulD<D>(va[u].z, pv0.x)) + popsum<D>(mulD<D>(vb[u].z, pv1.x));   // Z[:,i] . xs (old Z)
+        if (act && has0) M.stB(i, w0, XZ{addD<D>(va[u].x, smulD<D>(pv0.x, fi)), addD<D>(va[u].z, smulD<D>(pv0.z, fi))});
+        if (act && has1) M.stB(i, w1, XZ{addD<D>(vb[u].x, smulD<D>(pv1.x, fi)), addD<D>(vb[u].z, smulD<D>(pv1.z, fi))});
+        for (int off = 1; off < gb; off <<= 1) dot += T.shfl_xor(dot, off);
         if (act && sub == 0) {
           // P_i += f*ps + po*((Z_i.xs)*f + sd*f(f-1)/2*po)      (tableau_prime.py:310-312,317-319)
           const uint32_t ph = M.ph8[i];
-          M.ph8[i] = (uint8_t)((ph + fi * ps + PO * (((dot % D) * fi + sd * ((fi * (fi - 1u)) >> 1) * PO) % D)) % ORDER);
+          M.ph8[i] = (uint8_t)((ph + fi * ps + PO * ((dot * fi + sd * ((fi * (fi - 1u)) >> 1) * PO) % D)) % ORDER);
         }
       }
-      __syncwarp();
+      k0 += UB * ng;
+      if (k0 >= total) break;
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int k = k0 + u * ng + grp;
+        ent[u] = (k < total) ? (uint32_t)M.list[k] | 0x8000u : 0u;
+        va[u] = vb[u] = zero;
+        if ((ent[u] & 0x8000u) && has0) va[u] = M.ldB(ent[u] & 0xFFFu, w0);
+        if ((ent[u] & 0x8000u) && has1) vb[u] = M.ldB(ent[u] & 0xFFFu, w1);
+      }
     }
+    T.sync();
     // X[r,:] += xs_r * f on the pivot's X support; column p <- 0 (stabilizer p becomes Z_q), column np+p <- xs
-    // (destabilizer p becomes the pivot), including rows where only the old destabilizer had an entry
+    // (destabilizer p becomes the pivot), including rows where only the old destabilizer had an entry.
+    // QX rows: gq = 2 gb lanes per row, lane `subq` holds lane words 2 subq and 2 subq + 1.
     {
-      const E xs = pv.x;
-      const uint32_t mr = (lane < Wq) ? (xs.l | xs.h | dxo.l | dxo.h) : 0u;
-      const int total = gm_compact(M.list, lane, mr, xs);
-      const int gsq = 2 << M.gs_shift, sub = lane & (gsq - 1), grp = lane >> (M.gs_shift + 1), ng = 16 >> M.gs_shift;
-      const E fq{__shfl_sync(FULL, f.l, sub), __shfl_sync(FULL, f.h, sub)};
-      const bool fix_p = sub == jp, fix_d = sub == Wq + jp;
-      for (int k0 = 0; k0 < total; k0 += ng) {
-        const int k = k0 + grp;
-        if (k < total && sub < Wb) {
-          const uint32_t ent = M.list[k];
-          const int r = ent & 0xFFFu;
-          const uint32_t s = ent >> 12;
-          if ((s && (fq.l | fq.h)) || fix_p || fix_d) {
-            E x = M.ldqx(r, sub);
-            x = addD<D>(x, smulD<D>(fq, s));
-            if (fix_p) x = setbit2(x, bp, 0u);
-            if (fix_d) x = setbit2(x, bp, s);
-            M.stqx(r, sub, x);
+      const bool lead = grp == 0;                                        // group 0 lists the rows
+      const int totq = gm_compact<LPS>(T, M.list, (lead && has0) ? (pv0.x.l | pv0.x.h | dx0.l | dx0.h) : 0u, pv0.x, w0,
+                                       (lead && has1) ? (pv1.x.l | pv1.x.h | dx1.l | dx1.h) : 0u, pv1.x, w1);
+      const int gq = 2 << M.gs_shift, subq = lane & (gq - 1), grpq = lane >> (M.gs_shift + 1), ngq = LPS >> (M.gs_shift + 1);
+      const int j0 = 2 * subq, j1 = 2 * subq + 1;
+      const bool hq = j0 < Wb;                                            // Wb is even: j1 < Wb as well
+      const E f0{T.shfl(f.l, j0 & (LPS - 1)), T.shfl(f.h, j0 & (LPS - 1))}, f1{T.shfl(f.l, j1 & (LPS - 1)), T.shfl(f.h, j1 & (LPS - 1))};
+      const bool fixp0 = j0 == jp, fixp1 = j1 == jp, fixd0 = j0 == Wq + jp, fixd1 = j1 == Wq + jp;
+      const bool fix = fixp0 || fixp1 || fixd0 || fixd1, any_f = (f0.l | f0.h | f1.l | f1.h) != 0u;
+      for (int k0 = 0; k0 < totq; k0 += UQ * ngq) {
+        E xa[UQ], xb[UQ];
+        uint32_t en[UQ];
+#pragma unroll
+        for (int u = 0; u < UQ; ++u) {
+          const int k = k0 + u * ngq + grpq;
+          en[u] = 0u;
+          xa[u] = xb[u] = ezero;
+          if (k < totq && hq) {
+            const uint32_t t = M.list[k];
+            if (((t >> 12) && any_f) || fix) { en[u] = t | 0x8000u; M.ldqx2(t & 0xFFFu, j0, xa[u], xb[u]); }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UQ; ++u) {
+          if (en[u] & 0x8000u) {
+            const uint32_t sv = (en[u] >> 12) & 3u;
+            E na = addD<D>(xa[u], smulD<D>(f0, sv)), nb = addD<D>(xb[u], smulD<D>(f1, sv));
+            if (fixp0) na = setbit2(na, bp, 0u);
+            if (fixp1) nb = setbit2(nb, bp, 0u);
+            if (fixd0) na = setbit2(na, bp, sv);
+            if (fixd1) nb = setbit2(nb, bp, sv);
+            M.stqx2(en[u] & 0xFFFu, j0, na, nb);
           }
         }
       }
     }
     // destabilizer p <- (xs, zs, ps); stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333)
-    if (lane < Wq) {
-      M.stB(np + piv, lane, pv);
-      XZ unit = zero;
-      if (lane == (q >> 5)) unit.z.l = 1u << (q & 31);
-      M.stB(piv, lane, unit);
+    if (grp == 0) {
+      XZ u0 = zero, u1 = zero;
+      if (w0 == (q >> 5)) u0.z.l = 1u << (q & 31);
+      if (w1 == (q >> 5)) u1.z.l = 1u << (q & 31);
+      if (has0) { M.stB(np + piv, w0, pv0); M.stB(piv, w0, u0); }
+      if (has1) { M.stB(np + piv, w1, pv1); M.stB(piv, w1, u1); }
     }
     if (lane == 0) {
       M.ph8[np + piv] = (uint8_t)ps;
@@ -227,54 +324,79 @@ __device__ __noinline__ uint32_t gm_measure(const GMImg<D> M, const int q, const
     rec = draw;        // replayed or Philox, resolved when the op was fetched (reference: random.choice, :332)
   } else {
     // ---- deterministic branch (tableau_prime.py:336-363): product of the stabilizers i with f_i = destab X[q,i],
-    // in increasing i, accumulated 32 qudits per lane ----
-    uint32_t wm = __ballot_sync(FULL, nz != 0u) >> Wq;                  // destabilizer lane words with a factor
-    E az{0u, 0u};
+    // in increasing i, accumulated 64 qudits per lane (every group computes the same); rows requested UB at a time ----
+    E fd = ezero;
+    if (lane >= Wq && lane < Wb) fd = xq;
+    const E fsh{T.shfl_down(fd.l, Wq & (LPS - 1)), T.shfl_down(fd.h, Wq & (LPS - 1))};   // lane j: destabilizer word j
+    const E fl = (lane < Wq && Wq < LPS) ? fsh : ezero;
+    const int total = gm_compact<LPS>(T, M.list, fl.l | fl.h, fl, lane, 0u, ezero, 0);   // ordered (stabilizer | f << 12)
+    E az0 = ezero, az1 = ezero;
     uint32_t cross = 0, sdg = 0, a1 = 0;
-    while (wm) {
-      const int j = __ffs(wm) - 1;
-      wm &= wm - 1;
-      const uint32_t fl = __shfl_sync(FULL, xq.l, Wq + j), fh = __shfl_sync(FULL, xq.h, Wq + j);
-      uint32_t mm = fl | fh;
-      while (mm) {
-        const int b = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const int i = 32 * j + b;
-        const uint32_t fi = ((fl >> b) & 1u) | (((fh >> b) & 1u) << 1);
-        XZ v = zero;
-        if (lane < Wq) v = M.ldB(i, lane);
-        cross += popsum<D>(mulD<D>(az, smulD<D>(v.x, fi)));            // ancilla_z . (f * x_i), running ancilla
-        az = addD<D>(az, smulD<D>(v.z, fi));
-        if (D == 3 && fi == 2u) sdg += popsum<D>(mulD<D>(v.x, v.z));    // x_i . z_i * f(f-1)/2
-        a1 += fi * M.ph8[i];
+    for (int k0 = 0; k0 < total; k0 += UB) {
+      XZ va[UB], vb[UB];
+      uint32_t ent[UB];
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        ent[u] = (k0 + u < total) ? (uint32_t)M.list[k0 + u] : 0u;
+        va[u] = vb[u] = zero;
+        if (k0 + u < total && has0) va[u] = M.ldB(ent[u] & 0xFFFu, w0);
+        if (k0 + u < total && has1) vb[u] = M.ldB(ent[u] & 0xFFFu, w1);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        if (k0 + u >= total) break;                                        // tile-uniform
+        const uint32_t fi = ent[u] >> 12;
+        cross += popsum<D>(mulD<D>(az0, smulD<D>(va[u].x, fi))) + popsum<D>(mulD<D>(az1, smulD<D>(vb[u].x, fi)));
+        az0 = addD<D>(az0, smulD<D>(va[u].z, fi));                         // running ancilla
+        az1 = addD<D>(az1, smulD<D>(vb[u].z, fi));
+        if (D == 3 && fi == 2u) sdg += popsum<D>(mulD<D>(va[u].x, va[u].z)) + popsum<D>(mulD<D>(vb[u].x, vb[u].z));
+        a1 += fi * M.ph8[ent[u] & 0xFFFu];
       }
     }
-    const uint32_t part = __reduce_add_sync(FULL, cross + PO * sdg) % D;
-    const uint32_t ap = (a1 % ORDER + PO * part) % ORDER;
+    uint32_t part = cross + PO * sdg;
+    for (int off = 1; off < gb; off <<= 1) part += T.shfl_xor(part, off);
+    const uint32_t ap = (a1 % ORDER + PO * (part % D)) % ORDER;
     const uint32_t outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);   // (-ap // po) % d  (:362)
     rec = outcome | SDIMB_REC_DET;
   }
-  __syncwarp();
+  T.sync();
   return rec;
 }
 
-// ---- the kernel of a trailing measurement run: one warp per shot ------------------------------------------------
-constexpr int kRunWarps = 4;          // warps (= shots in flight) per CTA
-constexpr int kRunCtasPerSm = 8;      // 32 warps per SM at 64 registers
-inline size_t run_smem_bytes(int n) {  // per CTA: list (2np uint16) + ph8 (2np bytes) per warp
-  const size_t np = (size_t)(n + 31) / 32 * 32;
-  return (size_t)kRunWarps * (4 * np + 2 * np);
+// ---- the kernel of a trailing measurement run: one tile per shot --------------------------------------------------
+#ifndef SDIMB_RUN_THREADS
+#define SDIMB_RUN_THREADS 128
+#endif
+#ifndef SDIMB_RUN_CTAS
+#define SDIMB_RUN_CTAS 8
+#endif
+constexpr int kRunThreads = SDIMB_RUN_THREADS;    // threads per CTA: kRunThreads / LPS shots in flight
+constexpr int kRunCtasPerSm = SDIMB_RUN_CTAS;     // 32 warps per SM at 64 registers
+inline int run_lps(int n) {                        // lanes per shot: the power of two >= Wb, at least 4
+  const int np = (n + 31) / 32 * 32, Wb = 2 * np / 32;
+  int lps = 4;
+  while (lps < Wb) lps *= 2;
+  if (const char* env = std::getenv("SDIMB_RUN_LPS")) {                  // developer knob (A/B timings)
+    const int m = std::atoi(env);
+    if (m >= lps && (m == 4 || m == 8 || m == 16 || m == 32)) lps = m;
+  }
+  return lps;
 }
-inline size_t run_slab_words(int n, int d) {   // B + QX of one warp
+inline size_t run_smem_bytes(int n) {  // per CTA: list (2np uint16) + ph8 (2np bytes) per tile
+  const size_t np = (size_t)(n + 31) / 32 * 32;
+  return (size_t)(kRunThreads / run_lps(n)) * (4 * np + 2 * np);
+}
+inline size_t run_slab_words(int n, int d) {   // B + QX of one tile
   const size_t np = (size_t)(n + 31) / 32 * 32, Wq = np / 32, Wb = 2 * Wq, EW = (d == 2) ? 2 : 4;
   return (2 * np * Wq * EW + (size_t)n * Wb * (EW / 2) + 7) & ~(size_t)7;
 }
 
-template <int D, bool IL>
-__global__ void __launch_bounds__(32 * kRunWarps, kRunCtasPerSm) run_tail_kernel(const __grid_constant__ KParams p) {
+template <int D, bool IL, int LPS>
+__global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  constexpr uint32_t FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int TILES = kRunThreads / LPS;
+  const Tile<LPS> T;
+  const int lane = T.lane, tile = threadIdx.x / LPS;
   Geo<D, IL> G;
   G.n = p.n;
   G.np = (p.n + 31) / 32 * 32;
@@ -284,27 +406,27 @@ __global__ void __launch_bounds__(32 * kRunWarps, kRunCtasPerSm) run_tail_kernel
   GMImg<D> M;
   M.n = G.n; M.np = G.np; M.Wq = G.np / 32; M.Wb = G.Wb;
   M.gs_shift = 0;
-  while ((1 << M.gs_shift) < M.Wq) ++M.gs_shift;
-  M.list = reinterpret_cast<uint16_t*>(smem) + (size_t)warp * 2 * G.np;
-  M.ph8 = smem + (size_t)kRunWarps * 4 * G.np + (size_t)warp * 2 * G.np;
-  M.B = p.gm_slab + ((int64_t)blockIdx.x * kRunWarps + warp) * p.gm_slab_words;
+  while ((2 << M.gs_shift) < M.Wq) ++M.gs_shift;                        // lanes per B row: two entries per lane
+  M.list = reinterpret_cast<uint16_t*>(smem) + (size_t)tile * 2 * G.np;
+  M.ph8 = smem + (size_t)TILES * 4 * G.np + (size_t)tile * 2 * G.np;
+  M.B = p.gm_slab + ((int64_t)blockIdx.x * TILES + tile) * p.gm_slab_words;
   M.QX = M.B + (size_t)2 * G.np * M.Wq * GMImg<D>::EW;
   for (;;) {
     int64_t shot = 0;
     if (lane == 0) shot = (int64_t)atomicAdd(p.shot_counter, 1u);
-    shot = __shfl_sync(FULL, shot, 0);
+    shot = T.shfl(shot, 0);
     if (shot >= p.shots) break;
     G.tab = p.plane_slab + shot * p.img_stride_words;          // the image the interpreter left for this shot
     {
       const uint2* ph = reinterpret_cast<const uint2*>(G.tab + row_words);
-      for (int j = 0; j < G.Wb; ++j) {
-        const uint2 w = ph[j];
-        M.ph8[32 * j + lane] = (uint8_t)(((w.x >> lane) & 1u) | (((w.y >> lane) & 1u) << 1));
+      for (int g = lane; g < 2 * G.np; g += LPS) {
+        const uint2 w = ph[g >> 5];
+        M.ph8[g] = (uint8_t)(((w.x >> (g & 31)) & 1u) | (((w.y >> (g & 31)) & 1u) << 1));
       }
     }
-    gm_transpose<D>(G, M, true, lane, 32);
-    __syncwarp();
-    for (int64_t i0 = p.tail_start; i0 < p.n_ops; i0 += 32) {
+    gm_transpose<D>(G, M, true, lane, LPS);
+    T.sync();
+    for (int64_t i0 = p.tail_start; i0 < p.n_ops; i0 += LPS) {
       int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);
       if (i0 + lane < p.n_ops) mine = __ldg(p.ops + i0 + lane);
       mine.x &= SDIMB_OP_MASK;
@@ -319,12 +441,13 @@ __global__ void __launch_bounds__(32 * kRunWarps, kRunCtasPerSm) run_tail_kernel
           mine.z = (int)__umulhi(r.x, (uint32_t)D);
         }
       }
-      uint32_t todo = __ballot_sync(FULL, is_m);
+      uint32_t todo = T.ballot(is_m);
       uint32_t myrec = 0;
       while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        const uint32_t rec = gm_measure<D>(M, __shfl_sync(FULL, mine.y, k), (uint32_t)__shfl_sync(FULL, mine.z, k));
+        const int qn = todo ? T.shfl(mine.y, __ffs(todo) - 1) : -1;      // next measurement of this batch, if any
+        const uint32_t rec = gm_measure<D, LPS>(T, M, T.shfl(mine.y, k), qn, (uint32_t)T.shfl(mine.z, k));
         if (lane == k) myrec = rec;
       }
       if (is_m) p.records[shot * p.rec_stride + mine.w] = (uint8_t)myrec;

@@ -106,6 +106,10 @@ bool planes_interleaved(int n) {
   return (n + 31) / 32 * 32 >= min_np;
 }
 using PlaneKernel = void (*)(const KParams);
+PlaneKernel planes_gates_only_kernel(int d, bool il) {
+  if (il) return (d == 2) ? planes::interp_planes_kernel<2, true, true, true> : planes::interp_planes_kernel<3, true, true, true>;
+  return (d == 2) ? planes::interp_planes_kernel<2, true, false, true> : planes::interp_planes_kernel<3, true, false, true>;
+}
 PlaneKernel planes_global_kernel(int d, bool il) {
   if (il) return (d == 2) ? planes::interp_planes_kernel<2, true, true> : planes::interp_planes_kernel<3, true, true>;
   return (d == 2) ? planes::interp_planes_kernel<2, true, false> : planes::interp_planes_kernel<3, true, false>;
@@ -134,18 +138,28 @@ int planes_global_ctas(int n, int d, size_t* smem_out) {
 }
 
 // Trailing measurement run on a generator-major image (planes_gm.cuh): kernel, resident CTAs, scratch layout.
-PlaneKernel run_tail_kernel_for(int d, bool il) {
-  if (il) return (d == 2) ? planes::run_tail_kernel<2, true> : planes::run_tail_kernel<3, true>;
-  return (d == 2) ? planes::run_tail_kernel<2, false> : planes::run_tail_kernel<3, false>;
+template <int LPS>
+PlaneKernel run_tail_kernel_lps(int d, bool il) {
+  if (il) return (d == 2) ? planes::run_tail_kernel<2, true, LPS> : planes::run_tail_kernel<3, true, LPS>;
+  return (d == 2) ? planes::run_tail_kernel<2, false, LPS> : planes::run_tail_kernel<3, false, LPS>;
+}
+PlaneKernel run_tail_kernel_for(int n, int d) {
+  const bool il = planes_interleaved(n);
+  switch (planes::run_lps(n)) {
+    case 4: return run_tail_kernel_lps<4>(d, il);
+    case 8: return run_tail_kernel_lps<8>(d, il);
+    case 16: return run_tail_kernel_lps<16>(d, il);
+    default: return run_tail_kernel_lps<32>(d, il);
+  }
 }
 bool tail_run_shape_ok(int n, int d) { return (d == 2 || d == 3) && (n + 31) / 32 * 32 <= 512; }   // Wb <= 32
 int run_tail_ctas(int n, int d) {
-  auto kern = run_tail_kernel_for(d, planes_interleaved(n));
+  auto kern = run_tail_kernel_for(n, d);
   const size_t smem = planes::run_smem_bytes(n);
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * planes::kRunWarps, smem) != cudaSuccess || per_sm < 1) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, planes::kRunThreads, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     return 0;
   }
@@ -156,10 +170,10 @@ int run_tail_ctas(int n, int d) {
   return sms * per_sm;
 }
 // scratch of a call that hands its tail run to run_tail_kernel: 256 bytes of counters, one image per SHOT, one
-// B + QX slab per resident warp of run_tail_kernel
+// B + QX slab per resident tile (= shot in flight) of run_tail_kernel
 size_t tail_run_scratch_bytes(int n, int d, int64_t shots, int run_ctas) {
   return 256 + (size_t)shots * 4 * planes::planes_img_stride_words(n, d) +
-         (size_t)run_ctas * planes::kRunWarps * 4 * planes::run_slab_words(n, d);
+         (size_t)run_ctas * (planes::kRunThreads / planes::run_lps(n)) * 4 * planes::run_slab_words(n, d);
 }
 
 // Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
@@ -346,6 +360,19 @@ int sdimb_run(const SdimbRunArgs* caller) {
       KParams p1 = p;
       p1.n_ops = a->n_ops - tail;
       int64_t grid1 = max_ctas < a->shots ? max_ctas : a->shots;
+      // every measurement of the stream sits in the tail run: the front part runs the gates-only instantiation
+      static const bool no_gates_only = std::getenv("SDIMB_NO_GATES_ONLY") != nullptr;     // developer knob (A/B timings)
+      if (a->n_meas == tail && !no_gates_only) {
+        kern = planes_gates_only_kernel(a->d, planes_interleaved(a->n));
+        int per_sm = 0, sms = 0, dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * SDIMB_SCHED_WARPS, smem) != cudaSuccess || per_sm < 1) {
+          cudaGetLastError();
+          return SDIMB_ECUDA;
+        }
+        grid1 = (int64_t)sms * per_sm < a->shots ? (int64_t)sms * per_sm : a->shots;
+      }
       kern<<<(unsigned)grid1, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p1);
       g_launches++;
       if (cudaGetLastError() != cudaSuccess) return SDIMB_ECUDA;
@@ -354,10 +381,11 @@ int sdimb_run(const SdimbRunArgs* caller) {
       p2.shot_counter = (unsigned int*)a->scratch + 1;
       p2.gm_slab = p.plane_slab + (int64_t)a->shots * p.img_stride_words;
       p2.gm_slab_words = (int64_t)planes::run_slab_words(a->n, a->d);
-      int64_t grid2 = (a->shots + planes::kRunWarps - 1) / planes::kRunWarps;
+      const int tiles = planes::kRunThreads / planes::run_lps(a->n);
+      int64_t grid2 = (a->shots + tiles - 1) / tiles;
       if (grid2 > run_ctas_max) grid2 = run_ctas_max;
-      auto kern2 = run_tail_kernel_for(a->d, planes_interleaved(a->n));
-      kern2<<<(unsigned)grid2, 32 * planes::kRunWarps, planes::run_smem_bytes(a->n), (cudaStream_t)a->stream>>>(p2);
+      auto kern2 = run_tail_kernel_for(a->n, a->d);
+      kern2<<<(unsigned)grid2, planes::kRunThreads, planes::run_smem_bytes(a->n), (cudaStream_t)a->stream>>>(p2);
       g_launches++;
       return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
     }
@@ -782,7 +810,7 @@ int64_t sdimb_scratch_bytes_shots(int n, int d, uint32_t flags, int64_t shots) {
   SdimbLayout L;
   if (shots <= 0 || sdimb_layout(n, d, &L) || plan_kernel(n, d, flags, L.np) != 3 || !tail_run_shape_ok(n, d)) return base;
   int ctas = run_tail_ctas(n, d);
-  if (ctas < 1) ctas = 148 * planes::kRunCtasPerSm;
+  if (ctas < 1) ctas = 148 * planes::kRunCtasPerSm;     // no device: the size a B200 would need
   const int64_t need = (int64_t)tail_run_scratch_bytes(n, d, shots, ctas);
   return need > base ? need : base;
 }
