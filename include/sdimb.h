@@ -30,6 +30,11 @@
  *          row q (qudit q):  X[q][0..W) at q*2W,  Z[q][0..W) at q*2W + W      (uint8, reduced mod d)
  *          phases:           P[0..W)    at n*2W                                 (uint8, reduced mod order)
  *   order = 2d for d = 2, d for odd prime d (sdim/tableau/dataclasses.py:88-106)
+ *
+ * Primes 127 < d < 32768 ("uint16 lanes"): the same store with TWO bytes per entry (SdimbLayout.elem_bytes = 2; all
+ * offsets double), and record / replay_meas / replay_noise elements are uint16 as well (SdimbLayout.rec_bytes = 2,
+ * bit 15 of a record = deterministic flag).  The pointer types below stay uint8_t*: for those dimensions they are
+ * read as uint16_t* (element strides rec_stride / n_meas / n_noise unchanged).  sdimb_frames stops at d = 127.
  */
 #ifndef SDIMB_H
 #define SDIMB_H
@@ -40,15 +45,15 @@
 extern "C" {
 #endif
 
-#define SDIMB_VERSION 2
+#define SDIMB_VERSION 3
 
 enum {
   SDIMB_OK = 0,
   SDIMB_EINVAL = -1,   /* bad argument (null pointer, n < 1, shots < 0, bad struct_size ...) */
-  SDIMB_EDIM = -2,     /* dimension not a prime in [2, 127] */
+  SDIMB_EDIM = -2,     /* dimension not a prime below 32768 (sdimb_frames: not a prime in [2, 127]) */
   SDIMB_EOP = -3,      /* invalid opcode / qudit index in the op stream ("Invalid gate value", sdim/program.py:381-382) */
   SDIMB_ECUDA = -4,    /* CUDA runtime error (no device, launch failure, out of memory) */
-  SDIMB_ETOOBIG = -5   /* forced resident mode but one tableau does not fit in shared memory */
+  SDIMB_ETOOBIG = -5   /* forced resident mode but one tableau does not fit in shared memory; d > 127 with n > 16384 */
 };
 
 /* Opcodes = gate ids of the reference gate table (sdim/gatedata.py:65-102). */
@@ -78,9 +83,12 @@ enum {
 #endif
 
 /* Record byte: low 7 bits = measured value, bit 7 = deterministic flag
- * (MeasurementResult.measurement_value / .deterministic, sdim/tableau/dataclasses.py:166-180). */
+ * (MeasurementResult.measurement_value / .deterministic, sdim/tableau/dataclasses.py:166-180).
+ * d > 127: uint16 records, low 15 bits = value, bit 15 = deterministic flag. */
 #define SDIMB_REC_DET 0x80u
 #define SDIMB_REC_VALUE 0x7Fu
+#define SDIMB_REC16_DET 0x8000u
+#define SDIMB_REC16_VALUE 0x7FFFu
 
 /* sdimb_run flags */
 #define SDIMB_FRESH 0x1u           /* start every shot from |0...0> (ignore/skip the contents of `tableau`) */
@@ -96,13 +104,18 @@ enum {
 #define SDIMB_CLUSTER 0x80u        /* HBM store: run one shot per thread-block cluster whatever n and shots are
                                       (default: only for n > 512 with fewer shots than clusters fit on the GPU) */
 #define SDIMB_NO_CLUSTER 0x100u    /* HBM store: never use the cluster interpreter */
+#define SDIMB_TIME_KERNELS 0x200u  /* measurement aid: a call that runs two kernels (interpreter + tail run) records CUDA
+                                      events around each on `stream`; sdimb_kernel_times reads them (one set per
+                                      process, not for concurrent callers) */
 
 typedef struct SdimbLayout {
   int32_t n, d, np, lanes;   /* lanes = W = 2*np */
   int32_t order, phase_order;
   int64_t row_bytes;         /* 2*W: X row then Z row of one qudit */
   int64_t phase_offset;      /* n*row_bytes */
-  int64_t shot_bytes;        /* phase_offset + W */
+  int64_t shot_bytes;        /* phase_offset + W * elem_bytes */
+  int32_t elem_bytes;        /* bytes per tableau entry: 1 (d <= 127), 2 (127 < d < 32768); the byte counts above include it */
+  int32_t rec_bytes;         /* bytes per record / replay element, same rule */
 } SdimbLayout;
 
 typedef struct SdimbRunArgs {
@@ -214,11 +227,16 @@ int64_t sdimb_tail_run(const int32_t* ops, int64_t n_ops);
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store (one CTA or
  * one thread-block cluster per shot, chosen per call from n and shots), 1 uint8 lanes resident in shared memory,
  * 2 bit-plane resident (d = 2, 3), 3 bit planes on a global image held in SdimbRunArgs.scratch (d = 2, 3 beyond
- * the shared-memory limit); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for these flags. */
+ * the shared-memory limit), 4 uint16 lanes on the HBM store (d > 127); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for these flags. */
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 int64_t sdimb_launch_count(void);
+
+/* Device time of the two kernels of the last sdimb_run that carried SDIMB_TIME_KERNELS and split its stream into
+ * interpreter + tail run (waits for that call to finish); SDIMB_EINVAL if there was none.  bench.py's per-kernel
+ * roofline uses it. */
+int sdimb_kernel_times(float* front_ms, float* tail_ms);
 
 /* Cluster size sdimb_run would give the cluster interpreter for (n, d, shots, flags) on the current device;
  * 0 = that call runs one CTA per shot (or another interpreter).  Needs a CUDA device (else 0). */

@@ -41,13 +41,14 @@ def _p(a):
 
 def run(n, d, ops, shots, shot_offset=0, seed=0, replay_meas=None, replay_noise=None, thresh24=None, channel=None,
         want_final=False, nthreads=0, meas_nnz=None):
-    """Returns (records uint8[shots, n_meas], final dict or None).  Replay arrays as in the CUDA path."""
+    """Returns (records uint8[shots, n_meas] (uint16 for d > 127), final dict or None).  Replay arrays as in the CUDA path."""
     ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 4)
     n_meas = int(np.isin(ops[:, 0], (14, 15, 16)).sum())
     n_noise = int((ops[:, 0] == 17).sum())
-    rec = np.zeros((shots, n_meas), dtype=np.uint8)
-    rm = None if replay_meas is None else np.ascontiguousarray(replay_meas, dtype=np.uint8)
-    rn = None if replay_noise is None else np.ascontiguousarray(replay_noise, dtype=np.uint8)
+    rdt = np.uint16 if d > 127 else np.uint8       # element width of records / replay arrays (include/sdimb.h)
+    rec = np.zeros((shots, n_meas), dtype=rdt)
+    rm = None if replay_meas is None else np.ascontiguousarray(replay_meas, dtype=rdt)
+    rn = None if replay_noise is None else np.ascontiguousarray(replay_noise, dtype=rdt)
     th = None if thresh24 is None else np.ascontiguousarray(thresh24, dtype=np.uint32)
     ch = None if channel is None else np.ascontiguousarray(channel, dtype=np.uint8)
     if n_noise and rn is None and (th is None or ch is None):

@@ -148,6 +148,30 @@ def main_large():
     print(f"wrote {len(cases)} cases ({dropped} dropped) -> {path} ({os.path.getsize(path)} bytes)")
 
 
+def main_wide():
+    """Primes above 127 (the uint16-lane path of the CUDA store, csrc/wide.cuh): same construction as --large.
+    Shallow circuits for the same overflow reason; 32749 is the largest prime the store accepts."""
+    plan, seed = [], 7000
+    for d in (131, 251, 257, 1031, 32749):
+        for n, depth, reps in ((1, 16, 2), (2, 24, 3), (3, 36, 3), (5, 48, 3), (8, 60, 2)):
+            for _ in range(reps):
+                plan.append((seed, n, d, depth))
+                seed += 1
+    cases, dropped = [], 0
+    for seed, n, d, depth in plan:
+        case = make_case(seed, n, d, depth)
+        if case is None:
+            dropped += 1
+        else:
+            cases.append(case)
+    out = {"generator": "oracle/make_golden.py --wide", "reference": "events555/sdim @ /root/reference",
+           "dropped_for_reference_int64_overflow": dropped, "cases": cases}
+    path = os.path.join(GOLDEN_DIR, "wide_primes.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh, separators=(",", ":"))
+    print(f"wrote {len(cases)} cases ({dropped} dropped) -> {path} ({os.path.getsize(path)} bytes)")
+
+
 def config_cases():
     """(name, n, d, ops, noise_ab) of the BASELINE.json config-size shots: circuits from the product's workload
     builders (sdim_b200/workloads.py, same constructions as SURVEY 8d), N1 events as the (a, b) draws of Philox
@@ -211,5 +235,7 @@ if __name__ == "__main__":
         main_configs()
     elif "--large" in sys.argv:
         main_large()
+    elif "--wide" in sys.argv:
+        main_wide()
     else:
         main()

@@ -234,10 +234,16 @@ static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-static void run_one(Tab* t, int64_t local, int64_t gshot, const int32_t* ops, int64_t n_ops, uint8_t* records,
-                    int64_t n_meas, const uint8_t* replay_meas, const uint8_t* replay_noise, const uint32_t* thresh,
+/* Records and replay arrays are one byte per element for d <= 127 (bit 7 = deterministic) and uint16 for larger
+ * primes (bit 15 = deterministic), as in include/sdimb.h. */
+static int rd_elem(const void* a, int64_t i, int wide) {
+  return wide ? ((const uint16_t*)a)[i] : ((const uint8_t*)a)[i];
+}
+
+static void run_one(Tab* t, int64_t local, int64_t gshot, const int32_t* ops, int64_t n_ops, void* records,
+                    int64_t n_meas, const void* replay_meas, const void* replay_noise, const uint32_t* thresh,
                     const uint8_t* chan, int64_t n_noise, uint64_t seed, int32_t* meas_nnz) {
-  const int d = t->d;
+  const int d = t->d, wide = d > 127;
   tab_reset(t);
   for (int64_t i = 0; i < n_ops; ++i) { /* program.py:311-351 */
     const int op = ops[4 * i], a = ops[4 * i + 1], b = ops[4 * i + 2], slot = ops[4 * i + 3];
@@ -259,7 +265,7 @@ static void run_one(Tab* t, int64_t local, int64_t gshot, const int32_t* ops, in
       case 14: case 15: case 16: {
         if (op == 15) hadamard(t, a, 1); /* tableau_gates.py:292-296 */
         int draw;
-        if (replay_meas) draw = replay_meas[local * n_meas + slot];
+        if (replay_meas) draw = rd_elem(replay_meas, local * n_meas + slot, wide);
         else {
           uint32_t c[4] = {(uint32_t)gshot, (uint32_t)((uint64_t)gshot >> 32), (uint32_t)slot, 0u};
           philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -268,18 +274,19 @@ static void run_one(Tab* t, int64_t local, int64_t gshot, const int32_t* ops, in
         int det = 0, nnz = 0;
         const int m = measure(t, a, draw, &det, &nnz);
         if (meas_nnz) meas_nnz[slot] = nnz;
-        records[local * n_meas + slot] = (uint8_t)((m & 0x7F) | (det ? 0x80 : 0));
+        if (wide) ((uint16_t*)records)[local * n_meas + slot] = (uint16_t)((m & 0x7FFF) | (det ? 0x8000 : 0));
+        else ((uint8_t*)records)[local * n_meas + slot] = (uint8_t)((m & 0x7F) | (det ? 0x80 : 0));
         if (op == 16 && m) pauli(t, a, (d - m) % d, 0); /* program.py:335-339 */
         break;
       }
       case 17: {
         int na = 0, nb = 0;
-        if (replay_noise) { na = replay_noise[(local * n_noise + slot) * 2]; nb = replay_noise[(local * n_noise + slot) * 2 + 1]; }
+        if (replay_noise) { na = rd_elem(replay_noise, (local * n_noise + slot) * 2, wide); nb = rd_elem(replay_noise, (local * n_noise + slot) * 2 + 1, wide); }
         else {
           uint32_t c[4] = {(uint32_t)gshot, (uint32_t)((uint64_t)gshot >> 32), (uint32_t)slot, 1u};
           philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
           if ((c[0] >> 8) >= thresh[slot]) { /* program.py:486-507 */
-            if (chan[slot] == 0) { const uint32_t r = 1u + (uint32_t)(((uint64_t)c[1] * (uint64_t)(d * d - 1)) >> 32); na = r % d; nb = r / d; }
+            if (chan[slot] == 0) { const uint32_t r = 1u + (uint32_t)(((uint64_t)c[1] * (uint64_t)((uint32_t)d * (uint32_t)d - 1u)) >> 32); na = r % d; nb = r / d; }
             else { const uint32_t e = 1u + (uint32_t)(((uint64_t)c[1] * (uint64_t)(d - 1)) >> 32); if (chan[slot] == 1) na = e; else nb = e; }
           }
         }
@@ -302,8 +309,8 @@ int oracle_max_threads(void) {
 /* final (nullable): the LAST shot's six arrays as int64, concatenated x,z,dx,dz (n*n each) then p,dp (n each).
  * meas_nnz (nullable, [n_meas]): for the LAST shot, the number of generators with a non-zero factor in each
  * measurement (the ones the reference does not skip, tableau_prime.py:308,315,351) - used for byte accounting. */
-int oracle_run(int n, int d, int64_t shots, int64_t shot_offset, const int32_t* ops, int64_t n_ops, uint8_t* records,
-               int64_t n_meas, const uint8_t* replay_meas, const uint8_t* replay_noise, const uint32_t* thresh,
+int oracle_run(int n, int d, int64_t shots, int64_t shot_offset, const int32_t* ops, int64_t n_ops, void* records,
+               int64_t n_meas, const void* replay_meas, const void* replay_noise, const uint32_t* thresh,
                const uint8_t* chan, int64_t n_noise, uint64_t seed, int64_t* final, int32_t* meas_nnz, int threads) {
   if (n < 1 || d < 2 || shots < 0) return -1;
   int failed = 0;

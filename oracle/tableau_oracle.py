@@ -242,12 +242,13 @@ def run_shots(n: int, d: int, ops, shots: int, meas_draws: Optional[np.ndarray] 
     """
     ops = np.asarray(ops, dtype=np.int64).reshape(-1, 4)
     n_meas = int(np.isin(ops[:, 0], (OP_M, OP_M_X, OP_RESET)).sum())
-    out = np.zeros((shots, n_meas), dtype=np.uint8)
+    wide = d > 127                       # uint16 records, bit 15 = deterministic (include/sdimb.h)
+    out = np.zeros((shots, n_meas), dtype=np.uint16 if wide else np.uint8)
     last = None
     for s in range(shots):
         md = (lambda k, s=s: int(meas_draws[s, k])) if meas_draws is not None else None
         na = noise_ab[s] if noise_ab is not None else None
         recs, last = run_shot(n, d, ops, md, na)
         for k, (_, det, m) in enumerate(recs):
-            out[s, k] = (m & 0x7F) | (0x80 if det else 0)
+            out[s, k] = ((m & 0x7FFF) | (0x8000 if det else 0)) if wide else ((m & 0x7F) | (0x80 if det else 0))
     return out, (last if keep_tableau else None)

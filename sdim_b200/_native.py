@@ -8,20 +8,21 @@ from .build import LIB_PATH
 
 OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
 FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT, FORCE_LANES, FORCE_PLANES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
-SCHEDULED, CLUSTER, NO_CLUSTER = 0x40, 0x80, 0x100
+SCHEDULED, CLUSTER, NO_CLUSTER, TIME_KERNELS = 0x40, 0x80, 0x100, 0x200
 OP_BARRIER = 18
-KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident", 3: "planes-global"}
+KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident", 3: "planes-global", 4: "lanes16-global"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
                     "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes", "sdimb_cluster_size",
-                    "sdimb_scratch_bytes_shots", "sdimb_tail_run")
+                    "sdimb_scratch_bytes_shots", "sdimb_tail_run", "sdimb_kernel_times")
 
 
 class SdimbLayout(C.Structure):
     _fields_ = [("n", C.c_int32), ("d", C.c_int32), ("np", C.c_int32), ("lanes", C.c_int32),
                 ("order", C.c_int32), ("phase_order", C.c_int32),
-                ("row_bytes", C.c_int64), ("phase_offset", C.c_int64), ("shot_bytes", C.c_int64)]
+                ("row_bytes", C.c_int64), ("phase_offset", C.c_int64), ("shot_bytes", C.c_int64),
+                ("elem_bytes", C.c_int32), ("rec_bytes", C.c_int32)]
 
 
 class SdimbRunArgs(C.Structure):
@@ -74,6 +75,7 @@ def lib() -> C.CDLL:
     L.sdimb_scratch_bytes_shots.restype = C.c_int64
     L.sdimb_tail_run.argtypes = [C.c_void_p, C.c_int64]
     L.sdimb_tail_run.restype = C.c_int64
+    L.sdimb_kernel_times.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.sdimb_cluster_size.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint32]
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
@@ -112,6 +114,14 @@ def schedule(n: int, ops):
     check(lib().sdimb_schedule(n, ops.ctypes.data if ops.size else None, ops.shape[0], out.ctypes.data,
                                out.shape[0], C.byref(count)))
     return out[: count.value].copy()
+
+
+def kernel_times():
+    """(interpreter ms, tail-run ms) of the last run that carried TIME_KERNELS and split its stream; None otherwise."""
+    a, b = C.c_float(0.0), C.c_float(0.0)
+    if lib().sdimb_kernel_times(C.byref(a), C.byref(b)) != OK:
+        return None
+    return float(a.value), float(b.value)
 
 
 def tail_run(sched) -> int:

@@ -38,6 +38,7 @@ namespace {
 #include "planes.cuh"
 #include "util_kernels.cuh"
 #include "frames.cuh"
+#include "wide.cuh"
 
 bool is_prime(int d) {
   if (d < 2) return false;
@@ -48,7 +49,8 @@ bool is_prime(int d) {
 
 int check_dims(int n, int d) {
   if (n < 1) return SDIMB_EINVAL;
-  if (d < 2 || d > 127 || !is_prime(d)) return SDIMB_EDIM;
+  if (d < 2 || d >= (1 << 15) || !is_prime(d)) return SDIMB_EDIM;
+  if (d > 127 && n > 16384) return SDIMB_ETOOBIG;      // uint16 lanes: row indices and scratch of wide.cuh
   return SDIMB_OK;
 }
 
@@ -77,6 +79,8 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
   SdimbLayout L;
   const int rc = sdimb_layout(n, d, &L);
   if (rc) return rc;
+  if (d > 127)      // uint16 lanes (wide.cuh): one interpreter, on the HBM store
+    return (flags & (SDIMB_FORCE_RESIDENT | SDIMB_FORCE_PLANES)) ? SDIMB_ETOOBIG : 4;
   const bool fits = (size_t)L.shot_bytes + scratch_bytes(np) <= (size_t)kSmemLimit;
   const bool planes_ok = d == 2 || d == 3;
   const bool planes_fit = planes_ok && planes::planes_smem_bytes(n, d) <= (size_t)kSmemLimit;
@@ -211,6 +215,16 @@ int max_active_clusters(const SdimbLayout& L, int C) {
   return nc;
 }
 
+// SDIMB_TIME_KERNELS: events around the two kernels of a tail-run call, read back by sdimb_kernel_times (bench.py's
+// per-kernel roofline).  One set per process: a measurement aid, not for concurrent callers.
+cudaEvent_t g_time_ev[3] = {nullptr, nullptr, nullptr};
+int g_time_valid = 0;
+bool time_events_ready() {
+  for (auto& e : g_time_ev)
+    if (!e && cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
 int plan_cluster(const SdimbLayout& L, int64_t shots, uint32_t flags) {
   if (flags & SDIMB_NO_CLUSTER) return 0;
   if (flags & SDIMB_CLUSTER) {
@@ -237,7 +251,7 @@ const char* sdimb_strerror(int code) {
   switch (code) {
     case SDIMB_OK: return "ok";
     case SDIMB_EINVAL: return "invalid argument";
-    case SDIMB_EDIM: return "dimension must be a prime in [2, 127]";
+    case SDIMB_EDIM: return "dimension must be a prime below 32768 (the frame sampler: at most 127)";
     case SDIMB_EOP: return "Invalid gate value";
     case SDIMB_ECUDA: return "CUDA error (is a GPU present? there is no CPU fallback)";
     case SDIMB_ETOOBIG: return "tableau does not fit in shared memory for the resident interpreter";
@@ -256,9 +270,11 @@ int sdimb_layout(int n, int d, SdimbLayout* out) {
   out->lanes = 2 * out->np;
   out->order = (int32_t)A.order;
   out->phase_order = (int32_t)A.po;
-  out->row_bytes = 2ll * out->lanes;
+  out->elem_bytes = d > 127 ? 2 : 1;
+  out->rec_bytes = out->elem_bytes;
+  out->row_bytes = 2ll * out->lanes * out->elem_bytes;
   out->phase_offset = (int64_t)n * out->row_bytes;
-  out->shot_bytes = out->phase_offset + out->lanes;
+  out->shot_bytes = out->phase_offset + (int64_t)out->lanes * out->elem_bytes;
   return SDIMB_OK;
 }
 
@@ -269,6 +285,11 @@ int sdimb_init(void* tableau, int n, int d, int64_t shots, void* stream) {
   if (!tableau || shots < 0) return SDIMB_EINVAL;
   if (shots == 0) return SDIMB_OK;
   const int grid = (int)(shots < 148 * 16 ? shots : 148 * 16);
+  if (L.elem_bytes == 2) {
+    wide::init16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint16_t*)tableau, n, L.np, L.lanes, L.shot_bytes / 2, shots);
+    g_launches++;
+    return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+  }
   init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint8_t*)tableau, n, L.np, L.lanes, L.row_bytes, L.shot_bytes,
                                                       shots);
   g_launches++;
@@ -298,7 +319,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
   if (kernel < 0) return kernel;
   const size_t scratch = scratch_bytes(L.np);
   const bool use_planes = kernel == 2, resident = kernel >= 1;   // 3 keeps its image in scratch: no store needed either
-  const bool need_tab = !resident || !(a->flags & SDIMB_FRESH) || (a->flags & SDIMB_WRITEBACK);
+  const bool need_tab = !resident || kernel == 4 || !(a->flags & SDIMB_FRESH) || (a->flags & SDIMB_WRITEBACK);
   if (need_tab && !a->tableau) return SDIMB_EINVAL;
 
   KParams p;
@@ -326,6 +347,20 @@ int sdimb_run(const SdimbRunArgs* caller) {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
+  if (kernel == 4) {     // uint16 lanes, one CTA per shot on the HBM store
+    const size_t smem = wide::smem_bytes(L.np);
+    auto kern = wide::interp_wide16_kernel;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wide::kThreads, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      return SDIMB_ECUDA;
+    }
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > a->shots) grid = a->shots;
+    kern<<<(unsigned)grid, wide::kThreads, smem, (cudaStream_t)a->stream>>>(p);
+    g_launches++;
+    return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+  }
   // the global-image plane interpreter needs its slabs; a caller that brought none still gets the resident one
   // where that fits (it was the only plane interpreter of this ABI's first version)
   if (kernel == 3 && !(a->flags & SDIMB_FORCE_GLOBAL) && planes::planes_smem_bytes(a->n, a->d) <= (size_t)kSmemLimit &&
@@ -373,9 +408,13 @@ int sdimb_run(const SdimbRunArgs* caller) {
         }
         grid1 = (int64_t)sms * per_sm < a->shots ? (int64_t)sms * per_sm : a->shots;
       }
+      const bool timed = (a->flags & SDIMB_TIME_KERNELS) && time_events_ready();
+      g_time_valid = 0;
+      if (timed) cudaEventRecord(g_time_ev[0], (cudaStream_t)a->stream);
       kern<<<(unsigned)grid1, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p1);
       g_launches++;
       if (cudaGetLastError() != cudaSuccess) return SDIMB_ECUDA;
+      if (timed) cudaEventRecord(g_time_ev[1], (cudaStream_t)a->stream);
       KParams p2 = p;
       p2.tail_start = a->n_ops - tail;
       p2.shot_counter = (unsigned int*)a->scratch + 1;
@@ -387,6 +426,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
       auto kern2 = run_tail_kernel_for(a->n, a->d);
       kern2<<<(unsigned)grid2, planes::kRunThreads, planes::run_smem_bytes(a->n), (cudaStream_t)a->stream>>>(p2);
       g_launches++;
+      if (timed) { cudaEventRecord(g_time_ev[2], (cudaStream_t)a->stream); g_time_valid = 1; }
       return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
     }
     if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
@@ -470,6 +510,11 @@ int sdimb_export(const void* tableau, int n, int d, int64_t shot, int64_t* x, in
   const uint8_t* T = (const uint8_t*)tableau + shot * L.shot_bytes;
   const int64_t total = (int64_t)n * n;
   const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  if (L.elem_bytes == 2) {
+    wide::export16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)T, n, L.np, L.lanes, x, z, p, dx, dz, dp);
+    g_launches++;
+    return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+  }
   export_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, n, L.np, L.lanes, L.row_bytes, L.phase_offset, x, z, p, dx,
                                                         dz, dp);
   g_launches++;
@@ -586,12 +631,13 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   }
 
   // carve the device arena
-  const size_t b_ops = align256((size_t)up_n * 16), b_rec = align256((size_t)shots * n_meas);
+  const size_t eb = (size_t)L.rec_bytes;     // records / replayed outcomes / replayed exponents: 1 byte, 2 for d > 127
+  const size_t b_ops = align256((size_t)up_n * 16), b_rec = align256((size_t)shots * n_meas * eb);
   const size_t b_rm = replay_meas ? b_rec : 0;
-  const size_t b_rn = replay_noise ? align256((size_t)shots * n_noise * 2) : 0;
+  const size_t b_rn = replay_noise ? align256((size_t)shots * n_noise * 2 * eb) : 0;
   const size_t b_th = (n_noise && noise_thresh24) ? align256((size_t)n_noise * 4) : 0;
   const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
-  const size_t b_tab = kernel == 0 ? align256((size_t)shots * L.shot_bytes) : 0;
+  const size_t b_tab = (kernel == 0 || kernel == 4) ? align256((size_t)shots * L.shot_bytes) : 0;
   const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
   const size_t b_scr = align256((size_t)sdimb_scratch_bytes_shots(n, d, mode_flags, tail_len ? shots : 0));
   const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_scr + 256;
@@ -615,8 +661,8 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   do {
     if (cudaEventRecord(g_ws.e0, st) != cudaSuccess) break;
     if (up_n && cudaMemcpyAsync(d_ops, up_ops, (size_t)up_n * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-    if (d_rm && cudaMemcpyAsync(d_rm, replay_meas, (size_t)shots * n_meas, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-    if (d_rn && cudaMemcpyAsync(d_rn, replay_noise, (size_t)shots * n_noise * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (d_rm && cudaMemcpyAsync(d_rm, replay_meas, (size_t)shots * n_meas * eb, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (d_rn && cudaMemcpyAsync(d_rn, replay_noise, (size_t)shots * n_noise * 2 * eb, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_th && cudaMemcpyAsync(d_th, noise_thresh24, (size_t)n_noise * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_ch && cudaMemcpyAsync(d_ch, noise_channel, (size_t)n_noise, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     SdimbRunArgs a;
@@ -635,7 +681,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     rc = sdimb_run(&a);
     if (rc) break;
     rc = SDIMB_ECUDA;
-    const size_t rec_bytes = (size_t)shots * n_meas;
+    const size_t rec_bytes = (size_t)shots * n_meas * eb;
     if (rec_bytes && cudaMemcpyAsync(g_ws.pin, d_rec, rec_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
     if (cudaEventRecord(g_ws.e1, st) != cudaSuccess) break;
     if (cudaStreamSynchronize(st) != cudaSuccess) break;
@@ -648,6 +694,17 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
 }
 
 int64_t sdimb_launch_count(void) { return g_launches.load(); }
+
+int sdimb_kernel_times(float* front_ms, float* tail_ms) {
+  if (!front_ms || !tail_ms) return SDIMB_EINVAL;
+  if (!g_time_valid) return SDIMB_EINVAL;
+  if (cudaEventSynchronize(g_time_ev[2]) != cudaSuccess || cudaEventElapsedTime(front_ms, g_time_ev[0], g_time_ev[1]) != cudaSuccess ||
+      cudaEventElapsedTime(tail_ms, g_time_ev[1], g_time_ev[2]) != cudaSuccess) {
+    cudaGetLastError();
+    return SDIMB_ECUDA;
+  }
+  return SDIMB_OK;
+}
 
 #ifdef SDIMB_PHASE_CLOCKS
 // developer build only: read (and clear) the cluster interpreter's per-phase clock accumulators
@@ -772,6 +829,7 @@ int sdimb_frames(int n, int d, int64_t shots, int64_t shot_offset, const int32_t
                  void* stream) {
   const int rc = check_dims(n, d);
   if (rc) return rc;
+  if (d > 127) return SDIMB_EDIM;       // frames and packed record bytes are uint8 here
   if (shots < 0 || n_ops < 0 || n_meas < 0 || n_noise < 0) return SDIMB_EINVAL;
   if (shots == 0) return SDIMB_OK;
   if ((n_ops > 0 && !ops) || !frames) return SDIMB_EINVAL;
@@ -835,7 +893,7 @@ int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau) {
   const int k = plan_kernel(n, d, flags, L.np);
   if (k < 0) return k;
   if (kernel) *kernel = k;
-  if (needs_tableau) *needs_tableau = (k == 0 || !(flags & SDIMB_FRESH) || (flags & SDIMB_WRITEBACK)) ? 1 : 0;   // k = 3 keeps its image in scratch
+  if (needs_tableau) *needs_tableau = (k == 0 || k == 4 || !(flags & SDIMB_FRESH) || (flags & SDIMB_WRITEBACK)) ? 1 : 0;   // k = 3 keeps its image in scratch
   return SDIMB_OK;
 }
 

@@ -21,16 +21,16 @@ def shard_range(shots: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def gather_records(local, shots: int, n_meas: int, group=None):
-    """all_gather the per-rank [local_shots, n_meas] uint8 tensors into [shots, n_meas] on every rank."""
+    """all_gather the per-rank [local_shots, n_meas] record tensors (uint8; int16 bits for d > 127) into [shots, n_meas] on every rank."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     if world == 1:
         return local
     per = -(-shots // world)                         # ceil: ranks pad to a common size
-    padded = torch.zeros((per, n_meas), dtype=torch.uint8, device=local.device)
+    padded = torch.zeros((per, n_meas), dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
-    out = torch.empty((world * per, n_meas), dtype=torch.uint8, device=local.device)
+    out = torch.empty((world * per, n_meas), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     pieces = []
     for r in range(world):

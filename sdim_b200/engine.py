@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import records as R
 from .ir import CompiledProgram
 
 
@@ -65,6 +66,7 @@ class TableauEngine:
         self._scratch: Dict[tuple, torch.Tensor] = {}   # per (mode flags, tail-run shots): counter, images, slabs
         self.tableau: Optional[torch.Tensor] = None     # uint8 [shots, shot_bytes] of the last run that kept it
         self.tableau_shots = 0
+        self.rec_dtype = R.torch_dtype(prog.dimension)   # packed records / replay arrays: uint8, int16 bits for d > 127
 
     # ------------------------------------------------------------------------------------------
     def plan(self, mode: Optional[str] = None, fresh: bool = True, keep_tableau: bool = False):
@@ -118,7 +120,8 @@ class TableauEngine:
             replay_meas: Optional[torch.Tensor] = None, replay_noise: Optional[torch.Tensor] = None,
             keep_tableau: bool = False, mode: Optional[str] = None,
             tableau: Optional[torch.Tensor] = None, fresh: bool = True,
-            op_range: Optional[tuple] = None, records: Optional[torch.Tensor] = None) -> torch.Tensor:
+            op_range: Optional[tuple] = None, records: Optional[torch.Tensor] = None,
+            time_kernels: bool = False) -> torch.Tensor:
         """Simulate local shots [0, shots) with global ids shot_offset + local; returns records on device.
 
         replay_meas  uint8[shots, n_meas]      outcome to use where measurement k is random (else Philox)
@@ -137,6 +140,8 @@ class TableauEngine:
         use_sched = wants_layers and op_range is None and self.ops_sched is not None
         if use_sched:
             flags |= N.SCHEDULED
+        if time_kernels:
+            flags |= N.TIME_KERNELS       # per-kernel events, read with _native.kernel_times()
         with torch.cuda.device(dev):
             if need_tab:
                 if tableau is None:
@@ -144,13 +149,15 @@ class TableauEngine:
                 if tableau.shape != (shots, L.shot_bytes) or tableau.dtype != torch.uint8 or not tableau.is_contiguous():
                     raise ValueError("tableau buffer has the wrong shape/dtype for this program")
             if records is None:
-                records = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device=dev)
+                records = torch.empty((shots, prog.n_meas), dtype=self.rec_dtype, device=dev)
+            elif records.dtype != self.rec_dtype:
+                raise ValueError(f"records buffer must be {self.rec_dtype} for dimension {prog.dimension}")
             if replay_meas is not None:
-                replay_meas = replay_meas.to(device=dev, dtype=torch.uint8).contiguous()
+                replay_meas = replay_meas.to(device=dev, dtype=self.rec_dtype).contiguous()
                 if replay_meas.shape != (shots, prog.n_meas):
                     raise ValueError("replay_meas must be [shots, n_meas]")
             if replay_noise is not None:
-                replay_noise = replay_noise.to(device=dev, dtype=torch.uint8).contiguous()
+                replay_noise = replay_noise.to(device=dev, dtype=self.rec_dtype).contiguous()
                 if replay_noise.shape != (shots, prog.n_noise, 2):
                     raise ValueError("replay_noise must be [shots, n_noise, 2]")
             lo, hi = (0, prog.n_ops) if op_range is None else op_range
@@ -239,11 +246,12 @@ def simulate_host(prog: CompiledProgram, shots: int, shot_offset: int = 0, seed:
     """Host-buffer entry (sdimb_simulate_host): numpy in, numpy records out, plus device ms of the call."""
     lib = N.lib()
     ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
-    rec = np.empty((shots, prog.n_meas), dtype=np.uint8)
+    rdt = R.np_dtype(prog.dimension)
+    rec = np.empty((shots, prog.n_meas), dtype=rdt)
     thr = np.ascontiguousarray(prog.noise_thresh24, dtype=np.uint32)
     ch = np.ascontiguousarray(prog.noise_channel, dtype=np.uint8)
-    rm = None if replay_meas is None else np.ascontiguousarray(replay_meas, dtype=np.uint8)
-    rn = None if replay_noise is None else np.ascontiguousarray(replay_noise, dtype=np.uint8)
+    rm = None if replay_meas is None else np.ascontiguousarray(replay_meas, dtype=rdt)
+    rn = None if replay_noise is None else np.ascontiguousarray(replay_noise, dtype=rdt)
     ms = C.c_float(0.0)
 
     def p(arr):

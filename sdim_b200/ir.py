@@ -26,7 +26,7 @@ from .circuit import Circuit
 from .gatedata import (MEASURE_OPS, NUM_OPS, OP_I, OP_N1, TWO_QUDIT_OPS)
 from .rng import CHANNEL_CODES, prob_to_thresh24
 
-MAX_DIMENSION = 127        # uint8 lanes: a + b < 256 for reduced a, b
+MAX_DIMENSION = 32749      # largest prime below 2^15: uint8 lanes up to 127, uint16 lanes above (csrc/wide.cuh)
 
 
 def is_prime(d: int) -> bool:

@@ -22,6 +22,7 @@ from typing import List, Optional
 
 import numpy as np
 
+from . import records as R
 from .circuit import Circuit, CircuitInstruction
 from .gatedata import MEASURE_OPS, OP_RESET
 from .ir import MAX_DIMENSION, CompiledProgram, compile_circuits, is_prime
@@ -58,7 +59,7 @@ class SimulationOptions:
 class RecordTable:
     """Packed result of a run: one row per shot, one column per chronological measurement."""
 
-    values: np.ndarray          # uint8 [shots, n_meas]
+    values: np.ndarray          # uint8 [shots, n_meas] (uint16 for d > 127)
     deterministic: np.ndarray   # bool  [shots, n_meas]
     meas_qudit: np.ndarray      # int32 [n_meas]
     meas_round: np.ndarray      # int32 [n_meas]
@@ -120,7 +121,7 @@ class Program:
             raise ValueError(f"dimension {d} is not prime: only the prime-dimension (ExtendedTableau) path of the "
                              "reference is implemented; composite dimensions (WeylTableau) are out of scope")
         if d > MAX_DIMENSION:
-            raise ValueError(f"dimension {d} exceeds the uint8-lane limit of {MAX_DIMENSION}")
+            raise ValueError(f"dimension {d} exceeds the uint16-lane limit of {MAX_DIMENSION}")
         self.circuits: List[Circuit] = [circuit]
         self.measurement_results: list = []
         self.device = device
@@ -209,7 +210,7 @@ class Program:
                                    replay_meas=replay_meas, replay_noise=replay_noise)
         else:
             rec = self._run_local(compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split=True)
-        values, det = rec if isinstance(rec, tuple) else (rec & 0x7F, (rec & 0x80) != 0)
+        values, det = rec if isinstance(rec, tuple) else R.split(rec)
         table = RecordTable(values=values, deterministic=det,
                             meas_qudit=compiled.meas_qudit, meas_round=compiled.meas_round,
                             seed=seed, shot_offset=shot_offset)
@@ -220,6 +221,8 @@ class Program:
         import torch
         engine = self._get_engine(compiled)
         # reference shot: N1 is the identity there (sdim/program.py:31,245-247)
+        if compiled.dimension >= R.WIDE_MIN_DIMENSION:
+            raise ValueError("method='frame' supports dimensions up to 127; larger primes run the tableau path")
         quiet = torch.zeros((1, compiled.n_noise, 2), dtype=torch.uint8) if compiled.n_noise else None
         store = self._initial_store(engine, 1)
         if store is None:
@@ -245,20 +248,21 @@ class Program:
         tensor (the sharded path gathers them over NCCL from there); waves then only bound the HBM tableau store."""
         import torch
         engine = self._get_engine(compiled)
-        rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
-        rn = None if replay_noise is None else torch.as_tensor(np.asarray(replay_noise, dtype=np.uint8))
+        rdt, tdt = R.np_dtype(compiled.dimension), R.torch_dtype(compiled.dimension)
+        rm = None if replay_meas is None else R.to_device(replay_meas, compiled.dimension)
+        rn = None if replay_noise is None else R.to_device(replay_noise, compiled.dimension)
         # Shots run in waves sized to the device: a run that needs one HBM tableau per shot (uint8 lanes in global
         # mode, or a user-supplied initial tableau) must fit next to the records; resident kernels take any count.
         _, need_tab = engine.plan(mode, fresh=self.initial_tableau is None)
         wave = shots
         if need_tab and shots > 0:
             free_bytes, _total = torch.cuda.mem_get_info(engine.device)
-            per_shot = engine.layout.shot_bytes + 3 * compiled.n_meas + 2 * compiled.n_noise
+            per_shot = engine.layout.shot_bytes + (3 * compiled.n_meas + 2 * compiled.n_noise) * np.dtype(rdt).itemsize
             wave = max(1, min(shots, int(0.6 * free_bytes) // max(per_shot, 1)))
         elif shots > 0:
-            wave = max(1, min(shots, self.WAVE_RECORD_BYTES // max(compiled.n_meas, 1)))
+            wave = max(1, min(shots, self.WAVE_RECORD_BYTES // max(compiled.n_meas * np.dtype(rdt).itemsize, 1)))
         if on_device:
-            full = torch.empty((shots, compiled.n_meas), dtype=torch.uint8, device=engine.device)
+            full = torch.empty((shots, compiled.n_meas), dtype=tdt, device=engine.device)
             step = max(wave, 1) if need_tab else max(shots, 1)
             for lo in range(0, shots, step):
                 hi = min(shots, lo + step)
@@ -269,13 +273,15 @@ class Program:
                 del store
             self._set_last_shot_thunk(compiled, engine, shots, shot_offset, seed, rm, rn, mode)
             return full
-        out = np.empty((shots, compiled.n_meas), dtype=np.uint8)
+        out = np.empty((shots, compiled.n_meas), dtype=rdt)
         det = np.empty((shots, compiled.n_meas), dtype=bool) if split else None
+        det_bit, val_mask = R.masks(rdt)
 
         def deliver(lo, hi, packed):
+            packed = R.unsigned(packed)
             if split:
-                np.bitwise_and(packed, 0x7F, out=out[lo:hi])
-                np.not_equal(packed & 0x80, 0, out=det[lo:hi])
+                np.bitwise_and(packed, rdt(val_mask), out=out[lo:hi])
+                np.not_equal(packed & rdt(det_bit), 0, out=det[lo:hi])
             else:
                 out[lo:hi] = packed
 
@@ -292,8 +298,8 @@ class Program:
             dev = engine.device
             with torch.cuda.device(dev):
                 compute, copier = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
-                recs = [torch.empty((wave, compiled.n_meas), dtype=torch.uint8, device=dev) for _ in range(2)]
-                pins = [torch.empty((wave, compiled.n_meas), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+                recs = [torch.empty((wave, compiled.n_meas), dtype=tdt, device=dev) for _ in range(2)]
+                pins = [torch.empty((wave, compiled.n_meas), dtype=tdt, pin_memory=True) for _ in range(2)]
                 copied = [None, None]                            # (event, lo, hi) of the copy in flight per buffer
 
                 def collect(slot):
@@ -392,9 +398,9 @@ class Program:
         shots = options.shots
         if seed is None:
             seed = random.getrandbits(63)
-        rm = None if replay_meas is None else torch.as_tensor(np.asarray(replay_meas, dtype=np.uint8))
-        rn = None if replay_noise is None else torch.as_tensor(np.asarray(replay_noise, dtype=np.uint8))
-        values = np.zeros((shots, compiled.n_meas), dtype=np.uint8)
+        rm = None if replay_meas is None else R.to_device(replay_meas, compiled.dimension)
+        rn = None if replay_noise is None else R.to_device(replay_noise, compiled.dimension)
+        values = np.zeros((shots, compiled.n_meas), dtype=R.np_dtype(compiled.dimension))
         det = np.zeros((shots, compiled.n_meas), dtype=bool)
         snaps = [[None] * compiled.n_meas for _ in range(shots)] if options.record_tableau else None
         user_ops = [op for c in self.circuits for op in c.operations if op.gate_id != 0]
@@ -405,7 +411,7 @@ class Program:
             if store is None:
                 store = engine.alloc_tableau(1)
                 engine.init_tableau(store)
-            rec = torch.zeros((1, compiled.n_meas), dtype=torch.uint8, device=engine.device)
+            rec = torch.zeros((1, compiled.n_meas), dtype=R.torch_dtype(compiled.dimension), device=engine.device)
             srm = None if rm is None else rm[s:s + 1]
             srn = None if rn is None else rn[s:s + 1]
             if options.verbose:
@@ -422,7 +428,7 @@ class Program:
                         # The reference snapshots right after measure(), before the RESET correction
                         # (program.py:323-324 precede :335-339); the device op does both, so the correction's
                         # phase update is taken back out of the exported copy.
-                        outcome = int(rec[0, slot].item()) & 0x7F
+                        outcome = int(R.split(rec[0, slot:slot + 1].cpu().numpy())[0][0])
                         arrays = undo_reset_correction(arrays, int(compiled.ops[i][1]), outcome, compiled.dimension)
                     snaps[s][slot] = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, arrays)
                 if options.show_gate:
@@ -433,8 +439,7 @@ class Program:
                     ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
                                                 engine.export(store, 0)).print_tableau()
                     print("\n")
-            r = rec.cpu().numpy()[0]
-            values[s], det[s] = r & 0x7F, (r & 0x80) != 0
+            values[s], det[s] = R.split(rec.cpu().numpy()[0])
             last = store
         if last is not None:
             self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
@@ -458,12 +463,12 @@ class Program:
         out = None
         arrays = engine.export(store, 0)
         if compiled.n_meas:
-            r = int(rec.cpu().numpy()[0, 0])
-            out = MeasurementResult(int(compiled.meas_qudit[0]), bool(r & 0x80), r & 0x7F)
+            rv, rd = R.split(rec.cpu().numpy()[0, :1])
+            out = MeasurementResult(int(compiled.meas_qudit[0]), bool(rd[0]), int(rv[0]))
             if instruc.gate_id == OP_RESET:
                 # the reference's apply_reset only measures (tableau_gates.py:331-346); the X correction belongs to
                 # its shot loop (program.py:335-339).  The device op does both, so the correction is taken back out.
-                arrays = undo_reset_correction(arrays, int(compiled.meas_qudit[0]), r & 0x7F, compiled.dimension)
+                arrays = undo_reset_correction(arrays, int(compiled.meas_qudit[0]), int(rv[0]), compiled.dimension)
         self.stabilizer_tableau = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, arrays)
         return out
 

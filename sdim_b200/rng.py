@@ -73,7 +73,7 @@ def measurement_draws(seed: int, d: int, shot_ids, n_meas: int) -> np.ndarray:
     shot_ids = np.asarray(shot_ids, dtype=np.uint64).reshape(-1, 1)
     slots = np.arange(n_meas, dtype=np.uint64).reshape(1, -1)
     w0 = _words(seed, shot_ids, slots, STREAM_MEAS)[0].astype(np.uint64)
-    return ((w0 * np.uint64(d)) >> _S32).astype(np.uint8)
+    return ((w0 * np.uint64(d)) >> _S32).astype(np.uint16 if d > 127 else np.uint8)
 
 
 def noise_draws(seed: int, d: int, shot_ids, thresh24, channel) -> np.ndarray:
@@ -90,7 +90,7 @@ def noise_draws(seed: int, d: int, shot_ids, thresh24, channel) -> np.ndarray:
     a = np.where(channel == CHANNEL_D, r % np.uint64(d), np.where(channel == CHANNEL_F, e, 0))
     b = np.where(channel == CHANNEL_D, r // np.uint64(d), np.where(channel == CHANNEL_P, e, 0))
     out = np.stack((np.where(fire, a, 0), np.where(fire, b, 0)), axis=-1)
-    return out.astype(np.uint8)
+    return out.astype(np.uint16 if d > 127 else np.uint8)
 
 
 def frame_z0_draws(seed: int, d: int, shot_ids, n: int) -> np.ndarray:

@@ -169,10 +169,11 @@ class ExtendedTableau(Tableau):
                    destab_phase_vector=arrays["dp"], destab_z_block=arrays["dz"], destab_x_block=arrays["dx"])
 
     def pack(self, np_pad: int) -> np.ndarray:
-        """uint8 image of this tableau in the device layout of include/sdimb.h (one shot)."""
+        """Byte image of this tableau in the device layout of include/sdimb.h (one shot): uint8 entries, uint16 for
+        d > 127."""
         n, d, o = self.num_qudits, self.dimension, self.order
         W = 2 * np_pad
-        img = np.zeros((2 * n + 1, W), dtype=np.uint8)
+        img = np.zeros((2 * n + 1, W), dtype=np.uint16 if d > 127 else np.uint8)
         rows = img[: 2 * n].reshape(n, 2, W)
         rows[:, 0, :n] = np.asarray(self.x_block) % d
         rows[:, 1, :n] = np.asarray(self.z_block) % d
@@ -180,4 +181,4 @@ class ExtendedTableau(Tableau):
         rows[:, 1, np_pad:np_pad + n] = np.asarray(self.destab_z_block) % d
         img[2 * n, :n] = np.asarray(self.phase_vector) % o
         img[2 * n, np_pad:np_pad + n] = np.asarray(self.destab_phase_vector) % o
-        return img.reshape(-1)
+        return img.reshape(-1).view(np.uint8)

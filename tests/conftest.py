@@ -62,6 +62,13 @@ def golden_large_primes():
 
 
 @pytest.fixture(scope="session")
+def golden_wide_primes():
+    """tests/golden/wide_primes.json (oracle/make_golden.py --wide): d in {131, 251, 257, 1031, 32749}."""
+    with open(os.path.join(GOLDEN_DIR, "wide_primes.json")) as fh:
+        return json.load(fh)["cases"]
+
+
+@pytest.fixture(scope="session")
 def golden_config_sizes():
     """tests/golden/config_sizes.npz (oracle/make_golden.py --configs): one shot of the UNMODIFIED reference per
     BASELINE.json config size.  -> list of dicts (name, n, d, ops, noise_ab, records, final)."""

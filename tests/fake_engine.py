@@ -8,6 +8,7 @@ import torch
 
 from oracle.tableau_oracle import OracleTableau, run_shot
 from sdim_b200 import _native as N
+from sdim_b200 import records as R
 from oracle.frame_oracle import simulate_frames
 from sdim_b200.rng import frame_z0_draws, frame_zm_draws, measurement_draws, noise_draws
 from sdim_b200.tableau import ExtendedTableau
@@ -16,7 +17,10 @@ from sdim_b200.tableau import ExtendedTableau
 def unpack(img: np.ndarray, n: int, d: int, np_pad: int) -> OracleTableau:
     """Inverse of ExtendedTableau.pack: device image of one shot (include/sdimb.h) -> oracle tableau."""
     W = 2 * np_pad
-    img = np.asarray(img, dtype=np.int64).reshape(2 * n + 1, W)
+    img = np.ascontiguousarray(img)
+    if d > 127:
+        img = img.view(np.uint16)                       # uint16 lanes: two bytes per entry
+    img = img.astype(np.int64).reshape(2 * n + 1, W)
     rows = img[: 2 * n].reshape(n, 2, W)
     t = OracleTableau(n, d)
     t.x, t.z = rows[:, 0, :n].copy(), rows[:, 1, :n].copy()
@@ -36,6 +40,7 @@ class FakeEngine:
         self.prog, self.device = prog, torch.device("cpu")
         self.layout = N.layout(prog.num_qudits, prog.dimension)
         self.tableau, self.tableau_shots = None, 0
+        self.rec_dtype = R.torch_dtype(prog.dimension)
         self.runs = []                                   # (shots, op_range, n_ops) of every call, for assertions
 
     def plan(self, mode=None, fresh=True, keep_tableau=False):
@@ -54,21 +59,23 @@ class FakeEngine:
         lo, hi = (0, prog.n_ops) if op_range is None else op_range
         self.runs.append((shots, op_range, prog.n_ops))
         if records is None:
-            records = torch.zeros((shots, prog.n_meas), dtype=torch.uint8)
+            records = torch.zeros((shots, prog.n_meas), dtype=self.rec_dtype)
+        det_bit, val_mask = R.masks(R.np_dtype(d))
         if (not fresh or keep_tableau) and tableau is None:
             tableau = self.alloc_tableau(shots)
         for s in range(shots):
             gid = shot_offset + s
-            md = replay_meas[s].numpy() if replay_meas is not None else measurement_draws(seed, d, [gid], prog.n_meas)[0]
+            md = R.unsigned(replay_meas[s].numpy()) if replay_meas is not None else measurement_draws(seed, d, [gid], prog.n_meas)[0]
             nd = None
             if prog.n_noise:
-                nd = replay_noise[s].numpy() if replay_noise is not None else \
+                nd = R.unsigned(replay_noise[s].numpy()) if replay_noise is not None else \
                     noise_draws(seed, d, [gid], prog.noise_thresh24, prog.noise_channel)[0]
             start = None if fresh else unpack(tableau[s].numpy(), n, d, self.layout.np)
             recs, t = run_shot(n, d, prog.ops[lo:hi], lambda k: int(md[k]), nd, tableau=start)
             slots = [int(o[3]) for o in prog.ops[lo:hi] if int(o[0]) in (14, 15, 16)]
             for slot, (_, det, m) in zip(slots, recs):
-                records[s, slot] = (m & 0x7F) | (0x80 if det else 0)
+                v = (m & val_mask) | (det_bit if det else 0)
+                records[s, slot] = v - 0x10000 if v >= 0x8000 else v        # int16 bits of a uint16 record
             if keep_tableau:
                 tableau[s] = torch.from_numpy(pack(t, self.layout.np))
         if keep_tableau:

@@ -25,7 +25,7 @@ def test_library_exists_and_exports_every_declared_symbol():
     assert set(declared) == set(N.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sdimb_version() == 2
+    assert lib.sdimb_version() == 3
 
 
 def test_layout_matches_header_contract():
@@ -40,8 +40,18 @@ def test_layout_matches_header_contract():
     assert L.shot_bytes == 4096 * 16384 + 8192                   # 64 MiB + 8 KiB
 
 
+def test_layout_of_the_uint16_lanes():
+    """127 < d < 2^15: two bytes per entry and per record, everything else as the uint8 store."""
+    a, b = N.layout(20, 127), N.layout(20, 131)
+    assert (a.elem_bytes, a.rec_bytes, b.elem_bytes, b.rec_bytes) == (1, 1, 2, 2)
+    assert (b.np, b.lanes, b.order, b.phase_order) == (a.np, a.lanes, 131, 1)
+    assert (b.row_bytes, b.phase_offset, b.shot_bytes) == (2 * a.row_bytes, 2 * a.phase_offset, 2 * a.shot_bytes)
+    assert N.plan(20, 131, 0) == (4, True) and N.KERNEL_NAMES[4] == "lanes16-global"
+    assert N.layout(3, 32749).order == 32749
+
+
 def test_error_codes_map_to_value_errors():
-    for n, d in ((4, 4), (4, 1), (4, 128), (4, 131), (0, 3)):
+    for n, d in ((4, 4), (4, 1), (4, 128), (4, 32771), (4, 32767), (20000, 131), (0, 3)):
         with pytest.raises(ValueError):
             N.layout(n, d)
     lib = N.lib()
@@ -136,7 +146,7 @@ def test_host_entry_validates_before_touching_cuda():
     assert call(4, 3, [[9, 1, 7, -1]]) == N.EOP
     assert call(4, 3, [[14, 0, -1, 3]], n_meas=1) == N.EOP              # record slot out of range
     assert call(4, 3, [[17, 0, -1, 0]], n_noise=0) == N.EOP             # noise slot out of range
-    assert call(4, 4, [[5, 0, -1, -1]]) == N.EDIM and call(4, 131, [[5, 0, -1, -1]]) == N.EDIM
+    assert call(4, 4, [[5, 0, -1, -1]]) == N.EDIM and call(4, 32771, [[5, 0, -1, -1]]) == N.EDIM
     assert call(0, 3, [[5, 0, -1, -1]]) == N.EINVAL and call(4, 3, [[5, 0, -1, -1]], shots=-1) == N.EINVAL
     assert call(4, 3, [[17, 0, -1, 0]], n_noise=1) == N.EINVAL          # Philox mode without noise tables
     assert call(4, 3, [[5, 0, -1, -1]], shots=0) == N.OK                # nothing to do

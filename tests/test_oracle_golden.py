@@ -73,6 +73,31 @@ def test_oracles_match_reference_goldens_at_large_primes(golden_large_primes):
                 assert np.array_equal(fin[key], np.array(case["final"][key])), (case["seed"], key)
 
 
+def test_oracles_match_reference_goldens_above_127(golden_wide_primes):
+    """d in {131, 251, 257, 1031, 32749}: the dimensions of the uint16-lane store (records and replay arrays are
+    uint16 there, bit 15 = deterministic).  Both restatements against the unmodified reference
+    (`oracle/make_golden.py --wide`); the GPU tests of csrc/wide.cuh compare with these goldens and the C oracle."""
+    assert {c["d"] for c in golden_wide_primes} == {131, 251, 257, 1031, 32749} and len(golden_wide_primes) >= 55
+    assert sum(1 for c in golden_wide_primes for r in c["records"] if not r[1]) > 80
+    assert max(r[2] for c in golden_wide_primes for r in c["records"]) > 255        # values that need the second byte
+    for case in golden_wide_primes:
+        draws = [r[2] for r in case["records"]]
+        noise64 = np.array(case["noise_ab"], dtype=np.int64).reshape(-1, 2)
+        recs, t = run_shot(case["n"], case["d"], case["ops"], lambda k: draws[k], noise64)
+        assert recs == [(q, bool(det), m) for q, det, m in case["records"]], case["seed"]
+        for key, arr in zip(KEYS, t.arrays()):
+            assert np.array_equal(arr, np.array(case["final"][key])), (case["seed"], key)
+        want = np.array([(m & 0x7FFF) | (0x8000 if det else 0) for _, det, m in case["records"]], dtype=np.uint16)
+        packed, _ = run_shots(case["n"], case["d"], case["ops"], 1, np.array(draws)[None, :], noise64[None])
+        assert packed.dtype == np.uint16 and np.array_equal(packed[0], want), case["seed"]
+        if c_oracle.available():
+            rec, fin = c_oracle.run(case["n"], case["d"], case["ops"], 1, replay_meas=(want & 0x7FFF)[None, :],
+                                    replay_noise=noise64.astype(np.uint16).reshape(1, -1, 2), want_final=True)
+            assert rec.dtype == np.uint16 and np.array_equal(rec[0], want), case["seed"]
+            for key in KEYS:
+                assert np.array_equal(fin[key], np.array(case["final"][key])), (case["seed"], key)
+
+
 def test_oracles_match_reference_goldens_at_config_sizes(golden_config_sizes):
     """One reference shot per BASELINE.json config size — config 2 (n = 64, d = 3), the distance-7 surface code
     (n = 97, d = 2), the distance-25 qutrit repetition code (n = 49), the headline (n = 256, d = 3; N1 events = shot 0

@@ -35,7 +35,7 @@ def same_tableau(got: ExtendedTableau, oracle_tableau):
         assert np.array_equal(getattr(got, key), want), key
 
 
-@pytest.mark.parametrize("d", [2, 3, 5])
+@pytest.mark.parametrize("d", [2, 3, 5, 257])
 def test_simulate_shapes_grouping_and_last_tableau(d):
     circ = random_circuit(31 + d, 5, d, 70)
     prog = compile_circuits([circ])
@@ -60,18 +60,19 @@ def test_simulate_shapes_grouping_and_last_tableau(d):
     assert P.measurement_results is nested
 
 
-def test_record_tableau_snapshots_including_reset(capsys):
-    circ = random_circuit(77, 4, 3, 60, p_meas=0.2)
+@pytest.mark.parametrize("d", [3, 257])
+def test_record_tableau_snapshots_including_reset(capsys, d):
+    circ = random_circuit(77, 4, d, 60, p_meas=0.2)
     prog = compile_circuits([circ])
     assert 16 in prog.meas_opcode                            # the circuit has RESETs
     res = Program(circ).simulate(shots=2, record_tableau=True, seed=5)
     for s in range(2):
-        md = measurement_draws(5, 3, [s], prog.n_meas)[0]
-        nd = noise_draws(5, 3, [s], prog.noise_thresh24, prog.noise_channel)[0]
+        md = measurement_draws(5, d, [s], prog.n_meas)[0]
+        nd = noise_draws(5, d, [s], prog.noise_thresh24, prog.noise_channel)[0]
         seen, t = {}, None
         for i, (op, a, b, slot) in enumerate(prog.ops.tolist()):
             # RESET: run its measurement only — the snapshot sits between measure() and the correction
-            _, t = run_shot(4, 3, [[14 if op == 16 else op, a, b, slot]], lambda k: int(md[k]), nd, tableau=t)
+            _, t = run_shot(4, d, [[14 if op == 16 else op, a, b, slot]], lambda k: int(md[k]), nd, tableau=t)
             snap_want = [arr.copy() for arr in t.arrays()]
             if op in (14, 15, 16):
                 r = seen.get(a, 0)
@@ -81,7 +82,7 @@ def test_record_tableau_snapshots_including_reset(capsys):
                 for key, want in zip(KEYS, snap_want):
                     assert np.array_equal(getattr(snap, key), want), (s, i, key)
                 if op == 16:                                 # now the correction, to carry on
-                    t.pauli(a, (-got.measurement_value) % 3, 0)
+                    t.pauli(a, (-got.measurement_value) % d, 0)
 
 
 def test_verbose_and_show_gate_step_every_op(capsys):
@@ -132,14 +133,15 @@ def test_apply_gate_and_initial_tableau():
         Program(Circuit(3, 3), tableau=t0).simulate()        # tableau / circuit size mismatch
 
 
-def test_replayed_draws_and_record_table_columns():
-    circ = random_circuit(5, 4, 3, 50)
+@pytest.mark.parametrize("d", [3, 1031])
+def test_replayed_draws_and_record_table_columns(d):
+    circ = random_circuit(5, 4, d, 50)
     prog = compile_circuits([circ])
-    rm = np.random.default_rng(0).integers(0, 3, size=(3, prog.n_meas)).astype(np.uint8)
-    rn = np.zeros((3, prog.n_noise, 2), dtype=np.uint8)
+    rm = np.random.default_rng(0).integers(0, d, size=(3, prog.n_meas)).astype(np.uint16 if d > 127 else np.uint8)
+    rn = np.zeros((3, prog.n_noise, 2), dtype=rm.dtype)
     table = Program(circ).simulate_records(3, seed=1, replay_meas=rm, replay_noise=rn)
     for s in range(3):
-        recs, _ = run_shot(4, 3, prog.ops, lambda k: int(rm[s, k]), rn[s])
+        recs, _ = run_shot(4, d, prog.ops, lambda k: int(rm[s, k]), rn[s])
         assert [(m, det) for _, det, m in recs] == list(zip(table.values[s].tolist(), table.deterministic[s].tolist()))
     assert table.column(int(prog.meas_qudit[-1]), int(prog.meas_round[-1])) == prog.n_meas - 1
     with pytest.raises(ValueError):
