@@ -104,6 +104,8 @@ enum {
 #define SDIMB_CLUSTER 0x80u        /* HBM store: run one shot per thread-block cluster whatever n and shots are
                                       (default: only for n > 512 with fewer shots than clusters fit on the GPU) */
 #define SDIMB_NO_CLUSTER 0x100u    /* HBM store: never use the cluster interpreter */
+#define SDIMB_NO_TILE 0x400u       /* d = 2, 3 with n <= 128: one shot per warp (interp_planes_kernel) instead of the tile
+                                      interpreter with several shots per warp (tests, A/B timings) */
 #define SDIMB_TIME_KERNELS 0x200u  /* measurement aid: a call that runs two kernels (interpreter + tail run) records CUDA
                                       events around each on `stream`; sdimb_kernel_times reads them (one set per
                                       process, not for concurrent callers) */
@@ -227,7 +229,8 @@ int64_t sdimb_tail_run(const int32_t* ops, int64_t n_ops);
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store (one CTA or
  * one thread-block cluster per shot, chosen per call from n and shots), 1 uint8 lanes resident in shared memory,
  * 2 bit-plane resident (d = 2, 3), 3 bit planes on a global image held in SdimbRunArgs.scratch (d = 2, 3 beyond
- * the shared-memory limit), 4 uint16 lanes on the HBM store (d > 127); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for these flags. */
+ * the shared-memory limit), 4 uint16 lanes on the HBM store (d > 127), 5 bit planes resident with several shots per
+ * warp (d = 2, 3, n <= 128; sdim_b200/csrc/planes_tile.cuh); *needs_tableau = whether SdimbRunArgs.tableau must be a valid store for these flags. */
 int sdimb_plan(int n, int d, uint32_t flags, int* kernel, int* needs_tableau);
 
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */

@@ -8,9 +8,10 @@ from .build import LIB_PATH
 
 OK, EINVAL, EDIM, EOP, ECUDA, ETOOBIG = 0, -1, -2, -3, -4, -5
 FRESH, WRITEBACK, FORCE_GLOBAL, FORCE_RESIDENT, FORCE_LANES, FORCE_PLANES = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
-SCHEDULED, CLUSTER, NO_CLUSTER, TIME_KERNELS = 0x40, 0x80, 0x100, 0x200
+SCHEDULED, CLUSTER, NO_CLUSTER, TIME_KERNELS, NO_TILE = 0x40, 0x80, 0x100, 0x200, 0x400
 OP_BARRIER = 18
-KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident", 3: "planes-global", 4: "lanes16-global"}
+KERNEL_NAMES = {0: "lanes-global", 1: "lanes-resident", 2: "planes-resident", 3: "planes-global", 4: "lanes16-global",
+                5: "planes-tile"}
 REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",

@@ -98,4 +98,5 @@ struct KParams {
   int64_t tail_start;          // run_tail_kernel: index of the first op of the run (ops [tail_start, n_ops) are M ops)
   uint32_t* gm_slab;           // run_tail_kernel: one B + QX slab per resident warp
   int64_t gm_slab_words;
+  int64_t tile_stride_words;   // interp_tile_kernel: words between the shared-memory images of two tiles
 };

@@ -70,6 +70,13 @@ size_t scratch_bytes(int np) {
   return 4 * W + W + 32 * 4 + 4 * 4 + 32 * 16 + 4 * (size_t)np + 2 * (W / 4) + 2 * (size_t)np + 128;
 }
 
+// rows of at most 8 lane words and a warp's tiles in shared memory: the tile interpreter's shapes.  The environment
+// variable SDIMB_NO_TILE (developer knob, A/B timings) sends them back to one shot per warp.
+bool tile_shape_ok(int n, int d) {
+  static const bool off = std::getenv("SDIMB_NO_TILE") != nullptr;
+  return !off && (d == 2 || d == 3) && n <= 128 && planes::tile_smem_bytes(n, d) <= (size_t)kSmemLimit;
+}
+
 // Which interpreter a (n, d, flags) call runs: 0 = uint8 lanes in global memory, 1 = uint8 lanes resident in
 // shared memory, 2 = bit-plane resident (d = 2, 3), 3 = bit planes on a global image in caller scratch (d = 2, 3
 // when the planes do not fit in shared memory, or FORCE_PLANES | FORCE_GLOBAL).  Negative = error code.
@@ -89,6 +96,10 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
   if ((flags & SDIMB_FORCE_PLANES) && !planes_fit) return SDIMB_ETOOBIG;
   if ((flags & SDIMB_FORCE_RESIDENT) && !fits) return SDIMB_ETOOBIG;
   const bool free_choice = !(flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES | SDIMB_CLUSTER));
+  // small tableaus (rows of at most 8 lane words, n <= 128): several shots per warp (planes_tile.cuh)
+  if (planes_ok && tile_shape_ok(n, d) && !(flags & SDIMB_NO_TILE) &&
+      (free_choice || ((flags & SDIMB_FORCE_PLANES) && !(flags & SDIMB_FORCE_GLOBAL))))
+    return 5;
   if (free_choice && !(flags & SDIMB_FORCE_PLANES) && planes_ok) {
     // Shared memory holds few large images: at 3 or fewer resident CTAs per SM the same interpreter on an L2 image
     // with 8 CTAs per SM is faster (d = 3: n = 224 +19 %, 256 +22 %; d = 2: n = 320 +21 %, 400 +52 %); at 4 it is a
@@ -102,6 +113,13 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
   return (fits && !(flags & SDIMB_FORCE_GLOBAL)) ? 1 : 0;
 }
 
+// The tile interpreter (planes_tile.cuh): kernel for (d, lanes per shot).
+using PlaneKernel = void (*)(const KParams);
+PlaneKernel tile_kernel_for(int n, int d) {
+  if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4> : planes::interp_tile_kernel<3, 4>;
+  return (d == 2) ? planes::interp_tile_kernel<2, 8> : planes::interp_tile_kernel<3, 8>;
+}
+
 // The global-image plane interpreter for (d, interleaved image or not): see SDIMB_PG_IL_MIN_NP in planes.cuh.
 // The environment variable of the same name moves the threshold (tests run the goldens through both images).
 bool planes_interleaved(int n) {
@@ -109,7 +127,6 @@ bool planes_interleaved(int n) {
   if (const char* env = std::getenv("SDIMB_PG_IL_MIN_NP")) min_np = std::atoi(env);
   return (n + 31) / 32 * 32 >= min_np;
 }
-using PlaneKernel = void (*)(const KParams);
 PlaneKernel planes_gates_only_kernel(int d, bool il) {
   if (il) return (d == 2) ? planes::interp_planes_kernel<2, true, true, true> : planes::interp_planes_kernel<3, true, true, true>;
   return (d == 2) ? planes::interp_planes_kernel<2, true, false, true> : planes::interp_planes_kernel<3, true, false, true>;
@@ -318,7 +335,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
   const int kernel = plan_kernel(a->n, a->d, a->flags, L.np);
   if (kernel < 0) return kernel;
   const size_t scratch = scratch_bytes(L.np);
-  const bool use_planes = kernel == 2, resident = kernel >= 1;   // 3 keeps its image in scratch: no store needed either
+  const bool use_planes = kernel == 2, resident = kernel >= 1;   // 3 keeps its image in scratch, 5 in shared memory: no store needed either
   const bool need_tab = !resident || kernel == 4 || !(a->flags & SDIMB_FRESH) || (a->flags & SDIMB_WRITEBACK);
   if (need_tab && !a->tableau) return SDIMB_EINVAL;
 
@@ -347,6 +364,27 @@ int sdimb_run(const SdimbRunArgs* caller) {
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
+  if (kernel == 5) {     // bit planes, several shots per warp: one-warp CTAs, 32 / LPS shots claimed at a time
+    auto kern = tile_kernel_for(a->n, a->d);
+    const size_t smem = planes::tile_smem_bytes(a->n, a->d);
+    const int tpw = 32 / planes::tile_lps(a->n);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      return SDIMB_ECUDA;
+    }
+    int64_t grid = (int64_t)sms * per_sm;
+    const int64_t groups = (a->shots + tpw - 1) / tpw;
+    if (grid > groups) grid = groups;
+    if (a->scratch && a->scratch_bytes >= (int64_t)sizeof(unsigned int)) {   // dynamic shot claiming
+      p.shot_counter = (unsigned int*)a->scratch;
+      if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
+    }
+    p.tile_stride_words = (int64_t)planes::tile_stride_words(a->n, a->d);
+    kern<<<(unsigned)grid, 32, smem, (cudaStream_t)a->stream>>>(p);
+    g_launches++;
+    return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
+  }
   if (kernel == 4) {     // uint16 lanes, one CTA per shot on the HBM store
     const size_t smem = wide::smem_bytes(L.np);
     auto kern = wide::interp_wide16_kernel;
@@ -605,7 +643,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   if (shots == 0) return SDIMB_OK;
 
   uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES |
-                                 SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER);
+                                 SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER | SDIMB_NO_TILE);
   int kernel = plan_kernel(n, d, mode_flags, L.np);
   if (kernel < 0) return kernel;
   // A few shots of a d = 2, 3 tableau too large for shared memory: one uint8 tableau per thread-block cluster beats
@@ -854,7 +892,7 @@ int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags) {
   SdimbLayout L;
   if (sdimb_layout(n, d, &L)) return 0;
   const int k = plan_kernel(n, d, flags, L.np);
-  if (k == 2) return 256;   // the shot counter
+  if (k == 2 || k == 5) return 256;   // the shot counter
   if (k == 3) {             // the shot counter + one image per CTA the device keeps resident (148 x 8 without a device)
     int ctas = planes_global_ctas(n, d, nullptr);
     if (ctas < 1) ctas = 148 * 8;

@@ -41,6 +41,7 @@ class TableauEngine:
     # large tableaus with few shots; "cluster" / "global-cta" pin that choice (tests, A/B timings).
     MODES = {None: 0, "auto": 0, "global": N.FORCE_GLOBAL, "resident": N.FORCE_RESIDENT, "lanes": N.FORCE_LANES,
              "planes": N.FORCE_PLANES, "planes-global": N.FORCE_PLANES | N.FORCE_GLOBAL,
+             "planes-warp": N.FORCE_PLANES | N.NO_TILE,      # one shot per warp even where the tile interpreter fits
              "cluster": N.FORCE_GLOBAL | N.CLUSTER, "global-cta": N.FORCE_GLOBAL | N.NO_CLUSTER}
 
     def __init__(self, prog: CompiledProgram, device=None):

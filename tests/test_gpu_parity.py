@@ -14,7 +14,7 @@ def _engine(n, d, ops):
     return prog, TableauEngine(prog)
 
 
-@pytest.mark.parametrize("mode", ["resident", "global", "planes", "cluster", "planes-global"])
+@pytest.mark.parametrize("mode", ["resident", "global", "planes", "planes-warp", "cluster", "planes-global"])
 def test_golden_random_circuits_replay(golden_random, mode):
     """Every reference golden case: records AND all six final arrays, bit-exact, under replayed draws."""
     import torch
@@ -44,7 +44,7 @@ def test_golden_random_circuits_replay(golden_random, mode):
     assert checked >= 40
 
 
-@pytest.mark.parametrize("mode", [None, "resident", "global", "planes", "planes-global", "cluster"])
+@pytest.mark.parametrize("mode", [None, "resident", "global", "planes", "planes-warp", "planes-global", "cluster"])
 def test_golden_config_sizes_replay(golden_config_sizes, mode):
     """Outputs of the UNMODIFIED reference at the BASELINE.json config sizes (config 2 n = 64, surface code n = 97,
     repetition code n = 49, headline n = 256): records and all six final arrays in every kernel that can hold the
@@ -104,7 +104,7 @@ def _run_gpu(prog, shots, seed, mode=None, shot_offset=0, keep=False):
 
 @pytest.mark.parametrize("d,n,depth", [(2, 5, 120), (2, 40, 900), (2, 97, 2500), (3, 1, 30), (3, 17, 500), (3, 64, 1500), (3, 100, 2500),
                                         (5, 33, 800), (7, 16, 400), (11, 9, 300), (13, 21, 500), (127, 6, 200)])
-@pytest.mark.parametrize("mode", ["resident", "global", "planes", "planes-global"])
+@pytest.mark.parametrize("mode", ["resident", "global", "planes", "planes-warp", "planes-global"])
 def test_philox_mode_matches_c_oracle(d, n, depth, mode):
     """Every opcode incl. M_X, RESET, SWAP and all three noise channels; ragged n (not a multiple of 16)."""
     from make_cases import random_program

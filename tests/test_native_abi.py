@@ -105,9 +105,13 @@ def test_kernel_selection_rule_without_a_gpu():
     names = {k: N.KERNEL_NAMES[N.plan(*k, fresh)[0]] for k in
              ((64, 3), (160, 3), (200, 3), (224, 3), (256, 3), (500, 3), (97, 2), (290, 2), (320, 2), (700, 2),
               (64, 5), (200, 7), (256, 5), (4096, 7), (6, 127))}
-    assert names[(64, 3)] == names[(160, 3)] == names[(200, 3)] == "planes-resident"
+    assert names[(64, 3)] == "planes-tile" and N.KERNEL_NAMES[N.plan(49, 3, fresh)[0]] == "planes-tile"     # n <= 128: several shots per warp
+    assert N.KERNEL_NAMES[N.plan(64, 3, fresh | N.NO_TILE)[0]] == "planes-resident"
+    assert N.KERNEL_NAMES[N.plan(128, 2, fresh | N.FORCE_PLANES)[0]] == "planes-tile"
+    assert N.KERNEL_NAMES[N.plan(129, 2, fresh | N.FORCE_PLANES)[0]] == "planes-resident"
+    assert names[(160, 3)] == names[(200, 3)] == "planes-resident"
     assert names[(224, 3)] == names[(256, 3)] == names[(500, 3)] == "planes-global"
-    assert names[(97, 2)] == names[(290, 2)] == "planes-resident"
+    assert names[(97, 2)] == "planes-tile" and names[(290, 2)] == "planes-resident"
     assert names[(320, 2)] == names[(700, 2)] == "planes-global"
     assert names[(64, 5)] == names[(200, 7)] == names[(6, 127)] == "lanes-resident"
     assert names[(256, 5)] == names[(4096, 7)] == "lanes-global"

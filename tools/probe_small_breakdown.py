@@ -20,24 +20,30 @@ def strip(circ, drop):
     return out
 
 
+MODE = sys.argv[1] if len(sys.argv) > 1 else None          # e.g. planes (tile interpreter where it fits) / planes-warp
+
+
 def timeit(prog, shots, reps=3):
     eng = TableauEngine(prog)
     rec = torch.empty((shots, prog.n_meas), dtype=torch.uint8, device="cuda")
     for _ in range(2):
-        eng.run(shots, 0, 1, records=rec)
+        eng.run(shots, 0, 1, records=rec, mode=MODE)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        eng.run(shots, 0, 1, records=rec)
+        eng.run(shots, 0, 1, records=rec, mode=MODE)
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
 
-cases = [("config 2 random Clifford d=3 n=64", generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1), 10000),
+cases = [("config 2 random Clifford d=3 n=64", generate_random_clifford_circuit(64, 2000, 3, measurement_rounds=1, seed=1), 100000),
          ("config 3 surface code d=2 distance 7", rotated_surface_code(7, 7, prob=1e-3), 200000),
          ("config 4 qutrit repetition code", qudit_repetition_code(25, 25, 3, prob=1e-2), 200000)]
+only = sys.argv[2] if len(sys.argv) > 2 else ""
 for name, circ, shots in cases:
+    if only and only not in name:
+        continue
     full = compile_circuits([circ])
     gates = compile_circuits([strip(circ, {"M", "M_X", "RESET", "N1"})])
     nonoise = compile_circuits([strip(circ, {"N1"})])
