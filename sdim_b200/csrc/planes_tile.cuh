@@ -176,13 +176,27 @@ struct TW {
 
 // Measurement of qudit q by every tile of the warp at once.  `on` lanes (j < Wb) own a lane word; ph is this lane's
 // phase word.  All lanes of the warp must call it together.
-template <int D, int LPS>
-__device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G, const int q, const uint32_t draw, E& ph) {
+//
+// UNI: every shot of the batch started from |0...0> (SDIMB_FRESH).  The X / Z blocks of a tableau do not depend on
+// measurement outcomes or Pauli noise — gates act on them linearly, a random measurement picks its pivot and its row
+// operations from the X block alone, Paulis (N1, the RESET correction) touch phases only — so the tiles of the warp hold
+// IDENTICAL X / Z images and differ in their phase words only.  Everything a measurement READS from the X / Z blocks
+// without writing (the pivot-column walk and its lists, the row pass of a deterministic measurement) is then done
+// ONCE per warp, by all 32 lanes on the image of tile 0 (G0), instead of once per tile by LPS lanes; every tile still
+// applies the row operations to its own image and its own phases.
+template <int D, int LPS, bool UNI, class DRAW>
+__device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G, const TImg<D>& G0, const int q,
+                                              const DRAW& draw_fn, E& ph) {
   constexpr uint32_t PO = (D == 2) ? 2u : 1u, ORDER = D * PO, FULL = 0xFFFFFFFFu;
   constexpr int WQM = LPS / 2;                                           // most stabilizer lane words a tile can have
+  constexpr int WL = UNI ? 32 : LPS;                                     // lanes that share one walk
   const int j = T.lane, Wb = G.Wb, Wq = G.Wq, n = G.n;
   const bool on = j < Wb;
-  const uint32_t lt = (1u << j) - 1u;
+  const TImg<D>& W = UNI ? G0 : G;                                       // image the walks read; its scratch holds their lists
+  const int wj = UNI ? (int)(threadIdx.x & 31) : j;
+  const uint32_t lt = (1u << wj) - 1u;
+  auto wballot = [&](bool pr) -> uint32_t { return UNI ? __ballot_sync(FULL, pr) : T.ballot(pr); };
+  auto wsum = [&](uint32_t v) -> uint32_t { return UNI ? __reduce_add_sync(FULL, v) : T.sum(v); };
   E xq{0u, 0u};
   if (on) xq = G.ld(q, j).x;
   const uint32_t nz = xq.l | xq.h;
@@ -192,6 +206,7 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
   uint32_t rec = 0;
   if (__any_sync(FULL, rnd)) {
     // ---- random branch (tableau_prime.py:294-334, exponentiate :365-380 folded in); tiles with !rnd idle through it ----
+    const uint32_t draw = draw_fn();        // replayed or Philox: only a random measurement consumes it
     const int jp = rnd ? (int)(piv >> 5) : 0, bp = piv & 31, jd = Wq + jp;
     const uint32_t e = (D == 3) ? bit2(E{T.shfl(xq.l, jp), T.shfl(xq.h, jp)}, bp) : 1u;   // inverse of v mod 3 is v
     const uint32_t ps_old = bit2(E{T.shfl(ph.l, jp), T.shfl(ph.h, jp)}, bp);
@@ -199,31 +214,31 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
     uint32_t sd_part = 0;
     int na = 0, nb = 0;
     // (two steps' loads are issued together: the list stores between them would otherwise order the loads)
-    for (int base = 0; base < n; base += 2 * LPS) {
+    for (int base = 0; base < n; base += 2 * WL) {
       uint32_t xr[2], zr[2], od[2];
       XZ s[2], dd[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int r = base + u * LPS + j;
+        const int r = base + u * WL + wj;
         s[u] = dd[u] = XZ{E{0u, 0u}, E{0u, 0u}};
-        if (r < n && rnd) { s[u] = G.ld(r, jp); dd[u] = G.ld(r, jd); }
+        if (r < n && rnd) { s[u] = W.ld(r, jp); dd[u] = W.ld(r, jd); }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int r = base + u * LPS + j;
+        const int r = base + u * WL + wj;
         od[u] = ((dd[u].x.l | dd[u].x.h | dd[u].z.l | dd[u].z.h) >> bp) & 1u;
         xr[u] = bit2(s[u].x, bp); zr[u] = bit2(s[u].z, bp);
         sd_part += xr[u] * zr[u];
         if (D == 3 && e == 2u) { xr[u] = (xr[u] >> 1) | ((xr[u] & 1u) << 1); zr[u] = (zr[u] >> 1) | ((zr[u] & 1u) << 1); }   // * 2 = negate
         const bool act = (xr[u] | zr[u]) != 0, stale = !act && od[u] != 0;
-        const uint32_t ma = T.ballot(act), mb = T.ballot(stale);
-        if (act) G.ar[na + __popc(ma & lt)] = (uint16_t)((uint32_t)r | (xr[u] << 12) | (zr[u] << 14));
-        if (stale) G.br[nb + __popc(mb & lt)] = (uint16_t)r;
+        const uint32_t ma = wballot(act), mb = wballot(stale);
+        if (act) W.ar[na + __popc(ma & lt)] = (uint16_t)((uint32_t)r | (xr[u] << 12) | (zr[u] << 14));
+        if (stale) W.br[nb + __popc(mb & lt)] = (uint16_t)r;
         na += __popc(ma);
         nb += __popc(mb);
       }
     }
-    const uint32_t sd_raw = T.sum(sd_part) % D;
+    const uint32_t sd_raw = wsum(sd_part) % D;
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
     T.sync();
@@ -243,7 +258,7 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         act[u] = work && k0 + u < na;
-        ent[u] = act[u] ? (uint32_t)G.ar[k0 + u] : 0u;
+        ent[u] = act[u] ? (uint32_t)W.ar[k0 + u] : 0u;
         v[u] = XZ{E{0u, 0u}, E{0u, 0u}};
         if (act[u]) v[u] = G.ld(ent[u] & 0xFFFu, j);
       }
@@ -267,7 +282,7 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
     }
     if (fixd) {            // rows outside the support: clear their stale destabilizer-p entry
       for (int k = 0; k < nb; ++k) {
-        const int r = G.br[k];
+        const int r = W.br[k];
         XZ dd = G.ld(r, jd);
         dd.x = setbit2(dd.x, bp, 0u);
         dd.z = setbit2(dd.z, bp, 0u);
@@ -322,39 +337,45 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
     // rows over the tile's lanes; a row on which every listed generator is the identity (the usual case: stabilizers
     // of a code act on a few qudits) costs its loads and one test
     uint32_t part = 0;
-    const int rows_w = (n + LPS - 1) / LPS;
-    for (int it = 0; it < rows_w; ++it) {
-      const int r = it * LPS + j;
-      if (r >= n || total == 0) continue;
-      XZ v[WQM];
-      uint32_t hit = 0;
+    constexpr int RU = 4;                                                // rows per lane whose loads are in flight together
+    for (int r0 = wj; r0 < n && total != 0; r0 += RU * WL) {
+      XZ v[RU][WQM];
+      uint32_t hit[RU];
 #pragma unroll
-      for (int w = 0; w < WQM; ++w) {
-        v[w] = XZ{E{0u, 0u}, E{0u, 0u}};
-        if (w < Wq && mw[w]) {
-          v[w] = G.ld(r, w);
-          hit |= (v[w].x.l | v[w].x.h | v[w].z.l | v[w].z.h) & mw[w];
+      for (int u = 0; u < RU; ++u) {
+        const int r = r0 + u * WL;
+        hit[u] = 0;
+#pragma unroll
+        for (int w = 0; w < WQM; ++w) {
+          v[u][w] = XZ{E{0u, 0u}, E{0u, 0u}};
+          if (r < n && w < Wq && mw[w]) {
+            v[u][w] = W.ld(r, w);
+            hit[u] |= (v[u][w].x.l | v[u][w].x.h | v[u][w].z.l | v[u][w].z.h) & mw[w];
+          }
         }
       }
-      if (!hit) continue;
-      uint32_t az = 0, cross = 0, sdg = 0;
-      for (int k = 0; k < total; ++k) {
-        const uint32_t ent = G.ar[k];
-        const int g = ent & 0xFFFu, w = g >> 5, b = g & 31;
-        const uint32_t fv = ent >> 12;
-        XZ vv = v[0];
 #pragma unroll
-        for (int u = 1; u < WQM; ++u) if (w == u) vv = v[u];
-        if ((((vv.x.l | vv.x.h | vv.z.l | vv.z.h) >> b) & 1u) == 0u) continue;    // generator g is the identity on row r
-        const uint32_t xi = bit2(vv.x, b), zi = bit2(vv.z, b);
-        cross += (fv * xi) * az;                                         // ancilla_z . (f * x_i), running ancilla
-        az = (az + fv * zi) % D;
-        sdg += xi * zi * ((fv * (fv - 1u)) >> 1);
-        if ((k & 15) == 15) { cross %= D; sdg %= D; }
+      for (int u = 0; u < RU; ++u) {
+        if (!hit[u]) continue;
+        uint32_t az = 0, cross = 0, sdg = 0;
+        for (int k = 0; k < total; ++k) {
+          const uint32_t ent = G.ar[k];
+          const int g = ent & 0xFFFu, w = g >> 5, b = g & 31;
+          const uint32_t fv = ent >> 12;
+          XZ vv = v[u][0];
+#pragma unroll
+          for (int x = 1; x < WQM; ++x) if (w == x) vv = v[u][x];
+          if ((((vv.x.l | vv.x.h | vv.z.l | vv.z.h) >> b) & 1u) == 0u) continue;    // generator g is the identity on this row
+          const uint32_t xi = bit2(vv.x, b), zi = bit2(vv.z, b);
+          cross += (fv * xi) * az;                                       // ancilla_z . (f * x_i), running ancilla
+          az = (az + fv * zi) % D;
+          sdg += xi * zi * ((fv * (fv - 1u)) >> 1);
+          if ((k & 15) == 15) { cross %= D; sdg %= D; }
+        }
+        part += (cross + PO * sdg) % D;
       }
-      part += (cross + PO * sdg) % D;
     }
-    part = T.sum(part);
+    part = wsum(part);
     const uint32_t ap = (a1 + PO * (part % D)) % ORDER;
     const uint32_t outcome = (D == 3) ? (3u - ap) % 3u : (((ap + 1u) >> 1) & 1u);   // (-ap // po) % d  (:362)
     if (det) rec = outcome | SDIMB_REC_DET;
@@ -363,7 +384,7 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
   return rec;
 }
 
-template <int D, int LPS>
+template <int D, int LPS, bool UNI>
 __global__ void __launch_bounds__(32) interp_tile_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TPW = 32 / LPS, EW = TImg<D>::EW;
@@ -381,6 +402,10 @@ __global__ void __launch_bounds__(32) interp_tile_kernel(const __grid_constant__
   G.tab = sm + (size_t)tw * p.tile_stride_words;
   G.ar = reinterpret_cast<uint16_t*>(G.tab + img_words);
   G.br = G.ar + G.np;
+  TImg<D> G0 = G;                                                        // tile 0 of the warp (UNI: the image the walks read)
+  G0.tab = sm;
+  G0.ar = reinterpret_cast<uint16_t*>(G0.tab + img_words);
+  G0.br = G0.ar + G.np;
   uint32_t* const evs = sm + (size_t)TPW * p.tile_stride_words;          // [32] packed N1 events of the current batch
   const bool on = j < G.Wb;
   const int jj = on ? j : 0;                                             // idle lanes of a tile (Wb < LPS) shadow word 0, never store
@@ -483,17 +508,15 @@ __global__ void __launch_bounds__(32) interp_tile_kernel(const __grid_constant__
             if (on) t_gate<D>(G, jj, SDIMB_OP_H_INV, a, 0, 0u, 0u, ph);   // tableau_gates.py:292-296
             T.sync();
           }
-          uint32_t draw;                // outcome this measurement takes if it is random
-          if (p.replay_meas) {
-            draw = p.replay_meas[shot * p.n_meas + slot];
-          } else {
+          auto draw_fn = [&]() -> uint32_t {      // outcome this measurement takes if it is random
+            if (p.replay_meas) return p.replay_meas[shot * p.n_meas + slot];
             const uint64_t gshot = (uint64_t)(p.shot_offset + shot);
             const uint4 r = philox4x32((uint32_t)gshot, (uint32_t)(gshot >> 32), (uint32_t)slot, 0u, (uint32_t)p.seed,
                                        (uint32_t)(p.seed >> 32));
-            draw = __umulhi(r.x, (uint32_t)D);
-          }
+            return __umulhi(r.x, (uint32_t)D);
+          };
           T.sync();                     // gates of this tile's lanes in front of the measurement
-          const uint32_t rec = t_measure<D, LPS>(T, G, a, draw, ph);
+          const uint32_t rec = t_measure<D, LPS, UNI>(T, G, G0, a, draw_fn, ph);
           if (j == 0 && real) p.records[shot * p.rec_stride + slot] = (uint8_t)rec;
           const uint32_t m = rec & SDIMB_REC_VALUE;
           if (code == SDIMB_OP_RESET && m && on) t_gate<D>(G, jj, SDIMB_OP_N1, a, 0, D - m, 0u, ph);   // program.py:335-339

@@ -115,9 +115,14 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
 
 // The tile interpreter (planes_tile.cuh): kernel for (d, lanes per shot).
 using PlaneKernel = void (*)(const KParams);
-PlaneKernel tile_kernel_for(int n, int d) {
-  if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4> : planes::interp_tile_kernel<3, 4>;
-  return (d == 2) ? planes::interp_tile_kernel<2, 8> : planes::interp_tile_kernel<3, 8>;
+// uni: every shot starts from |0...0> (SDIMB_FRESH): the tiles of a warp hold identical X / Z blocks, see t_measure
+PlaneKernel tile_kernel_for(int n, int d, bool uni) {
+  if (uni) {
+    if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4, true> : planes::interp_tile_kernel<3, 4, true>;
+    return (d == 2) ? planes::interp_tile_kernel<2, 8, true> : planes::interp_tile_kernel<3, 8, true>;
+  }
+  if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4, false> : planes::interp_tile_kernel<3, 4, false>;
+  return (d == 2) ? planes::interp_tile_kernel<2, 8, false> : planes::interp_tile_kernel<3, 8, false>;
 }
 
 // The global-image plane interpreter for (d, interleaved image or not): see SDIMB_PG_IL_MIN_NP in planes.cuh.
@@ -365,7 +370,8 @@ int sdimb_run(const SdimbRunArgs* caller) {
   if (cudaGetDevice(&dev) != cudaSuccess) return SDIMB_ECUDA;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
   if (kernel == 5) {     // bit planes, several shots per warp: one-warp CTAs, 32 / LPS shots claimed at a time
-    auto kern = tile_kernel_for(a->n, a->d);
+    const bool no_uni = std::getenv("SDIMB_TILE_NO_UNI") != nullptr;            // developer knob (tests, A/B timings)
+    auto kern = tile_kernel_for(a->n, a->d, (a->flags & SDIMB_FRESH) && !no_uni);
     const size_t smem = planes::tile_smem_bytes(a->n, a->d);
     const int tpw = 32 / planes::tile_lps(a->n);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||

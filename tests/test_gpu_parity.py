@@ -124,6 +124,51 @@ def test_philox_mode_matches_c_oracle(d, n, depth, mode):
         assert len({got[s].tobytes() for s in range(shots)}) > 1    # noise/draws really differ between shots
 
 
+@pytest.mark.parametrize("uni", [True, False])
+def test_tile_interpreter_both_measurement_forms(golden_random, golden_config_sizes, monkeypatch, uni):
+    """The tile interpreter (several shots per warp, n <= 128) with its measurement walks shared by the warp (fresh
+    batches: identical X / Z blocks in every tile) and per tile (SDIMB_TILE_NO_UNI, the form non-fresh runs take):
+    reference goldens incl. final tableaus, the config-size goldens that fit, and free-running shots that differ in
+    noise and outcomes against the C oracle — with shot counts that leave tiles of the last warp empty."""
+    import torch
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    if not uni:
+        monkeypatch.setenv("SDIMB_TILE_NO_UNI", "1")
+    checked = 0
+    cases = [c for c in golden_random if c["d"] <= 3] + [c for c in golden_config_sizes if c["n"] <= 128]
+    for case in cases:
+        n, d = case["n"], case["d"]
+        ops = case["ops"].tolist() if hasattr(case["ops"], "tolist") else case["ops"]
+        prog = compile_circuits([circuit_from_ops(n, d, ops)])
+        eng = TableauEngine(prog)
+        assert eng.plan("planes")[0] == "planes-tile"
+        want = np.array([(int(m) & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+        shots = 11
+        rm = torch.from_numpy(np.tile((want & 0x7F)[None, :], (shots, 1)))
+        noise = np.array(case["noise_ab"], dtype=np.uint8).reshape(-1, 2)
+        rn = torch.from_numpy(np.tile(noise[None], (shots, 1, 1))) if prog.n_noise else None
+        got = eng.run(shots, 0, 77, rm, rn, keep_tableau=True, mode="planes").cpu().numpy()
+        assert all(np.array_equal(got[s], want) for s in range(shots)), (n, d)
+        arrs = eng.export(eng.tableau, shots - 1)
+        for key in ("x", "z", "p", "dx", "dz", "dp"):
+            assert np.array_equal(arrs[key], np.array(case["final"][key])), (n, d, key)
+        checked += 1
+    assert checked >= 45
+    for d, n, depth, shots in ((2, 97, 2500, 37), (3, 49, 2000, 1001), (3, 64, 1500, 13), (2, 128, 1200, 9), (3, 5, 200, 3), (2, 33, 700, 50)):
+        prog = random_program(seed=31 * d + n, n=n, d=d, depth=depth)
+        eng = TableauEngine(prog)
+        got = eng.run(shots, 3, 99, mode="planes", keep_tableau=True).cpu().numpy()
+        want, fin = c_oracle.run(n, d, prog.ops, shots, 3, 99, thresh24=prog.noise_thresh24, channel=prog.noise_channel,
+                                 want_final=True)
+        assert np.array_equal(got, want), (d, n)
+        arrs = eng.export(eng.tableau, shots - 1)
+        for key in ("x", "z", "p", "dx", "dz", "dp"):
+            assert np.array_equal(arrs[key], fin[key]), (d, n, key)
+
+
 def test_noise_cache_refill_many_events():
     """More N1 events than one shared-memory noise chunk (1024), interleaved with measurements."""
     from make_cases import random_program
