@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SDIMB_VERSION 3
+#define SDIMB_VERSION 4
 
 enum {
   SDIMB_OK = 0,
@@ -146,6 +146,11 @@ typedef struct SdimbRunArgs {
                                     WRITEBACK the global-image bit-plane interpreter hands that run to a second kernel
                                     (one warp per shot on a generator-major image, sdim_b200/csrc/planes_gm.cuh).
                                     Callers built against the struct without this field are accepted (struct_size). */
+  const int32_t* gate_stream;    /* [device] nullable: output of sdimb_gate_stream for the ops in FRONT of the tail run */
+  int64_t gate_stream_rows;      /* (ops [0, n_ops - tail_run_len) of the same scheduled stream) and its row count.  When
+                                    the two-kernel path above applies and every measurement sits in the tail run, the
+                                    front part then runs as pre-decoded per-warp streams (sdim_b200/csrc/planes_stream.cuh)
+                                    instead of being interpreted.  Callers without these two fields are accepted. */
 } SdimbRunArgs;
 
 int sdimb_version(void);
@@ -225,6 +230,17 @@ int64_t sdimb_scratch_bytes_shots(int n, int d, uint32_t flags, int64_t shots);
 
 /* Length of the marked run of M ops (SDIMB_GM_*) that ends a scheduled HOST stream, 0 if it does not end in one. */
 int64_t sdimb_tail_run(const int32_t* ops, int64_t n_ops);
+
+/* Host-side compiler (no GPU work) of a gate-only stretch of a SCHEDULED stream — rows [0, n_ops) of sdimb_schedule's
+ * output, holding unitary gates, N1 and SDIMB_OP_BARRIER only — into the pre-decoded per-warp streams of
+ * gate_stream_kernel (sdim_b200/csrc/planes_stream.cuh): per layer, gates of one family on disjoint qudits are packed
+ * 32 / Wb to a warp-wide op, N1 events move to a table evaluated once per shot.  d = 2, 3 and n <= 512 only
+ * (SDIMB_EINVAL otherwise, or if the stretch holds a measurement, or more than 65 536 N1 ops: the caller then simply
+ * passes no gate stream).  Call with out = NULL to learn the row count (*out_rows; rows are 4 x int32), then again
+ * with room for it.  Replaces nothing in the reference, whose loop interprets one gate at a time
+ * (sdim/program.py:311-312, GATE_FUNCTIONS sdim/program.py:13-32). */
+int sdimb_gate_stream(int n, int d, const int32_t* sched_ops, int64_t n_ops, int32_t* out, int64_t out_cap_rows,
+                      int64_t* out_rows);
 
 /* Which interpreter sdimb_run would use for (n, d, flags): *kernel = 0 uint8 lanes on the HBM store (one CTA or
  * one thread-block cluster per shot, chosen per call from n and shots), 1 uint8 lanes resident in shared memory,

@@ -16,7 +16,7 @@ REC_DET, REC_VALUE = 0x80, 0x7F
 
 EXPORTED_SYMBOLS = ("sdimb_version", "sdimb_strerror", "sdimb_layout", "sdimb_init", "sdimb_run",
                     "sdimb_export", "sdimb_simulate_host", "sdimb_launch_count", "sdimb_plan", "sdimb_schedule", "sdimb_release_workspace", "sdimb_frames", "sdimb_scratch_bytes", "sdimb_cluster_size",
-                    "sdimb_scratch_bytes_shots", "sdimb_tail_run", "sdimb_kernel_times")
+                    "sdimb_scratch_bytes_shots", "sdimb_tail_run", "sdimb_kernel_times", "sdimb_gate_stream")
 
 
 class SdimbLayout(C.Structure):
@@ -33,7 +33,7 @@ class SdimbRunArgs(C.Structure):
                 ("rec_stride", C.c_int64), ("replay_meas", C.c_void_p), ("replay_noise", C.c_void_p),
                 ("noise_thresh24", C.c_void_p), ("noise_channel", C.c_void_p), ("n_noise", C.c_int64),
                 ("seed", C.c_uint64), ("stream", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
-                ("tail_run_len", C.c_int64)]
+                ("tail_run_len", C.c_int64), ("gate_stream", C.c_void_p), ("gate_stream_rows", C.c_int64)]
 
 
 class NativeError(RuntimeError):
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.sdimb_scratch_bytes_shots.restype = C.c_int64
     L.sdimb_tail_run.argtypes = [C.c_void_p, C.c_int64]
     L.sdimb_tail_run.restype = C.c_int64
+    L.sdimb_gate_stream.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.sdimb_kernel_times.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.sdimb_cluster_size.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_uint32]
     L.sdimb_plan.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -123,6 +124,20 @@ def kernel_times():
     if lib().sdimb_kernel_times(C.byref(a), C.byref(b)) != OK:
         return None
     return float(a.value), float(b.value)
+
+
+def gate_stream(n: int, d: int, sched_front):
+    """Pre-decoded per-warp streams (sdimb_gate_stream) of a gate-only stretch of a scheduled stream, int32[rows, 4];
+    None when the library does not compile this shape (d > 3, n > 512, a measurement in the stretch)."""
+    import numpy as np
+    sched_front = np.ascontiguousarray(sched_front, dtype=np.int32).reshape(-1, 4)
+    ptr = sched_front.ctypes.data if sched_front.size else None
+    rows = C.c_int64(0)
+    if lib().sdimb_gate_stream(n, d, ptr, sched_front.shape[0], None, 0, C.byref(rows)) != OK or rows.value <= 0:
+        return None
+    out = np.empty((rows.value, 4), dtype=np.int32)
+    check(lib().sdimb_gate_stream(n, d, ptr, sched_front.shape[0], out.ctypes.data, out.shape[0], C.byref(rows)))
+    return out
 
 
 def tail_run(sched) -> int:

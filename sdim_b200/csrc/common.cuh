@@ -99,4 +99,5 @@ struct KParams {
   uint32_t* gm_slab;           // run_tail_kernel: one B + QX slab per resident warp
   int64_t gm_slab_words;
   int64_t tile_stride_words;   // interp_tile_kernel: words between the shared-memory images of two tiles
+  const int32_t* gate_stream;  // gate_stream_kernel: pre-decoded per-warp streams (sdimb_gate_stream, planes_stream.cuh)
 };

@@ -851,6 +851,7 @@ inline size_t planes_img_stride_words(int n, int d) {
 }
 
 #include "planes_gm.cuh"
+#include "planes_stream.cuh"
 #include "planes_tile.cuh"
 
 }  // namespace planes

@@ -202,6 +202,39 @@ size_t tail_run_scratch_bytes(int n, int d, int64_t shots, int run_ctas) {
          (size_t)run_ctas * (planes::kRunThreads / planes::run_lps(n)) * 4 * planes::run_slab_words(n, d);
 }
 
+// Gate-stream kernel (planes_stream.cuh) for the gates in front of a tail run: image in shared memory when one image,
+// the accumulators of the widest launch and the largest fired-bit table fit (a rule of the shape alone, so that
+// sdimb_gate_stream and sdimb_run agree), else on the per-shot global image.  SDIMB_GS_GLOBAL / SDIMB_GS_WARPS /
+// SDIMB_NO_GATE_STREAM are developer knobs (A/B timings, tests of both forms).
+bool gate_stream_shape_ok(int n, int d) {
+  const bool off = std::getenv("SDIMB_NO_GATE_STREAM") != nullptr;
+  return !off && (d == 2 || d == 3) && planes::gate_stream_gpw(n) >= 1;
+}
+size_t gate_stream_img_bytes(int n, int d) {
+  const size_t EW = (d == 2) ? 2 : 4, np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32;
+  return 4 * (((size_t)n * EW * (Wb + (planes_interleaved(n) ? 0 : 1)) + 3) & ~(size_t)3);
+}
+bool gate_stream_in_smem(int n, int d) {
+  const bool force_global = std::getenv("SDIMB_GS_GLOBAL") != nullptr;
+  return !force_global && gate_stream_img_bytes(n, d) + 8 * 32 * planes::kGateStreamMaxWarps + planes::kGateStreamMaxNoise / 8 + 16 <=
+                              (size_t)kSmemLimit;
+}
+int gate_stream_warps(int n, int d) {
+  if (!gate_stream_in_smem(n, d)) return SDIMB_SCHED_WARPS;     // the global-image form is compiled for 4-warp CTAs
+  int nw = 8;
+  if (const char* env = std::getenv("SDIMB_GS_WARPS")) nw = std::atoi(env);
+  return nw < 1 ? 1 : nw > planes::kGateStreamMaxWarps ? planes::kGateStreamMaxWarps : nw;
+}
+PlaneKernel gate_stream_kernel_for(int n, int d) {
+  const bool il = planes_interleaved(n);
+  if (gate_stream_in_smem(n, d)) {
+    if (il) return (d == 2) ? planes::gate_stream_kernel<2, true, true> : planes::gate_stream_kernel<3, true, true>;
+    return (d == 2) ? planes::gate_stream_kernel<2, false, true> : planes::gate_stream_kernel<3, false, true>;
+  }
+  if (il) return (d == 2) ? planes::gate_stream_kernel<2, true, false> : planes::gate_stream_kernel<3, true, false>;
+  return (d == 2) ? planes::gate_stream_kernel<2, false, false> : planes::gate_stream_kernel<3, false, false>;
+}
+
 // Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
 // one CTA per shot.  By default only tableaus with rows wider than one 256-thread CTA (n > 512), and the largest
 // cluster size (16 = the non-portable maximum, then 8, 4, 2) of which the GPU can keep one per shot resident at the
@@ -319,8 +352,9 @@ int sdimb_init(void* tableau, int n, int d, int64_t shots, void* stream) {
 }
 
 int sdimb_run(const SdimbRunArgs* caller) {
-  // version 1 callers pass the struct without its last field (tail_run_len)
-  if (!caller || (caller->struct_size != sizeof(SdimbRunArgs) && caller->struct_size != offsetof(SdimbRunArgs, tail_run_len)))
+  // older callers pass the struct without its last fields (tail_run_len; gate_stream, gate_stream_rows)
+  if (!caller || (caller->struct_size != sizeof(SdimbRunArgs) && caller->struct_size != offsetof(SdimbRunArgs, tail_run_len) &&
+                  caller->struct_size != offsetof(SdimbRunArgs, gate_stream)))
     return SDIMB_EINVAL;
   SdimbRunArgs args;
   std::memset(&args, 0, sizeof(args));
@@ -452,10 +486,28 @@ int sdimb_run(const SdimbRunArgs* caller) {
         }
         grid1 = (int64_t)sms * per_sm < a->shots ? (int64_t)sms * per_sm : a->shots;
       }
+      // ... and as pre-decoded per-warp streams when the caller compiled them (sdimb_gate_stream)
+      int threads1 = 32 * SDIMB_SCHED_WARPS;
+      if (a->n_meas == tail && a->gate_stream && a->gate_stream_rows > 0 && gate_stream_shape_ok(a->n, a->d)) {
+        kern = gate_stream_kernel_for(a->n, a->d);
+        const int nw = gate_stream_warps(a->n, a->d);
+        threads1 = 32 * nw;
+        smem = planes::gate_stream_smem_bytes(a->n, a->n_noise, nw) + (gate_stream_in_smem(a->n, a->d) ? gate_stream_img_bytes(a->n, a->d) : 0);
+        int per_sm = 0, sms = 0, dev = 0;
+        if (smem > (size_t)kSmemLimit || cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads1, smem) != cudaSuccess || per_sm < 1) {
+          cudaGetLastError();
+          return SDIMB_ECUDA;
+        }
+        grid1 = (int64_t)sms * per_sm < a->shots ? (int64_t)sms * per_sm : a->shots;
+        p1.gate_stream = a->gate_stream;
+      }
       const bool timed = (a->flags & SDIMB_TIME_KERNELS) && time_events_ready();
       g_time_valid = 0;
       if (timed) cudaEventRecord(g_time_ev[0], (cudaStream_t)a->stream);
-      kern<<<(unsigned)grid1, 32 * SDIMB_SCHED_WARPS, smem, (cudaStream_t)a->stream>>>(p1);
+      kern<<<(unsigned)grid1, threads1, smem, (cudaStream_t)a->stream>>>(p1);
       g_launches++;
       if (cudaGetLastError() != cudaSuccess) return SDIMB_ECUDA;
       if (timed) cudaEventRecord(g_time_ev[1], (cudaStream_t)a->stream);
@@ -683,8 +735,25 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
   const size_t b_tab = (kernel == 0 || kernel == 4) ? align256((size_t)shots * L.shot_bytes) : 0;
   const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
+  // the gates in front of a tail run that holds every measurement: pre-decoded per-warp streams (planes_stream.cuh);
+  // that two-kernel path also beats the shared-memory interpreter where it fits (TableauEngine._auto_mode)
+  std::vector<int32_t> gstream;
+  int64_t gs_rows = 0;
+  if (kernel == 2 && mode_flags == 0 && tail_len > 0 && tail_len == n_meas && gate_stream_shape_ok(n, d) && tail_run_shape_ok(n, d) &&
+      plan_kernel(n, d, SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL, L.np) == 3) {
+    mode_flags = SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL;
+    kernel = 3;
+  }
+  if (kernel == 3 && tail_len > 0 && tail_len == n_meas && gate_stream_shape_ok(n, d) &&
+      sdimb_gate_stream(n, d, up_ops, up_n - tail_len, nullptr, 0, &gs_rows) == SDIMB_OK && gs_rows > 0) {
+    gstream.resize((size_t)gs_rows * 4);
+    if (sdimb_gate_stream(n, d, up_ops, up_n - tail_len, gstream.data(), gs_rows, &gs_rows) != SDIMB_OK) gs_rows = 0;
+  } else {
+    gs_rows = 0;
+  }
+  const size_t b_gs = align256((size_t)gs_rows * 16);
   const size_t b_scr = align256((size_t)sdimb_scratch_bytes_shots(n, d, mode_flags, tail_len ? shots : 0));
-  const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_scr + 256;
+  const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_gs + b_scr + 256;
 
   int cur_dev = 0;
   if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= kMaxDevices) { cudaGetLastError(); return SDIMB_ECUDA; }
@@ -700,6 +769,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   uint8_t* d_th = b_th ? base : nullptr; base += b_th;
   uint8_t* d_ch = b_ch ? base : nullptr; base += b_ch;
   uint8_t* d_tab = b_tab ? base : nullptr; base += b_tab;
+  uint8_t* d_gs = b_gs ? base : nullptr; base += b_gs;
   uint8_t* d_scr = b_scr ? base : nullptr;
   rc = SDIMB_ECUDA;
   do {
@@ -709,6 +779,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     if (d_rn && cudaMemcpyAsync(d_rn, replay_noise, (size_t)shots * n_noise * 2 * eb, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_th && cudaMemcpyAsync(d_th, noise_thresh24, (size_t)n_noise * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_ch && cudaMemcpyAsync(d_ch, noise_channel, (size_t)n_noise, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (d_gs && cudaMemcpyAsync(d_gs, gstream.data(), (size_t)gs_rows * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     SdimbRunArgs a;
     std::memset(&a, 0, sizeof(a));
     a.struct_size = sizeof(a);
@@ -722,6 +793,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     a.seed = seed; a.stream = st;
     a.scratch = d_scr; a.scratch_bytes = (int64_t)b_scr;
     a.tail_run_len = tail_len;
+    a.gate_stream = (const int32_t*)d_gs; a.gate_stream_rows = gs_rows;
     rc = sdimb_run(&a);
     if (rc) break;
     rc = SDIMB_ECUDA;
@@ -863,6 +935,134 @@ int sdimb_schedule(int n, const int32_t* ops, int64_t n_ops, int32_t* out, int64
   }
   flush();
   *out_n = w;
+  return SDIMB_OK;
+}
+
+int sdimb_gate_stream(int n, int d, const int32_t* ops, int64_t n_ops, int32_t* out, int64_t out_cap_rows, int64_t* out_rows) {
+  if (n < 1 || (d != 2 && d != 3) || n_ops < 0 || (n_ops > 0 && !ops) || !out_rows) return SDIMB_EINVAL;
+  const int gpw = planes::gate_stream_gpw(n);
+  if (gpw < 1) return SDIMB_EINVAL;
+  const int nw = gate_stream_warps(n, d);
+  const bool il = planes_interleaved(n);
+  const int32_t rs_bytes = (int32_t)(4 * ((d == 2) ? 2 : 4) * (2 * ((n + 31) / 32 * 32) / 32 + (il ? 0 : 1)));   // Geo<D, IL>::RS words
+  struct Row { int32_t x, y, z, w; };
+  std::vector<std::vector<Row>> ws(nw);          // per-warp streams: entries of gpw rows
+  std::vector<Row> tab;                          // N1 events (slot, qudit), layer by layer
+  std::vector<int64_t> wrote(n, -1), read(n, -1);   // layer that last wrote / read a row (check of the layering)
+  int64_t layers = 0, max_slot = -1;
+  auto family = [&](int op, int32_t& flags) -> int {
+    switch (op) {
+      case SDIMB_OP_H: return planes::GS_H;
+      case SDIMB_OP_H_INV: flags = GS_INV; return planes::GS_H;
+      case SDIMB_OP_P: return planes::GS_P;
+      case SDIMB_OP_P_INV: flags = GS_INV; return planes::GS_P;
+      case SDIMB_OP_CNOT: return planes::GS_CNOT;
+      case SDIMB_OP_CNOT_INV: flags = GS_INV; return planes::GS_CNOT;
+      case SDIMB_OP_CZ: return planes::GS_CZ;
+      case SDIMB_OP_CZ_INV: flags = GS_INV; return planes::GS_CZ;
+      case SDIMB_OP_SWAP: return planes::GS_SWAP;
+      default: return -1;
+    }
+  };
+  std::vector<Row> fam_rows[8];
+  for (int64_t i = 0; i < n_ops;) {
+    for (auto& v : fam_rows) v.clear();
+    const int32_t tab_lo = (int32_t)tab.size();
+    bool any = false;
+    for (; i < n_ops; ++i) {
+      const int32_t* o = ops + 4 * i;
+      const int op = o[0] & SDIMB_OP_MASK;
+      if (op == SDIMB_OP_BARRIER) { ++i; break; }
+      if (op == SDIMB_OP_I) continue;
+      if (o[1] < 0 || o[1] >= n) return SDIMB_EOP;
+      if (op == SDIMB_OP_N1) {
+        if (o[3] < 0 || wrote[o[1]] == layers) return SDIMB_EINVAL;
+        any = true;
+        read[o[1]] = layers;
+        tab.push_back(Row{o[3], o[1], 0, 0});
+        if (o[3] > max_slot) max_slot = o[3];
+        continue;
+      }
+      if (op >= SDIMB_OP_X && op <= SDIMB_OP_Z_INV) continue;       // Pauli gates: pushed back to the start, below
+      int32_t flags = 0;
+      const int fam = family(op, flags);
+      if (fam < 0) return SDIMB_EINVAL;                              // a measurement: not a gate-only stretch
+      const bool two = fam >= planes::GS_CNOT;
+      if (two && (o[2] < 0 || o[2] >= n || o[2] == o[1])) return SDIMB_EOP;
+      // rows of one layer: written by at most one op, and then read by no other (what sdimb_schedule guarantees)
+      any = true;
+      if (wrote[o[1]] == layers || read[o[1]] == layers) return SDIMB_EINVAL;
+      wrote[o[1]] = layers;
+      if (two) {
+        if (wrote[o[2]] == layers || read[o[2]] == layers) return SDIMB_EINVAL;
+        wrote[o[2]] = layers;
+      }
+      fam_rows[fam].push_back(Row{fam | flags | GS_ON, o[1] * rs_bytes, two ? o[2] * rs_bytes : 0, 0});
+    }
+    if (!any) continue;
+    for (int w = 0; w < nw; ++w)
+      for (int g = 0; g < gpw; ++g) ws[w].push_back(Row{planes::GS_SYNC, tab_lo, (int32_t)tab.size(), 0});
+    int64_t k = 0;
+    for (int fam = planes::GS_H; fam <= planes::GS_SWAP; ++fam) {
+      const auto& v = fam_rows[fam];
+      for (size_t c = 0; c < v.size(); c += gpw) {
+        auto& dst = ws[k++ % nw];
+        for (int g = 0; g < gpw; ++g) dst.push_back(c + g < v.size() ? v[c + g] : Row{fam, 0, 0, 0});
+      }
+    }
+    ++layers;
+  }
+  if ((int64_t)tab.size() > planes::kGateStreamMaxNoise || (int64_t)tab.size() > max_slot + 1) return SDIMB_EINVAL;
+  // Pauli gates, pushed BACK through the gates in front of them (P then U == U then U P U^-1, so walking backwards the
+  // pending Pauli takes the rule of the INVERSE gate on its exponents; the scheduled order is one valid sequential
+  // order of the stretch) and merged into one X^a Z^b per qudit at the start.  Global phases do not reach a tableau.
+  std::vector<int> pa(n, 0), pb(n, 0);
+  for (int64_t i = n_ops - 1; i >= 0; --i) {
+    const int32_t* o = ops + 4 * i;
+    const int q = o[1], t = o[2];
+    switch (o[0] & SDIMB_OP_MASK) {
+      case SDIMB_OP_X: pa[q] = (pa[q] + 1) % d; break;
+      case SDIMB_OP_X_INV: pa[q] = (pa[q] + d - 1) % d; break;
+      case SDIMB_OP_Z: pb[q] = (pb[q] + 1) % d; break;
+      case SDIMB_OP_Z_INV: pb[q] = (pb[q] + d - 1) % d; break;
+      case SDIMB_OP_H: { const int a = pa[q]; pa[q] = pb[q]; pb[q] = (d - a) % d; break; }          // H^-1: (x,z) <- (z,-x)
+      case SDIMB_OP_H_INV: { const int a = pa[q]; pa[q] = (d - pb[q]) % d; pb[q] = a; break; }      // H: (x,z) <- (-z,x)
+      case SDIMB_OP_P: pb[q] = (pb[q] + d - pa[q]) % d; break;                                      // P^-1: z -= x
+      case SDIMB_OP_P_INV: pb[q] = (pb[q] + pa[q]) % d; break;
+      case SDIMB_OP_CNOT: pa[t] = (pa[t] + d - pa[q]) % d; pb[q] = (pb[q] + pb[t]) % d; break;      // CNOT^-1: x[t] -= x[c], z[c] += z[t]
+      case SDIMB_OP_CNOT_INV: pa[t] = (pa[t] + pa[q]) % d; pb[q] = (pb[q] + d - pb[t]) % d; break;
+      case SDIMB_OP_CZ: { const int bq = (pb[q] + d - pa[t]) % d, bt = (pb[t] + d - pa[q]) % d; pb[q] = bq; pb[t] = bt; break; }   // CZ^-1: z[a] -= x[b], z[b] -= x[a]
+      case SDIMB_OP_CZ_INV: { const int bq = (pb[q] + pa[t]) % d, bt = (pb[t] + pa[q]) % d; pb[q] = bq; pb[t] = bt; break; }
+      case SDIMB_OP_SWAP: std::swap(pa[q], pa[t]); std::swap(pb[q], pb[t]); break;
+      default: break;
+    }
+  }
+  std::vector<Row> pauli;
+  for (int q = 0; q < n; ++q)
+    if (pa[q] || pb[q]) pauli.push_back(Row{q, pa[q], pb[q], 0});
+  for (int w = 0; w < nw; ++w)
+    for (int g = 0; g < planes::kGateStreamPadRows; ++g) ws[w].push_back(Row{planes::GS_END, 0, 0, 0});
+  int64_t total = planes::kGateStreamHeaderRows + nw;
+  for (int w = 0; w < nw; ++w) total += (int64_t)ws[w].size();
+  const int64_t tab_base = total;
+  total += (int64_t)tab.size() + (int64_t)pauli.size();
+  *out_rows = total;
+  if (!out) return SDIMB_OK;
+  if (out_cap_rows < total || total > 0x7FFFFFFF) return SDIMB_EINVAL;
+  Row* R = reinterpret_cast<Row*>(out);
+  R[0] = Row{planes::kGateStreamMagic, gpw, nw, (int32_t)tab.size()};
+  R[1] = Row{(int32_t)tab_base, (int32_t)total, (int32_t)layers, (int32_t)pauli.size()};
+  R[2] = Row{rs_bytes, il ? 1 : 0, 0, 0};
+  int64_t at = planes::kGateStreamHeaderRows + nw;
+  for (int w = 0; w < nw; ++w) {
+    // entries up to and including the first END
+    R[planes::kGateStreamHeaderRows + w] = Row{(int32_t)at, (int32_t)((ws[w].size() - planes::kGateStreamPadRows) / gpw + 1), 0, 0};
+    std::memcpy(R + at, ws[w].data(), ws[w].size() * sizeof(Row));
+    at += (int64_t)ws[w].size();
+  }
+  if (!tab.empty()) std::memcpy(R + at, tab.data(), tab.size() * sizeof(Row));
+  at += (int64_t)tab.size();
+  if (!pauli.empty()) std::memcpy(R + at, pauli.data(), pauli.size() * sizeof(Row));
   return SDIMB_OK;
 }
 

@@ -446,6 +446,54 @@ def test_tail_run_kernel_on_the_reference_goldens(golden_random, golden_config_s
     assert (two_kernels >= 20) if min_run == "2" else (two_kernels == 0)
 
 
+@pytest.mark.parametrize("form", ["smem-8", "smem-4", "smem-3", "global", "off"])
+@pytest.mark.parametrize("d,n,depth,il", [(3, 256, 2500, "100000"), (2, 300, 3000, "100000"), (3, 97, 1500, "0"),
+                                          (2, 33, 900, "100000"), (3, 500, 1200, "0"), (2, 512, 1500, "100000"),
+                                          (3, 40, 800, "100000"), (3, 5, 300, "100000")])
+def test_gate_stream_kernel_matches_c_oracle(monkeypatch, d, n, depth, il, form):
+    """Gates and the three noise channels in front of the final all-qudit measurement: the front part runs as
+    pre-decoded per-warp streams (gate_stream_kernel, planes_stream.cuh) — image in shared memory with 8 / 4 / 3 warps
+    per shot, or on the per-shot global image — and must give the records of the C oracle for every shot, like the
+    interpreted form ("off").  Also: N1 events replayed instead of drawn, and a run that continues from a uint8 store."""
+    import torch
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine, simulate_host
+    monkeypatch.setenv("SDIMB_GM_MIN_RUN", "2")
+    monkeypatch.setenv("SDIMB_PG_IL_MIN_NP", il)
+    if form == "off":
+        monkeypatch.setenv("SDIMB_NO_GATE_STREAM", "1")
+    elif form == "global":
+        monkeypatch.setenv("SDIMB_GS_GLOBAL", "1")
+    else:
+        monkeypatch.setenv("SDIMB_GS_WARPS", form.split("-")[1])
+    prog = random_program(seed=77 * d + n, n=n, d=d, depth=depth, p_meas=0.0, p_noise=0.25)
+    eng = TableauEngine(prog)
+    assert eng.tail_run_len == n and eng.gate_stream is not None      # "off": compiled, but the library ignores it
+    shots, seed = (3000 if n <= 97 else 400), 41
+    before = _launches()
+    got = eng.run(shots, 11, seed, mode="planes-global").cpu().numpy()
+    assert _launches() - before == 2
+    want, _ = c_oracle.run(n, d, prog.ops, shots, 11, seed, thresh24=prog.noise_thresh24, channel=prog.noise_channel)
+    assert np.array_equal(got, want)
+    if n >= 130:                                   # the host-buffer entry compiles its own streams (auto: planes-global)
+        host, _ = simulate_host(prog, 64, 11, seed)
+        assert np.array_equal(host, want[:64])
+    # replayed N1 exponents: every event fires
+    k = 50
+    rng = np.random.default_rng(n)
+    rn = rng.integers(0, d, size=(k, prog.n_noise, 2), dtype=np.uint8)
+    got = eng.run(k, 0, seed, replay_noise=torch.from_numpy(rn), mode="planes-global").cpu().numpy()
+    want, _ = c_oracle.run(n, d, prog.ops, k, 0, seed, replay_noise=rn)
+    assert np.array_equal(got, want)
+    # continue from a store: |0...0> written by sdimb_init, packed into bit planes by the kernel
+    tab = eng.alloc_tableau(k)
+    eng.init_tableau(tab)
+    got = eng.run(k, 0, seed, mode="planes-global", tableau=tab, fresh=False).cpu().numpy()
+    want, _ = c_oracle.run(n, d, prog.ops, k, 0, seed, thresh24=prog.noise_thresh24, channel=prog.noise_channel)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("il", ["0", "100000"])
 @pytest.mark.parametrize("d,n,depth", [(2, 33, 900), (3, 97, 2500), (3, 256, 3000), (2, 300, 3000), (3, 500, 3000),
                                        (2, 512, 2500), (3, 17, 600), (3, 1, 40), (2, 2, 60)])

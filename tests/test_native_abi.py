@@ -25,7 +25,7 @@ def test_library_exists_and_exports_every_declared_symbol():
     assert set(declared) == set(N.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sdimb_version() == 3
+    assert lib.sdimb_version() == 4
 
 
 def test_layout_matches_header_contract():
