@@ -8,7 +8,8 @@
 //   * a "wide op" = GPW = 32 / Wb gates of ONE family on pairwise disjoint rows (same layer), one row of the stream
 //     per lane group: lane group g of the warp loads its own row (family | flags, qudit a, qudit b) and runs its gate
 //     on its lane word — no filtering, no shuffles, all 32 lanes busy;
-//   * layers are separated by SYNC rows (one block barrier each, same count in every warp's stream);
+//   * layers (ASAP over the gates that write rows, computed by the compiler itself) are separated by SYNC rows (one
+//     block barrier each, same count in every warp's stream);
 //   * the Pauli gates X, X^-1, Z, Z^-1 (a third of a random Clifford circuit) are not in the stream either: a Pauli
 //     commutes through a Clifford gate into another Pauli (Pauli-frame propagation, the mechanism of the reference's
 //     simulate_frame, sdim/program.py:82-120, applied to gates instead of errors), so the host pushes every one of
@@ -17,9 +18,10 @@
 //     initial Pauli is a closed form (stabilizer q: -a_q po, destabilizer q: +b_q po), on a loaded store n phase passes;
 //   * N1 noise ops are not in the stream at all: a pre-pass per shot evaluates every event of the segment (Philox or
 //     replay, all threads of the CTA, fully packed) and sets one bit per FIRED event in shared memory; the SYNC row
-//     that opens a layer carries that layer's range of the noise table, warp 0 scans those bits and applies the rare
-//     fired events.  An N1 commutes with everything in its layer: the scheduler put it behind the last writer of its
-//     row and in front of the next one.
+//     that opens a layer carries that layer's range of the noise table and the index of its "some event fired" bit:
+//     if that is set (rare), warp 0 applies the fired events and the CTA takes a second barrier before the layer's
+//     gates.  An N1 belongs to the start of the layer of the NEXT writer of its row, so it sees the row as the program
+//     order says and costs no layer of its own.
 // SM = true keeps the shot's image in SHARED memory while the gates run (a gate is then one LDS.128 + LOP3s + one
 // STS.128 per lane, ~30 cycles instead of an L1/L2 round trip, and neither L2 nor HBM sees the 2 000 row updates of
 // a shot) and copies it out once, coalesced, to the per-shot image run_tail_kernel picks up; SM = false runs on that
@@ -41,6 +43,7 @@
 enum { GS_END = 0, GS_SYNC = 1, GS_H = 2, GS_P = 3, GS_CNOT = 4, GS_CZ = 5, GS_SWAP = 6 };
 #define GS_INV 0x100          // inverse gate (H_INV, P_INV, CNOT_INV, CZ_INV)
 #define GS_ON 0x200           // this lane group has a gate (padding rows of a wide op do not)
+#define GS_LAYER_SHIFT 12     // SYNC rows: ordinal of the layer among the layers that have N1 events
 constexpr int kGateStreamMagic = 0x47533033;   // "GS03"
 constexpr int kGateStreamMaxNoise = 1 << 16;   // fired bits live in shared memory: 8 KB at most
 constexpr int kGateStreamMaxWarps = 8;
@@ -59,7 +62,7 @@ inline int gate_stream_gpw(int n) {
 inline size_t gate_stream_smem_bytes(int n, int64_t n_noise, int nw) {
   const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32;
   const size_t gpw = Wb <= 32 ? 32 / Wb : 1;
-  return 8 * (size_t)nw * gpw * Wb + 4 * (((size_t)n_noise + 31) / 32) + 16;
+  return 8 * (size_t)nw * gpw * Wb + 2 * 4 * (((size_t)n_noise + 31) / 32) + 16;   // fired bits per event and per layer
 }
 
 template <int D, bool IL, bool SM>
@@ -86,7 +89,8 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
   uint32_t* const img = reinterpret_cast<uint32_t*>(smem);                  // SM: the shot's image (row_words words)
   uint2* const acc = reinterpret_cast<uint2*>(smem + (SM ? 4 * (size_t)row_words : 0));   // [NW * GPW][Wb]
   uint32_t* const fired = reinterpret_cast<uint32_t*>(acc + NW * GPW * Wb);  // [(n_tab + 31) / 32]
-  int* const next = reinterpret_cast<int*>(fired + (n_tab + 31) / 32);       // [2]
+  uint32_t* const lfired = fired + (n_tab + 31) / 32;                        // [(n_tab + 31) / 32] one bit per noisy layer
+  int* const next = reinterpret_cast<int*>(lfired + (n_tab + 31) / 32);      // [2]
   uint2* const pacc = acc + (warp * GPW + g) * Wb + j;
   int joff;                                                                  // word offset of lane word j inside a row
   { int e = j; if (IL) { const int h = G.np >> 5; e = (j < h) ? 2 * j : 2 * (j - h) + 1; } joff = e * EW; }
@@ -104,7 +108,7 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
     // ---- |0...0>, or pack from the uint8 store (same as interp_planes_kernel) ----
     for (int i = tid; i < row_words / 4; i += NT) reinterpret_cast<uint4*>(G.tab)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < NW * GPW * Wb; i += NT) acc[i] = make_uint2(0u, 0u);
-    for (int i = tid; i < (n_tab + 31) / 32; i += NT) fired[i] = 0u;
+    for (int i = tid; i < 2 * ((n_tab + 31) / 32); i += NT) fired[i] = 0u;     // fired and lfired
     __syncthreads();
     G.ph_base = acc;
     G.pacc = acc;
@@ -158,8 +162,11 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
     }
     // ---- noise pre-pass: one bit per fired event of the segment ----
     for (int t = tid; t < n_tab; t += NT) {
-      const int4 row = __ldg(S + tab_base + t);                        // (event slot, qudit, -, -)
-      if (p_noise_event<D>(p, row.x, shot)) atomicOr(&fired[t >> 5], 1u << (t & 31));
+      const int4 row = __ldg(S + tab_base + t);                        // (event slot, qudit, noisy-layer ordinal, -)
+      if (p_noise_event<D>(p, row.x, shot)) {
+        atomicOr(&fired[t >> 5], 1u << (t & 31));
+        atomicOr(&lfired[row.z >> 5], 1u << (row.z & 31));
+      }
     }
     __syncthreads();
     // this lane's phase accumulator (warp, lane group, lane word) lives in a register while the gates run
@@ -196,7 +203,12 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
         case GS_END: goto stream_done;
         case GS_SYNC: {
           __syncthreads();
-          if (warp == 0 && opy < opz) {                                    // fired N1 events of the layer that starts here
+          // N1 events of the layer that starts here: they act before its gates.  Almost always none fired (one bit per
+          // layer, set by the pre-pass); if one did, warp 0 applies them — it reads rows and adds to its own phase
+          // accumulator — and one more barrier keeps the layer's writers behind those reads.
+          const int lay = opx >> GS_LAYER_SHIFT;
+          if (opy < opz && ((lfired[lay >> 5] >> (lay & 31)) & 1u)) {
+           if (warp == 0) {
             for (int t0 = opy & ~31; t0 < opz; t0 += 32) {
               uint32_t m = fired[t0 >> 5];
               if (t0 < opy) m &= ~((1u << (opy - t0)) - 1u);
@@ -214,6 +226,8 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
                 }
               }
             }
+           }
+           __syncthreads();
           }
           break;
         }

@@ -718,12 +718,26 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   uint32_t sched_flag = 0;
   // bit-plane interpreter and cluster interpreter (wide rows on the HBM store): upload the layered stream
   const bool maybe_cluster = kernel == 0 && !(flags & SDIMB_NO_CLUSTER) && (L.lanes / 4 > kMaxThreads || (flags & SDIMB_CLUSTER));
-  if ((kernel == 2 || kernel == 3 || maybe_cluster) && n_ops > 0) {
+  // (a tile-interpreter call above 64 qudits is scheduled too: it may turn into a two-kernel call, see below)
+  const bool tile_to_two = kernel == 5 && n > 64 && mode_flags == 0 && n_meas > 0;
+  if ((kernel == 2 || kernel == 3 || maybe_cluster || tile_to_two) && n_ops > 0) {
     sched.resize((size_t)(2 * n_ops + 1) * 4);
     rc = sdimb_schedule(n, ops, n_ops, sched.data(), 2 * n_ops + 1, &up_n);
     if (rc) return rc;
     up_ops = sched.data();
     sched_flag = SDIMB_SCHEDULED;
+  }
+  // Every measurement in the trailing run: the two-kernel path (gate_stream_kernel + run_tail_kernel) beats the
+  // shared-memory interpreters where those fit, and the tile interpreter above 64 qudits (TableauEngine._auto_mode)
+  if ((kernel == 2 || tile_to_two) && mode_flags == 0 && sched_flag) {
+    const int64_t t = sdimb_tail_run(up_ops, up_n);
+    if (t > 0 && t == n_meas && gate_stream_shape_ok(n, d) && tail_run_shape_ok(n, d) &&
+        plan_kernel(n, d, SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL, L.np) == 3) {
+      mode_flags = SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL;
+      kernel = 3;
+    } else if (tile_to_two) {         // stays with the tiles, on the stream as the caller wrote it
+      up_ops = ops; up_n = n_ops; sched_flag = 0;
+    }
   }
 
   // carve the device arena
@@ -735,15 +749,9 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
   const size_t b_tab = (kernel == 0 || kernel == 4) ? align256((size_t)shots * L.shot_bytes) : 0;
   const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
-  // the gates in front of a tail run that holds every measurement: pre-decoded per-warp streams (planes_stream.cuh);
-  // that two-kernel path also beats the shared-memory interpreter where it fits (TableauEngine._auto_mode)
+  // the gates in front of a tail run that holds every measurement: pre-decoded per-warp streams (planes_stream.cuh)
   std::vector<int32_t> gstream;
   int64_t gs_rows = 0;
-  if (kernel == 2 && mode_flags == 0 && tail_len > 0 && tail_len == n_meas && gate_stream_shape_ok(n, d) && tail_run_shape_ok(n, d) &&
-      plan_kernel(n, d, SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL, L.np) == 3) {
-    mode_flags = SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL;
-    kernel = 3;
-  }
   if (kernel == 3 && tail_len > 0 && tail_len == n_meas && gate_stream_shape_ok(n, d) &&
       sdimb_gate_stream(n, d, up_ops, up_n - tail_len, nullptr, 0, &gs_rows) == SDIMB_OK && gs_rows > 0) {
     gstream.resize((size_t)gs_rows * 4);
@@ -947,9 +955,8 @@ int sdimb_gate_stream(int n, int d, const int32_t* ops, int64_t n_ops, int32_t* 
   const int32_t rs_bytes = (int32_t)(4 * ((d == 2) ? 2 : 4) * (2 * ((n + 31) / 32 * 32) / 32 + (il ? 0 : 1)));   // Geo<D, IL>::RS words
   struct Row { int32_t x, y, z, w; };
   std::vector<std::vector<Row>> ws(nw);          // per-warp streams: entries of gpw rows
-  std::vector<Row> tab;                          // N1 events (slot, qudit), layer by layer
-  std::vector<int64_t> wrote(n, -1), read(n, -1);   // layer that last wrote / read a row (check of the layering)
-  int64_t layers = 0, max_slot = -1;
+  std::vector<Row> tab;                          // N1 events (slot, qudit, noisy-layer ordinal), layer by layer
+  int64_t max_slot = -1;
   auto family = [&](int op, int32_t& flags) -> int {
     switch (op) {
       case SDIMB_OP_H: return planes::GS_H;
@@ -964,54 +971,57 @@ int sdimb_gate_stream(int n, int d, const int32_t* ops, int64_t n_ops, int32_t* 
       default: return -1;
     }
   };
-  std::vector<Row> fam_rows[8];
-  for (int64_t i = 0; i < n_ops;) {
-    for (auto& v : fam_rows) v.clear();
-    const int32_t tab_lo = (int32_t)tab.size();
-    bool any = false;
-    for (; i < n_ops; ++i) {
-      const int32_t* o = ops + 4 * i;
-      const int op = o[0] & SDIMB_OP_MASK;
-      if (op == SDIMB_OP_BARRIER) { ++i; break; }
-      if (op == SDIMB_OP_I) continue;
-      if (o[1] < 0 || o[1] >= n) return SDIMB_EOP;
-      if (op == SDIMB_OP_N1) {
-        if (o[3] < 0 || wrote[o[1]] == layers) return SDIMB_EINVAL;
-        any = true;
-        read[o[1]] = layers;
-        tab.push_back(Row{o[3], o[1], 0, 0});
-        if (o[3] > max_slot) max_slot = o[3];
-        continue;
-      }
-      if (op >= SDIMB_OP_X && op <= SDIMB_OP_Z_INV) continue;       // Pauli gates: pushed back to the start, below
-      int32_t flags = 0;
-      const int fam = family(op, flags);
-      if (fam < 0) return SDIMB_EINVAL;                              // a measurement: not a gate-only stretch
-      const bool two = fam >= planes::GS_CNOT;
-      if (two && (o[2] < 0 || o[2] >= n || o[2] == o[1])) return SDIMB_EOP;
-      // rows of one layer: written by at most one op, and then read by no other (what sdimb_schedule guarantees)
-      any = true;
-      if (wrote[o[1]] == layers || read[o[1]] == layers) return SDIMB_EINVAL;
-      wrote[o[1]] = layers;
-      if (two) {
-        if (wrote[o[2]] == layers || read[o[2]] == layers) return SDIMB_EINVAL;
-        wrote[o[2]] = layers;
-      }
-      fam_rows[fam].push_back(Row{fam | flags | GS_ON, o[1] * rs_bytes, two ? o[2] * rs_bytes : 0, 0});
+  // Layers of THIS kernel: ASAP over the gates that write rows.  The input order is one valid sequential order of the
+  // stretch (sdimb_schedule's, or the program's own); its layering is not reused, because there every N1 and Pauli
+  // reader sits in a layer of its own kind between two writers of its row (gate, N1, gate ... costs two layers per
+  // gate).  Here Pauli gates leave the stream (below) and an N1 event belongs to the START of the layer of the next
+  // writer of its row: the kernel applies the fired events of a layer before any of its gates runs.
+  struct Layer { std::vector<Row> fam[8]; std::vector<Row> noise; };
+  std::vector<Layer> L;
+  std::vector<int64_t> lvl(n, 0);                // first layer in which row q may be written again
+  for (int64_t i = 0; i < n_ops; ++i) {
+    const int32_t* o = ops + 4 * i;
+    const int op = o[0] & SDIMB_OP_MASK;
+    if (op == SDIMB_OP_BARRIER || op == SDIMB_OP_I) continue;
+    if (o[1] < 0 || o[1] >= n) return SDIMB_EOP;
+    if (op >= SDIMB_OP_X && op <= SDIMB_OP_Z_INV) continue;         // Pauli gates: pushed back to the start, below
+    if (op == SDIMB_OP_N1) {
+      if (o[3] < 0) return SDIMB_EINVAL;
+      if ((int64_t)L.size() <= lvl[o[1]]) L.resize(lvl[o[1]] + 1);
+      L[lvl[o[1]]].noise.push_back(Row{o[3], o[1], 0, 0});
+      if (o[3] > max_slot) max_slot = o[3];
+      continue;
     }
-    if (!any) continue;
+    int32_t flags = 0;
+    const int fam = family(op, flags);
+    if (fam < 0) return SDIMB_EINVAL;                                // a measurement: not a gate-only stretch
+    const bool two = fam >= planes::GS_CNOT;
+    if (two && (o[2] < 0 || o[2] >= n || o[2] == o[1])) return SDIMB_EOP;
+    const int64_t level = two ? std::max(lvl[o[1]], lvl[o[2]]) : lvl[o[1]];
+    lvl[o[1]] = level + 1;
+    if (two) lvl[o[2]] = level + 1;
+    if ((int64_t)L.size() <= level) L.resize(level + 1);
+    L[level].fam[fam].push_back(Row{fam | flags | GS_ON, o[1] * rs_bytes, two ? o[2] * rs_bytes : 0, 0});
+  }
+  const int64_t layers = (int64_t)L.size();
+  int32_t noisy = 0;                             // layers with N1 events so far: index of the layer's "some event fired" bit
+  for (auto& layer : L) {
+    const int32_t tab_lo = (int32_t)tab.size();
+    for (Row r : layer.noise) { r.z = noisy; tab.push_back(r); }
+    const int32_t sync_x = planes::GS_SYNC | (noisy << GS_LAYER_SHIFT);
+    if (!layer.noise.empty()) ++noisy;
     for (int w = 0; w < nw; ++w)
-      for (int g = 0; g < gpw; ++g) ws[w].push_back(Row{planes::GS_SYNC, tab_lo, (int32_t)tab.size(), 0});
+      for (int g = 0; g < gpw; ++g) ws[w].push_back(Row{sync_x, tab_lo, (int32_t)tab.size(), 0});
     int64_t k = 0;
     for (int fam = planes::GS_H; fam <= planes::GS_SWAP; ++fam) {
-      const auto& v = fam_rows[fam];
+      const auto& v = layer.fam[fam];
       for (size_t c = 0; c < v.size(); c += gpw) {
         auto& dst = ws[k++ % nw];
         for (int g = 0; g < gpw; ++g) dst.push_back(c + g < v.size() ? v[c + g] : Row{fam, 0, 0, 0});
       }
     }
-    ++layers;
   }
+  if (noisy >= (1 << (31 - GS_LAYER_SHIFT))) return SDIMB_EINVAL;
   if ((int64_t)tab.size() > planes::kGateStreamMaxNoise || (int64_t)tab.size() > max_slot + 1) return SDIMB_EINVAL;
   // Pauli gates, pushed BACK through the gates in front of them (P then U == U then U P U^-1, so walking backwards the
   // pending Pauli takes the rule of the INVERSE gate on its exponents; the scheduled order is one valid sequential

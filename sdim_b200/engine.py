@@ -99,9 +99,12 @@ class TableauEngine:
         # every measurement in the trailing run and the gates compiled into per-warp streams: the two-kernel path
         # (gate_stream_kernel + run_tail_kernel) also beats the shared-memory interpreter where that fits
         # (d = 3: n = 160 12.4 ms against 20.5 ms per 16 384 shots, n = 192 10.4 / 19.7; d = 2, n = 200: 7.5 / 13.5)
-        if mode in (None, "auto") and self.gate_stream is not None and not keep_tableau and \
-                self.plan(None)[0] == "planes-resident":
-            return "planes-global"
+        # ... and the tile interpreter above 64 qudits (d = 3, n = 128: 10.7 / 24.8 ms; d = 2, n = 100: 5.1 / 5.6; at
+        # n = 64 the tiles win, 3.8 / 4.9)
+        if mode in (None, "auto") and self.gate_stream is not None and not keep_tableau:
+            kernel = self.plan(None)[0]
+            if kernel == "planes-resident" or (kernel == "planes-tile" and self.prog.num_qudits > 64):
+                return "planes-global"
         return mode
 
     def cluster_size(self, shots: int, mode: Optional[str] = None) -> int:
