@@ -98,6 +98,8 @@ struct KParams {
   int64_t tail_start;          // run_tail_kernel: index of the first op of the run (ops [tail_start, n_ops) are M ops)
   uint32_t* gm_slab;           // run_tail_kernel: one B + QX slab per resident warp
   int64_t gm_slab_words;
+  int gm_per_shot;             // gate_stream_kernel leaves B + QX + phase planes of shot s at gm_slab + s * gm_shot_stride_words
+  int64_t gm_shot_stride_words;  // (it transposes its shared-memory image itself); run_tail_kernel works on them in place
   int64_t tile_stride_words;   // interp_tile_kernel: words between the shared-memory images of two tiles
   const int32_t* gate_stream;  // gate_stream_kernel: pre-decoded per-warp streams (sdimb_gate_stream, planes_stream.cuh)
 };

@@ -386,9 +386,15 @@ inline size_t run_smem_bytes(int n) {  // per CTA: list (2np uint16) + ph8 (2np 
   const size_t np = (size_t)(n + 31) / 32 * 32;
   return (size_t)(kRunThreads / run_lps(n)) * (4 * np + 2 * np);
 }
+inline size_t run_shot_stride_words(int n, int d);
 inline size_t run_slab_words(int n, int d) {   // B + QX of one tile
   const size_t np = (size_t)(n + 31) / 32 * 32, Wq = np / 32, Wb = 2 * Wq, EW = (d == 2) ? 2 : 4;
   return (2 * np * Wq * EW + (size_t)n * Wb * (EW / 2) + 7) & ~(size_t)7;
+}
+
+inline size_t run_shot_stride_words(int n, int d) {   // B + QX + phase planes of one shot (gm_per_shot)
+  const size_t np = (size_t)(n + 31) / 32 * 32, Wb = 2 * np / 32;
+  return (run_slab_words(n, d) + 2 * Wb + 7) & ~(size_t)7;
 }
 
 template <int D, bool IL, int LPS>
@@ -416,15 +422,20 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
     if (lane == 0) shot = (int64_t)atomicAdd(p.shot_counter, 1u);
     shot = T.shfl(shot, 0);
     if (shot >= p.shots) break;
-    G.tab = p.plane_slab + shot * p.img_stride_words;          // the image the interpreter left for this shot
-    {
-      const uint2* ph = reinterpret_cast<const uint2*>(G.tab + row_words);
-      for (int g = lane; g < 2 * G.np; g += LPS) {
-        const uint2 w = ph[g >> 5];
-        M.ph8[g] = (uint8_t)(((w.x >> (g & 31)) & 1u) | (((w.y >> (g & 31)) & 1u) << 1));
-      }
+    const uint2* ph;
+    if (p.gm_per_shot) {         // gate_stream_kernel already left B, QX and the phase planes of this shot in place
+      M.B = p.gm_slab + shot * p.gm_shot_stride_words;
+      M.QX = M.B + (size_t)2 * G.np * M.Wq * GMImg<D>::EW;
+      ph = reinterpret_cast<const uint2*>(M.B + p.gm_slab_words);
+    } else {
+      G.tab = p.plane_slab + shot * p.img_stride_words;          // the image the interpreter left for this shot
+      ph = reinterpret_cast<const uint2*>(G.tab + row_words);
     }
-    gm_transpose<D>(G, M, true, lane, LPS);
+    for (int g = lane; g < 2 * G.np; g += LPS) {
+      const uint2 w = ph[g >> 5];
+      M.ph8[g] = (uint8_t)(((w.x >> (g & 31)) & 1u) | (((w.y >> (g & 31)) & 1u) << 1));
+    }
+    if (!p.gm_per_shot) gm_transpose<D>(G, M, true, lane, LPS);
     T.sync();
     for (int64_t i0 = p.tail_start; i0 < p.n_ops; i0 += LPS) {
       int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);

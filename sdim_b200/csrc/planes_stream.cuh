@@ -311,13 +311,22 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
   stream_done:
     if (lane_on) *pacc = make_uint2(ph.l, ph.h);
     __syncthreads();
-    if (SM) {                                                                // the image leaves shared memory once, coalesced
+    uint2* out = reinterpret_cast<uint2*>(gimg + row_words);
+    if (SM && p.gm_per_shot) {
+      // the image leaves shared memory TRANSPOSED: B (generator-major) and QX, the form run_tail_kernel works on, straight
+      // into this shot's slab — HBM never sees the qudit-major image, the tail kernel skips its transposition pass
+      GMImg<D> M;
+      M.n = G.n; M.np = G.np; M.Wq = G.np / 32; M.Wb = G.Wb;
+      M.B = p.gm_slab + shot * p.gm_shot_stride_words;
+      M.QX = M.B + (size_t)2 * G.np * M.Wq * GMImg<D>::EW;
+      gm_transpose<D>(G, M, true, tid, NT);
+      out = reinterpret_cast<uint2*>(M.B + p.gm_slab_words);
+    } else if (SM) {                                                         // ... or once as it is, coalesced
       for (int i = tid; i < row_words / 4; i += NT)
         reinterpret_cast<uint4*>(gimg)[i] = reinterpret_cast<const uint4*>(img)[i];
     }
-    // ---- folded phase planes behind the rows, for run_tail_kernel ----
+    // ---- folded phase planes, for run_tail_kernel ----
     {
-      uint2* const out = reinterpret_cast<uint2*>(gimg + row_words);
       for (int jj = tid; jj < Wb; jj += NT) {
         E a{0u, 0u};
         for (int w = 0; w < NW * GPW; ++w) {

@@ -201,6 +201,10 @@ size_t tail_run_scratch_bytes(int n, int d, int64_t shots, int run_ctas) {
   return 256 + (size_t)shots * 4 * planes::planes_img_stride_words(n, d) +
          (size_t)run_ctas * (planes::kRunThreads / planes::run_lps(n)) * 4 * planes::run_slab_words(n, d);
 }
+// ... and of one whose front kernel (gate_stream_kernel on a shared-memory image) writes B + QX per shot itself
+size_t tail_run_fused_scratch_bytes(int n, int d, int64_t shots) {
+  return 256 + (size_t)shots * 4 * planes::run_shot_stride_words(n, d);
+}
 
 // Gate-stream kernel (planes_stream.cuh) for the gates in front of a tail run: image in shared memory when one image,
 // the accumulators of the widest launch and the largest fired-bit table fit (a rule of the shape alone, so that
@@ -488,6 +492,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
       }
       // ... and as pre-decoded per-warp streams when the caller compiled them (sdimb_gate_stream)
       int threads1 = 32 * SDIMB_SCHED_WARPS;
+      bool fused = false;
       if (a->n_meas == tail && a->gate_stream && a->gate_stream_rows > 0 && gate_stream_shape_ok(a->n, a->d)) {
         kern = gate_stream_kernel_for(a->n, a->d);
         const int nw = gate_stream_warps(a->n, a->d);
@@ -503,6 +508,15 @@ int sdimb_run(const SdimbRunArgs* caller) {
         }
         grid1 = (int64_t)sms * per_sm < a->shots ? (int64_t)sms * per_sm : a->shots;
         p1.gate_stream = a->gate_stream;
+        // image in shared memory: it leaves the SM transposed, one B + QX slab per shot (SDIMB_GS_NO_FUSE: A/B knob)
+        if (gate_stream_in_smem(a->n, a->d) && !std::getenv("SDIMB_GS_NO_FUSE") &&
+            a->scratch_bytes >= (int64_t)tail_run_fused_scratch_bytes(a->n, a->d, a->shots)) {
+          fused = true;
+          p1.gm_per_shot = 1;
+          p1.gm_slab = p.plane_slab;
+          p1.gm_slab_words = (int64_t)planes::run_slab_words(a->n, a->d);
+          p1.gm_shot_stride_words = (int64_t)planes::run_shot_stride_words(a->n, a->d);
+        }
       }
       const bool timed = (a->flags & SDIMB_TIME_KERNELS) && time_events_ready();
       g_time_valid = 0;
@@ -516,6 +530,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
       p2.shot_counter = (unsigned int*)a->scratch + 1;
       p2.gm_slab = p.plane_slab + (int64_t)a->shots * p.img_stride_words;
       p2.gm_slab_words = (int64_t)planes::run_slab_words(a->n, a->d);
+      if (fused) { p2.gm_per_shot = 1; p2.gm_slab = p1.gm_slab; p2.gm_shot_stride_words = p1.gm_shot_stride_words; }
       const int tiles = planes::kRunThreads / planes::run_lps(a->n);
       int64_t grid2 = (a->shots + tiles - 1) / tiles;
       if (grid2 > run_ctas_max) grid2 = run_ctas_max;
@@ -1123,7 +1138,9 @@ int64_t sdimb_scratch_bytes_shots(int n, int d, uint32_t flags, int64_t shots) {
   if (shots <= 0 || sdimb_layout(n, d, &L) || plan_kernel(n, d, flags, L.np) != 3 || !tail_run_shape_ok(n, d)) return base;
   int ctas = run_tail_ctas(n, d);
   if (ctas < 1) ctas = 148 * planes::kRunCtasPerSm;     // no device: the size a B200 would need
-  const int64_t need = (int64_t)tail_run_scratch_bytes(n, d, shots, ctas);
+  int64_t need = (int64_t)tail_run_scratch_bytes(n, d, shots, ctas);
+  if (gate_stream_shape_ok(n, d) && gate_stream_in_smem(n, d) && (int64_t)tail_run_fused_scratch_bytes(n, d, shots) > need)
+    need = (int64_t)tail_run_fused_scratch_bytes(n, d, shots);
   return need > base ? need : base;
 }
 
