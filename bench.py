@@ -496,18 +496,23 @@ def bench_ours(args):
             t0 = time.perf_counter()
             rec_host, _ms = simulate_host(prog, e2e_shots, lo, seed, mode=args.mode)
             e2e_times.append(time.perf_counter() - t0)
-        h2d = up_rows * 16 + prog.noise_thresh24.nbytes + prog.noise_channel.nbytes      # what the call uploads
+        gs_rows = engine.gate_stream.shape[0] if getattr(engine, "gate_stream", None) is not None else 0
+        # what the call uploads: the scheduled op stream, the noise tables and the compiled gate streams
+        h2d = (up_rows + gs_rows) * 16 + prog.noise_thresh24.nbytes + prog.noise_channel.nbytes
         d2h = e2e_shots * prog.n_meas
         e2e_how = "sdimb_simulate_host (C ABI, host buffers)"
     else:
         # op stream from pinned host memory -> device, simulate, all-gather, gathered records -> pinned host (rank 0)
         host_ops = engine.ops_sched.cpu().pin_memory() if engine.ops_sched is not None else None
+        host_gs = engine.gate_stream.cpu().pin_memory() if getattr(engine, "gate_stream", None) is not None else None
         host_out = torch.empty((world * shots, prog.n_meas), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
         for it in range(1 + max(1, args.steps)):
             barrier()
             t0 = time.perf_counter()
             if host_ops is not None:
                 engine.ops_sched.copy_(host_ops, non_blocking=True)
+            if host_gs is not None:
+                engine.gate_stream.copy_(host_gs, non_blocking=True)
             step()
             if rank == 0:
                 host_out.copy_(gathered, non_blocking=True)
@@ -517,7 +522,7 @@ def bench_ours(args):
             if it > 0:
                 e2e_times.append(time.perf_counter() - t0)
         rec_host = records.cpu().numpy()
-        h2d = (host_ops.numel() * 4 if host_ops is not None else 0)
+        h2d = (host_ops.numel() * 4 if host_ops is not None else 0) + (host_gs.numel() * 4 if host_gs is not None else 0)
         d2h = world * shots * prog.n_meas
         e2e_how = "pinned op stream -> device, simulate, NCCL all_gather_into_tensor, gathered records -> pinned host on rank 0"
     e2e_t = reduce_max(float(np.mean(e2e_times)))
@@ -553,7 +558,9 @@ def bench_ours(args):
         n_front = prog.n_ops - tail_len          # user ops in front of the run (the run is the last tail_len ops)
         b_front = algorithmic_bytes_per_shot(prog, det_flags, meas_nnz, (0, n_front)) * shots
         b_tail = algorithmic_bytes_per_shot(prog, det_flags, meas_nnz, (n_front, prog.n_ops)) * shots
-        kernels = {"headline_front": {"kernel": "interp_planes_kernel (gates-only instantiation)", "ops": n_front,
+        front_name = ("gate_stream_kernel (pre-decoded per-warp streams, image in shared memory, leaves B + QX per shot)"
+                      if getattr(engine, "gate_stream", None) is not None else "interp_planes_kernel (gates-only instantiation)")
+        kernels = {"headline_front": {"kernel": front_name, "ops": n_front,
                                       "launch_ms": split_ms[0], "algorithmic_bytes_per_launch": b_front},
                    "headline_tail": {"kernel": "run_tail_kernel", "ops": tail_len, "launch_ms": split_ms[1],
                                      "algorithmic_bytes_per_launch": b_tail}}
@@ -680,6 +687,7 @@ def bench_ours(args):
         "dtype": "u8", "data": "synthetic",
         "config": shared_config(prog, world),
         "run": {"shots_per_gpu_per_step": shots, "mode": args.mode or "auto", "kernel": kernel_name,
+                "step_kernels": [k["kernel"].split(" (")[0] for k in kernels.values()] if kernels else [dominant],
                 "tableau_store_mib_per_step": (shots * L.shot_bytes / 2**20) if need_tab else 0.0,
                 "gather_ms_per_step": gather_ms if world > 1 else 0.0,
                 "gather_bytes_received_per_gpu_per_step": (world - 1) * shots * prog.n_meas},
