@@ -637,6 +637,15 @@ int sdimb_export(const void* tableau, int n, int d, int64_t shot, int64_t* x, in
 // the simulation of a small batch).  Calls on the same device are serialised by that workspace's mutex; host threads
 // driving different GPUs do not touch each other's workspace.  sdimb_release_workspace() frees all of them.
 namespace {
+struct HostPlan {          // see sdimb_simulate_host
+  bool valid = false;
+  int n = 0, d = 0, kernel = 0;
+  int64_t shots = 0, n_meas = 0, up_n = 0, tail_len = 0, gs_rows = 0;
+  uint32_t flags = 0, mode_flags = 0, sched_flag = 0;
+  uint64_t knobs = 0;
+  bool sched_used = false;
+  std::vector<int32_t> ops, sched, gstream;
+};
 struct HostWorkspace {
   std::mutex mu;
   int device = -1;
@@ -646,6 +655,7 @@ struct HostWorkspace {
   size_t pin_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  HostPlan plan;
   void release() {
     if (dev) cudaFree(dev);
     if (pin) cudaFreeHost(pin);
@@ -653,6 +663,7 @@ struct HostWorkspace {
     if (e1) cudaEventDestroy(e1);
     if (stream) cudaStreamDestroy(stream);
     dev = pin = nullptr; dev_cap = pin_cap = 0; stream = nullptr; e0 = e1 = nullptr; device = -1;
+    plan = HostPlan();
   }
   bool prepare(int cur, size_t dev_bytes, size_t pin_bytes) {   // caller holds mu and has `cur` as current device
     device = cur;
@@ -677,6 +688,79 @@ struct HostWorkspace {
 constexpr int kMaxDevices = 64;
 HostWorkspace g_ws_by_device[kMaxDevices];
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// everything a developer knob can change in a host plan (tests flip them between calls)
+uint64_t host_plan_knobs(int n, int d) {
+  uint64_t k = 0;
+  auto mix = [&](uint64_t v) { k = (k ^ v) * 0x100000001B3ull; };
+  mix(gate_stream_shape_ok(n, d)); mix(gate_stream_in_smem(n, d)); mix((uint64_t)gate_stream_warps(n, d));
+  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d));
+  for (const char* name : {"SDIMB_GM_MIN_RUN", "SDIMB_CLUSTER_SIZE", "SDIMB_CLUSTER_THREADS"}) {
+    const char* v = std::getenv(name);
+    mix(v ? (uint64_t)std::atoll(v) + 1 : 0);
+  }
+  return k;
+}
+
+int make_host_plan(int n, int d, int64_t shots, uint32_t flags, const int32_t* ops, int64_t n_ops, int64_t n_meas,
+                   const SdimbLayout& L, HostPlan& hp) {
+  int rc;
+  uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES |
+                                 SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER | SDIMB_NO_TILE);
+  int kernel = plan_kernel(n, d, mode_flags, L.np);
+  if (kernel < 0) return kernel;
+  // A few shots of a d = 2, 3 tableau too large for shared memory: one uint8 tableau per thread-block cluster beats
+  // one CTA per shot on bit planes (n = 2048, 8 shots: 12.8 ms against 30 ms), as long as every shot gets a cluster
+  if (kernel == 3 && !(mode_flags & SDIMB_FORCE_PLANES) && planes::planes_smem_bytes(n, d) > (size_t)kSmemLimit &&
+      plan_cluster(L, shots, mode_flags) > 0) {
+    mode_flags |= SDIMB_FORCE_LANES;
+    kernel = plan_kernel(n, d, mode_flags, L.np);
+    if (kernel < 0) return kernel;
+  }
+  std::vector<int32_t>& sched = hp.sched;
+  const int32_t* up_ops = ops;
+  int64_t up_n = n_ops;
+  uint32_t sched_flag = 0;
+  // bit-plane interpreter and cluster interpreter (wide rows on the HBM store): upload the layered stream
+  const bool maybe_cluster = kernel == 0 && !(flags & SDIMB_NO_CLUSTER) && (L.lanes / 4 > kMaxThreads || (flags & SDIMB_CLUSTER));
+  // (a tile-interpreter call above 64 qudits is scheduled too: it may turn into a two-kernel call, see below)
+  const bool tile_to_two = kernel == 5 && n > 64 && mode_flags == 0 && n_meas > 0;
+  if ((kernel == 2 || kernel == 3 || maybe_cluster || tile_to_two) && n_ops > 0) {
+    sched.resize((size_t)(2 * n_ops + 1) * 4);
+    rc = sdimb_schedule(n, ops, n_ops, sched.data(), 2 * n_ops + 1, &up_n);
+    if (rc) return rc;
+    up_ops = sched.data();
+    sched_flag = SDIMB_SCHEDULED;
+  }
+  // Every measurement in the trailing run: the two-kernel path (gate_stream_kernel + run_tail_kernel) beats the
+  // shared-memory interpreters where those fit, and the tile interpreter above 64 qudits (TableauEngine._auto_mode)
+  if ((kernel == 2 || tile_to_two) && mode_flags == 0 && sched_flag) {
+    const int64_t t = sdimb_tail_run(up_ops, up_n);
+    if (t > 0 && t == n_meas && gate_stream_shape_ok(n, d) && tail_run_shape_ok(n, d) &&
+        plan_kernel(n, d, SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL, L.np) == 3) {
+      mode_flags = SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL;
+      kernel = 3;
+    } else if (tile_to_two) {         // stays with the tiles, on the stream as the caller wrote it
+      up_ops = ops; up_n = n_ops; sched_flag = 0;
+    }
+  }
+
+  const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
+  // the gates in front of a tail run that holds every measurement: pre-decoded per-warp streams (planes_stream.cuh)
+  std::vector<int32_t>& gstream = hp.gstream;
+  int64_t gs_rows = 0;
+  if (kernel == 3 && tail_len > 0 && tail_len == n_meas && gate_stream_shape_ok(n, d) &&
+      sdimb_gate_stream(n, d, up_ops, up_n - tail_len, nullptr, 0, &gs_rows) == SDIMB_OK && gs_rows > 0) {
+    gstream.resize((size_t)gs_rows * 4);
+    if (sdimb_gate_stream(n, d, up_ops, up_n - tail_len, gstream.data(), gs_rows, &gs_rows) != SDIMB_OK) gs_rows = 0;
+  } else {
+    gs_rows = 0;
+  }
+  hp.mode_flags = mode_flags; hp.sched_flag = sched_flag; hp.kernel = kernel;
+  hp.sched_used = up_ops != ops;
+  hp.up_n = up_n; hp.tail_len = tail_len; hp.gs_rows = gs_rows;
+  return SDIMB_OK;
+}
 }  // namespace
 
 int sdimb_release_workspace(void) {
@@ -715,45 +799,32 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   if (n_noise > 0 && !replay_noise && (!noise_thresh24 || !noise_channel)) return SDIMB_EINVAL;
   if (shots == 0) return SDIMB_OK;
 
-  uint32_t mode_flags = flags & (SDIMB_FORCE_GLOBAL | SDIMB_FORCE_RESIDENT | SDIMB_FORCE_LANES |
-                                 SDIMB_FORCE_PLANES | SDIMB_CLUSTER | SDIMB_NO_CLUSTER | SDIMB_NO_TILE);
-  int kernel = plan_kernel(n, d, mode_flags, L.np);
-  if (kernel < 0) return kernel;
-  // A few shots of a d = 2, 3 tableau too large for shared memory: one uint8 tableau per thread-block cluster beats
-  // one CTA per shot on bit planes (n = 2048, 8 shots: 12.8 ms against 30 ms), as long as every shot gets a cluster
-  if (kernel == 3 && !(mode_flags & SDIMB_FORCE_PLANES) && planes::planes_smem_bytes(n, d) > (size_t)kSmemLimit &&
-      plan_cluster(L, shots, mode_flags) > 0) {
-    mode_flags |= SDIMB_FORCE_LANES;
-    kernel = plan_kernel(n, d, mode_flags, L.np);
-    if (kernel < 0) return kernel;
-  }
-  std::vector<int32_t> sched;
-  const int32_t* up_ops = ops;
-  int64_t up_n = n_ops;
-  uint32_t sched_flag = 0;
-  // bit-plane interpreter and cluster interpreter (wide rows on the HBM store): upload the layered stream
-  const bool maybe_cluster = kernel == 0 && !(flags & SDIMB_NO_CLUSTER) && (L.lanes / 4 > kMaxThreads || (flags & SDIMB_CLUSTER));
-  // (a tile-interpreter call above 64 qudits is scheduled too: it may turn into a two-kernel call, see below)
-  const bool tile_to_two = kernel == 5 && n > 64 && mode_flags == 0 && n_meas > 0;
-  if ((kernel == 2 || kernel == 3 || maybe_cluster || tile_to_two) && n_ops > 0) {
-    sched.resize((size_t)(2 * n_ops + 1) * 4);
-    rc = sdimb_schedule(n, ops, n_ops, sched.data(), 2 * n_ops + 1, &up_n);
+  // ---- host-side plan of the call: interpreter choice, scheduled stream, tail run, compiled gate streams.  A pure
+  // function of (n, d, shots, flags, op stream, developer knobs); the workspace keeps the plan of its last program, so
+  // a caller that simulates one program batch after batch (Program.simulate's waves, bench.py's steps) pays the
+  // scheduler and the gate-stream compiler once.  The op stream is compared byte for byte.
+  int cur_dev = 0;
+  if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= kMaxDevices) { cudaGetLastError(); return SDIMB_ECUDA; }
+  HostWorkspace& g_ws = g_ws_by_device[cur_dev];
+  std::lock_guard<std::mutex> lock(g_ws.mu);
+  HostPlan& hp = g_ws.plan;
+  const uint64_t knobs = host_plan_knobs(n, d);
+  const bool hit = hp.valid && hp.n == n && hp.d == d && hp.shots == shots && hp.flags == flags && hp.n_meas == n_meas &&
+                   hp.knobs == knobs && (int64_t)hp.ops.size() == 4 * n_ops &&
+                   (n_ops == 0 || std::memcmp(hp.ops.data(), ops, (size_t)n_ops * 16) == 0);
+  if (!hit) {
+    hp.valid = false;
+    rc = make_host_plan(n, d, shots, flags, ops, n_ops, n_meas, L, hp);
     if (rc) return rc;
-    up_ops = sched.data();
-    sched_flag = SDIMB_SCHEDULED;
+    hp.n = n; hp.d = d; hp.shots = shots; hp.flags = flags; hp.n_meas = n_meas; hp.knobs = knobs;
+    hp.ops.assign(ops, ops + 4 * n_ops);
+    hp.valid = true;
   }
-  // Every measurement in the trailing run: the two-kernel path (gate_stream_kernel + run_tail_kernel) beats the
-  // shared-memory interpreters where those fit, and the tile interpreter above 64 qudits (TableauEngine._auto_mode)
-  if ((kernel == 2 || tile_to_two) && mode_flags == 0 && sched_flag) {
-    const int64_t t = sdimb_tail_run(up_ops, up_n);
-    if (t > 0 && t == n_meas && gate_stream_shape_ok(n, d) && tail_run_shape_ok(n, d) &&
-        plan_kernel(n, d, SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL, L.np) == 3) {
-      mode_flags = SDIMB_FORCE_PLANES | SDIMB_FORCE_GLOBAL;
-      kernel = 3;
-    } else if (tile_to_two) {         // stays with the tiles, on the stream as the caller wrote it
-      up_ops = ops; up_n = n_ops; sched_flag = 0;
-    }
-  }
+  const uint32_t mode_flags = hp.mode_flags, sched_flag = hp.sched_flag;
+  const int kernel = hp.kernel;
+  const int32_t* up_ops = hp.sched_used ? hp.sched.data() : ops;
+  const int64_t up_n = hp.up_n, tail_len = hp.tail_len, gs_rows = hp.gs_rows;
+  const std::vector<int32_t>& gstream = hp.gstream;
 
   // carve the device arena
   const size_t eb = (size_t)L.rec_bytes;     // records / replayed outcomes / replayed exponents: 1 byte, 2 for d > 127
@@ -763,25 +834,10 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_th = (n_noise && noise_thresh24) ? align256((size_t)n_noise * 4) : 0;
   const size_t b_ch = (n_noise && noise_channel) ? align256((size_t)n_noise) : 0;
   const size_t b_tab = (kernel == 0 || kernel == 4) ? align256((size_t)shots * L.shot_bytes) : 0;
-  const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
-  // the gates in front of a tail run that holds every measurement: pre-decoded per-warp streams (planes_stream.cuh)
-  std::vector<int32_t> gstream;
-  int64_t gs_rows = 0;
-  if (kernel == 3 && tail_len > 0 && tail_len == n_meas && gate_stream_shape_ok(n, d) &&
-      sdimb_gate_stream(n, d, up_ops, up_n - tail_len, nullptr, 0, &gs_rows) == SDIMB_OK && gs_rows > 0) {
-    gstream.resize((size_t)gs_rows * 4);
-    if (sdimb_gate_stream(n, d, up_ops, up_n - tail_len, gstream.data(), gs_rows, &gs_rows) != SDIMB_OK) gs_rows = 0;
-  } else {
-    gs_rows = 0;
-  }
   const size_t b_gs = align256((size_t)gs_rows * 16);
   const size_t b_scr = align256((size_t)sdimb_scratch_bytes_shots(n, d, mode_flags, tail_len ? shots : 0));
   const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_gs + b_scr + 256;
 
-  int cur_dev = 0;
-  if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= kMaxDevices) { cudaGetLastError(); return SDIMB_ECUDA; }
-  HostWorkspace& g_ws = g_ws_by_device[cur_dev];
-  std::lock_guard<std::mutex> lock(g_ws.mu);
   if (!g_ws.prepare(cur_dev, total, b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
   cudaStream_t st = g_ws.stream;
   uint8_t* base = (uint8_t*)g_ws.dev;
