@@ -39,6 +39,7 @@ namespace {
 #include "util_kernels.cuh"
 #include "frames.cuh"
 #include "wide.cuh"
+#include "lanes_gm.cuh"
 
 bool is_prime(int d) {
   if (d < 2) return false;
@@ -237,6 +238,29 @@ PlaneKernel gate_stream_kernel_for(int n, int d) {
   }
   if (il) return (d == 2) ? planes::gate_stream_kernel<2, true, false> : planes::gate_stream_kernel<3, true, false>;
   return (d == 2) ? planes::gate_stream_kernel<2, false, false> : planes::gate_stream_kernel<3, false, false>;
+}
+
+// Trailing measurement run on uint8 lanes (lanes_gm.cuh): resident CTAs, scratch (counter + one B8 slab per resident warp)
+int run_tail8_ctas(int n, int W) {
+  const size_t smem = lanesgm::smem_bytes(n, W);
+  int dev = 0, sms = 0, per_sm = 0;
+  if (smem > (size_t)kSmemLimit || cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaFuncSetAttribute(lanesgm::run_tail8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanesgm::run_tail8_kernel, 32 * lanesgm::kWarps, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  return sms * per_sm;
+}
+size_t tail8_scratch_bytes(int n, int W, int ctas) { return 256 + (size_t)ctas * lanesgm::kWarps * lanesgm::slab_bytes(n, W); }
+bool tail8_enabled() { return std::getenv("SDIMB_NO_TAIL8") == nullptr; }    // developer knob (A/B timings, tests)
+// length of the run of plain M ops that ends an UNSCHEDULED host stream, 0 if shorter than the scheduler's run threshold
+int64_t raw_tail_run(int n, const int32_t* ops, int64_t n_ops) {
+  int64_t t = 0;
+  while (t < n_ops && (ops[4 * (n_ops - 1 - t)] & SDIMB_OP_MASK) == SDIMB_OP_M) ++t;
+  const int64_t min_run = n / 8 > 4 ? n / 8 : 4;
+  return t >= min_run ? t : 0;
 }
 
 // Cluster interpreter (clusters.cuh) for a call that plan_kernel sends to the HBM store: cluster size, or 0 for
@@ -595,9 +619,20 @@ int sdimb_run(const SdimbRunArgs* caller) {
       return SDIMB_OK;
     }
   }
+  // HBM store, fresh shots, tableau not kept, the caller says where the trailing run of M ops starts and brought
+  // scratch for the slabs: that run goes to run_tail8_kernel (one warp per shot on a generator-major copy, lanes_gm.cuh)
+  int64_t tail8 = 0;
+  int tail8_ctas = 0;
+  if (kernel == 0 && (a->flags & SDIMB_FRESH) && !(a->flags & (SDIMB_WRITEBACK | SDIMB_SCHEDULED)) && tail8_enabled() &&
+      lanesgm::shape_ok(a->n, a->d) && a->tail_run_len > 0 && a->tail_run_len <= a->n_ops && a->scratch) {
+    tail8_ctas = run_tail8_ctas(a->n, L.lanes);
+    if (tail8_ctas >= 1 && a->scratch_bytes >= (int64_t)tail8_scratch_bytes(a->n, L.lanes, tail8_ctas)) tail8 = a->tail_run_len;
+  }
+  if (tail8) p.n_ops = a->n_ops - tail8;
+  const int64_t front_meas = a->n_meas - tail8;
   // wide rows streamed from the HBM store: 16 lanes per thread (fewer, fatter threads; 128-bit accesses)
   // ... when the stream is gate-dominated: measurements want many threads per shot, gates want few fat ones
-  p.vec = (kernel == 0 && L.lanes / 4 >= 128 && L.lanes / 16 <= kMaxThreads && a->n_meas * 64 <= a->n_ops) ? 4 : 1;
+  p.vec = (kernel == 0 && L.lanes / 4 >= 128 && L.lanes / 16 <= kMaxThreads && front_meas * 64 <= p.n_ops) ? 4 : 1;
   const int threads = block_threads(L.lanes / p.vec);
   const size_t smem = scratch + (resident ? (size_t)L.shot_bytes : 0);
   auto lane_kernel = p.vec == 4 ? interp_kernel_stream : threads > kMaxThreads ? interp_kernel_wide : interp_kernel;
@@ -607,8 +642,27 @@ int sdimb_run(const SdimbRunArgs* caller) {
     return SDIMB_ECUDA;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > a->shots) grid = a->shots;
+  const bool timed8 = tail8 && (a->flags & SDIMB_TIME_KERNELS) && time_events_ready();
+  if (tail8) g_time_valid = 0;
+  if (timed8) cudaEventRecord(g_time_ev[0], (cudaStream_t)a->stream);
   lane_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)a->stream>>>(p);
   g_launches++;
+  if (cudaGetLastError() != cudaSuccess) return SDIMB_ECUDA;
+  if (tail8) {
+    if (timed8) cudaEventRecord(g_time_ev[1], (cudaStream_t)a->stream);
+    if (cudaMemsetAsync(a->scratch, 0, 256, (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
+    KParams p2 = p;
+    p2.n_ops = a->n_ops;
+    p2.tail_start = a->n_ops - tail8;
+    p2.shot_counter = (unsigned int*)a->scratch;
+    p2.gm_slab = (uint32_t*)((uint8_t*)a->scratch + 256);
+    p2.gm_slab_words = (int64_t)(lanesgm::slab_bytes(a->n, L.lanes) / 4);
+    int64_t grid2 = (a->shots + lanesgm::kWarps - 1) / lanesgm::kWarps;
+    if (grid2 > tail8_ctas) grid2 = tail8_ctas;
+    lanesgm::run_tail8_kernel<<<(unsigned)grid2, 32 * lanesgm::kWarps, lanesgm::smem_bytes(a->n, L.lanes), (cudaStream_t)a->stream>>>(p2);
+    g_launches++;
+    if (timed8) { cudaEventRecord(g_time_ev[2], (cudaStream_t)a->stream); g_time_valid = 1; }
+  }
   return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
 }
 
@@ -694,7 +748,7 @@ uint64_t host_plan_knobs(int n, int d) {
   uint64_t k = 0;
   auto mix = [&](uint64_t v) { k = (k ^ v) * 0x100000001B3ull; };
   mix(gate_stream_shape_ok(n, d)); mix(gate_stream_in_smem(n, d)); mix((uint64_t)gate_stream_warps(n, d));
-  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d));
+  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d)); mix(tail8_enabled());
   for (const char* name : {"SDIMB_GM_MIN_RUN", "SDIMB_CLUSTER_SIZE", "SDIMB_CLUSTER_THREADS"}) {
     const char* v = std::getenv(name);
     mix(v ? (uint64_t)std::atoll(v) + 1 : 0);
@@ -745,7 +799,10 @@ int make_host_plan(int n, int d, int64_t shots, uint32_t flags, const int32_t* o
     }
   }
 
-  const int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
+  int64_t tail_len = sched_flag ? sdimb_tail_run(up_ops, up_n) : 0;
+  // uint8 lanes on the HBM store, one CTA per shot: the trailing run of M ops of the stream as the caller wrote it
+  if (kernel == 0 && !sched_flag && lanesgm::shape_ok(n, d) && tail8_enabled() && plan_cluster(L, shots, mode_flags) == 0)
+    tail_len = raw_tail_run(n, ops, n_ops);
   // the gates in front of a tail run that holds every measurement: pre-decoded per-warp streams (planes_stream.cuh)
   std::vector<int32_t>& gstream = hp.gstream;
   int64_t gs_rows = 0;
@@ -1191,6 +1248,11 @@ int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags) {
 int64_t sdimb_scratch_bytes_shots(int n, int d, uint32_t flags, int64_t shots) {
   const int64_t base = sdimb_scratch_bytes(n, d, flags);
   SdimbLayout L;
+  if (shots > 0 && !sdimb_layout(n, d, &L) && plan_kernel(n, d, flags, L.np) == 0 && lanesgm::shape_ok(n, d) && tail8_enabled()) {
+    int c8 = run_tail8_ctas(n, L.lanes);                 // uint8 lanes on the HBM store: one B8 slab per resident warp
+    if (c8 < 1) c8 = 148 * 8;
+    return (int64_t)tail8_scratch_bytes(n, L.lanes, c8);
+  }
   if (shots <= 0 || sdimb_layout(n, d, &L) || plan_kernel(n, d, flags, L.np) != 3 || !tail_run_shape_ok(n, d)) return base;
   int ctas = run_tail_ctas(n, d);
   if (ctas < 1) ctas = 148 * planes::kRunCtasPerSm;     // no device: the size a B200 would need

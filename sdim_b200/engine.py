@@ -61,6 +61,12 @@ class TableauEngine:
         if self.tail_run_len and self.tail_run_len == prog.n_meas and prog.dimension in (2, 3):
             gs = N.gate_stream(prog.num_qudits, prog.dimension, sched[: sched.shape[0] - self.tail_run_len])
             self.gate_stream = torch.from_numpy(gs).to(dev) if gs is not None else None
+        # uint8 lanes on the HBM store run the stream as written: its trailing run of plain M ops (lanes_gm.cuh),
+        # if at least as long as the scheduler's run threshold
+        t = 0
+        while t < prog.n_ops and int(prog.ops[prog.n_ops - 1 - t][0]) == 14:
+            t += 1
+        self.tail_run_len_raw = t if t >= max(prog.num_qudits // 8, 4) else 0
         self.noise_thresh = torch.from_numpy(prog.noise_thresh24.astype(np.int64)).to(dev).to(torch.int32) \
             if prog.n_noise else None
         if prog.n_noise:
@@ -198,6 +204,8 @@ class TableauEngine:
             a.seed = seed & 0xFFFFFFFFFFFFFFFF
             a.stream = torch.cuda.current_stream(dev).cuda_stream
             tail = self.tail_run_len if (use_sched and not keep_tableau) else 0
+            if kernel == "lanes-global" and not use_sched and fresh and not keep_tableau and op_range is None:
+                tail = self.tail_run_len_raw
             scratch = self._scratch_for(self.MODES[mode], shots if tail else 0)
             a.scratch, a.scratch_bytes = _ptr(scratch), (scratch.numel() if scratch is not None else 0)
             a.tail_run_len = tail

@@ -446,6 +446,49 @@ def test_tail_run_kernel_on_the_reference_goldens(golden_random, golden_config_s
     assert (two_kernels >= 20) if min_run == "2" else (two_kernels == 0)
 
 
+@pytest.mark.parametrize("off", [False, True])
+@pytest.mark.parametrize("d,n,depth", [(5, 256, 2500), (7, 97, 1500), (3, 130, 1200), (2, 200, 1500), (13, 40, 900),
+                                       (127, 64, 700), (5, 500, 900), (11, 5, 300), (5, 512, 600)])
+def test_lanes_tail_run_kernel_matches_c_oracle(monkeypatch, d, n, depth, off):
+    """uint8 lanes on the HBM store ("global"): the run of M ops that ends the stream executes in run_tail8_kernel — one
+    warp per shot on a generator-major byte copy (lanes_gm.cuh) — for every prime d <= 127, ragged n up to 512, all
+    opcodes incl. mid-circuit M / M_X / RESET and noise in front of it, Philox draws and replayed outcomes; the records of
+    every shot vs the C oracle, with the second kernel and without it (SDIMB_NO_TAIL8), and from the host-buffer entry."""
+    import torch
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import TableauEngine, simulate_host
+    if off:
+        monkeypatch.setenv("SDIMB_NO_TAIL8", "1")
+    prog = random_program(seed=500 * d + n, n=n, d=d, depth=depth)
+    eng = TableauEngine(prog)
+    assert eng.tail_run_len_raw >= n
+    shots, seed = (600 if n <= 130 else 150), 19
+    before = _launches()
+    got = eng.run(shots, 7, seed, mode="global").cpu().numpy()
+    assert _launches() - before == (1 if off else 2)
+    want, _ = c_oracle.run(n, d, prog.ops, shots, 7, seed, thresh24=prog.noise_thresh24, channel=prog.noise_channel)
+    assert np.array_equal(got, want)
+    host, _ = simulate_host(prog, 40, 7, seed, mode="global")
+    assert np.array_equal(host, want[:40])
+    # replayed outcomes and noise
+    k = 30
+    rng = np.random.default_rng(n + d)
+    rm = rng.integers(0, d, size=(k, prog.n_meas), dtype=np.uint8)
+    rn = rng.integers(0, d, size=(k, prog.n_noise, 2), dtype=np.uint8)
+    got = eng.run(k, 0, seed, torch.from_numpy(rm), torch.from_numpy(rn), mode="global").cpu().numpy()
+    want, _ = c_oracle.run(n, d, prog.ops, k, 0, seed, replay_meas=rm, replay_noise=rn)
+    assert np.array_equal(got, want)
+    # the tableau is kept: one kernel, same records, final tableau vs the oracle
+    before = _launches()
+    got = eng.run(8, 0, seed, keep_tableau=True, mode="global").cpu().numpy()
+    assert _launches() - before == 1
+    want, fin = c_oracle.run(n, d, prog.ops, 8, 0, seed, thresh24=prog.noise_thresh24, channel=prog.noise_channel, want_final=True)
+    assert np.array_equal(got, want)
+    arrs = eng.export(eng.tableau, 7)
+    assert all(np.array_equal(arrs[key], fin[key]) for key in ("x", "z", "p", "dx", "dz", "dp"))
+
+
 @pytest.mark.parametrize("form", ["smem-8", "smem-4", "smem-3", "global", "off"])
 @pytest.mark.parametrize("d,n,depth,il", [(3, 256, 2500, "100000"), (2, 300, 3000, "100000"), (3, 97, 1500, "0"),
                                           (2, 33, 900, "100000"), (3, 500, 1200, "0"), (2, 512, 1500, "100000"),
