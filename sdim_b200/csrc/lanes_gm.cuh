@@ -19,8 +19,6 @@
 namespace lanesgm {
 
 constexpr int kWarps = 4;            // shots in flight per CTA
-constexpr int kMaxT = 4;             // words per lane of one half row of B8 (nq / 4 / 32 <= 4  <=>  n <= 512)
-constexpr int kMaxQ = 8;             // words per lane of one QX8 row (W / 4 / 32 <= 8)
 
 struct GM8 {
   uint8_t* B;          // this warp's slab
@@ -41,12 +39,18 @@ inline size_t warp_smem_bytes(int n, int W) {
 inline size_t smem_bytes(int n, int W) { return kWarps * ((warp_smem_bytes(n, W) + 15) & ~(size_t)15) + 128; }
 inline bool shape_ok(int n, int d) { return d <= 127 && n <= 512; }
 
-// w * s mod d on four packed lanes (s < d, every lane < d)
+// w * s mod d on four packed lanes (s < d, every lane < d).  The slow path is one out-of-line function: inlined at its
+// ~50 call sites it made the kernel 6 400 instructions (73 KB of hot code) and instruction fetch its top stall
+// (ncu: stall_no_inst 43 %, gpurun_out/l8b); code size is a resource here as in round 1.
+__device__ __noinline__ uint32_t smul4_slow(uint32_t d, uint32_t md, uint32_t w, uint32_t s) {
+  const uint32_t a = (w & 0xFFu) * s, b = ((w >> 8) & 0xFFu) * s, c = ((w >> 16) & 0xFFu) * s, e = (w >> 24) * s;
+  return (a - d * __umulhi(a, md)) | ((b - d * __umulhi(b, md)) << 8) | ((c - d * __umulhi(c, md)) << 16) |
+         ((e - d * __umulhi(e, md)) << 24);
+}
 __device__ __forceinline__ uint32_t smul4(const Arith& A, uint32_t w, uint32_t s) {
   if (w == 0u || s == 0u) return 0u;
   if (s == 1u) return w;
-  return mod_d(A, (w & 0xFFu) * s) | (mod_d(A, ((w >> 8) & 0xFFu) * s) << 8) | (mod_d(A, ((w >> 16) & 0xFFu) * s) << 16) |
-         (mod_d(A, (w >> 24) * s) << 24);
+  return smul4_slow(A.d, A.md, w, s);
 }
 
 // Ordered compaction of the non-zero bytes of a word vector held `words` per lane at word index lane + 32 t:
@@ -77,9 +81,12 @@ __device__ __forceinline__ int compact_bytes(const uint32_t* vec, int n_words, u
 }
 
 // store -> B8: tile = 32 qudits x one 4-lane word per lane; the lane then owns 32 consecutive bytes of four generator rows
-__device__ __forceinline__ void transpose_in(const GM8& M, int lane) {
+__device__ __noinline__ void transpose_in(const GM8& M, int lane) {
+#pragma unroll 1
   for (int half = 0; half < 2; ++half) {                        // X block, then Z block
+#pragma unroll 1
     for (int q0 = 0; q0 < M.nq; q0 += 32) {
+#pragma unroll 1
       for (int w0 = 0; w0 < M.Ww; w0 += 32) {
         const int w = w0 + lane;
         if (w >= M.Ww) continue;
@@ -108,18 +115,26 @@ __device__ __forceinline__ void transpose_in(const GM8& M, int lane) {
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
-// Measurement of qudit q by one warp; returns the record byte.
+// Measurement of qudit q by one warp; returns the record byte.  NT = words per lane of one half row of B8 (1, 2, 4:
+// n <= 128, 256, 512), a QX8 row has at most 2 NT words per lane.  Rows of a list are processed one at a time (the
+// next one is prefetched into L2): with 32 warps per SM the other shots hide the round trip, and the code stays small.
+template <int NT>
 __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const Swar& Sd, const int q, const uint32_t draw,
                                              const int lane) {
+  constexpr int NQ = 2 * NT;
   const int nqw = M.nqw, Ww = M.Ww, np = M.np, nq = M.nq;
   // ---- row q of QX8: staged, pivot = first stabilizer lane with an X component (tableau_prime.py:273-283) ----
   uint32_t piv = kNoPivot;
   {
     const uint32_t* rq = reinterpret_cast<const uint32_t*>(M.T + (int64_t)q * M.row_bytes);
-    for (int w = lane; w < Ww; w += 32) {
-      const uint32_t x = rq[w];
-      reinterpret_cast<uint32_t*>(M.xq)[w] = x;
-      if (x && 4 * w < np && piv == kNoPivot) piv = 4u * w + ((__ffs(x) - 1) >> 3);
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int w = lane + 32 * t;
+      if (w < Ww) {
+        const uint32_t x = rq[w];
+        reinterpret_cast<uint32_t*>(M.xq)[w] = x;
+        if (x && 4 * w < np && piv == kNoPivot) piv = 4u * w + ((__ffs(x) - 1) >> 3);
+      }
     }
     piv = __reduce_min_sync(0xFFFFFFFFu, piv);
     __syncwarp();
@@ -130,10 +145,10 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
     const uint32_t e = M.inv[M.xq[piv]];
     uint32_t* const Bp = reinterpret_cast<uint32_t*>(M.B + (size_t)piv * 2 * nq);
     uint32_t* const Bd = reinterpret_cast<uint32_t*>(M.B + (size_t)(np + piv) * 2 * nq);
-    uint32_t xs[kMaxT], zs[kMaxT], odx[kMaxT];
+    uint32_t xs[NT], zs[NT], odx[NT];
     uint32_t sd_raw = 0;
 #pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
+    for (int t = 0; t < NT; ++t) {
       const int w = lane + 32 * t;
       xs[t] = zs[t] = odx[t] = 0u;
       if (w < nqw) {
@@ -149,118 +164,97 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
     const uint32_t ps = mod_o(A, ps_old * e + A.po * mod_d(A, sd_raw * mod_d(A, (e * (e - 1u)) >> 1)));
     const uint32_t sd = mod_d(A, mod_d(A, sd_raw * e) * e);     // x_p . z_p after exponentiation
     // factors f_i = -X[q,i] of every lane but the pivot and its destabilizer (both are replaced below)
-    for (int w = lane; w < Ww; w += 32) {
-      uint32_t fw = swar_neg(Sd, reinterpret_cast<const uint32_t*>(M.xq)[w]);
-      if ((int)(piv >> 2) == w) fw &= ~(0xFFu << (8 * (piv & 3)));
-      if ((int)((np + piv) >> 2) == w) fw &= ~(0xFFu << (8 * ((np + piv) & 3)));
-      reinterpret_cast<uint32_t*>(M.f8)[w] = fw;
+    const int wp = (int)(piv >> 2), wd = (int)((np + piv) >> 2);
+    const uint32_t mp = ~(0xFFu << (8 * (piv & 3))), md = ~(0xFFu << (8 * ((np + piv) & 3)));
+#pragma unroll
+    for (int t = 0; t < NQ; ++t) {
+      const int w = lane + 32 * t;
+      if (w < Ww) {
+        uint32_t fw = swar_neg(Sd, reinterpret_cast<const uint32_t*>(M.xq)[w]);
+        if (w == wp) fw &= mp;
+        if (w == wd) fw &= md;
+        reinterpret_cast<uint32_t*>(M.f8)[w] = fw;
+      }
     }
     __syncwarp();
     const int total = compact_bytes(reinterpret_cast<const uint32_t*>(M.f8), Ww, M.gl, M.gf, lane);
-    // row_i += f_i * pivot for every listed generator, two rows in flight      (tableau_prime.py:306-321)
-    for (int k0 = 0; k0 < total; k0 += 2) {
-      uint32_t xa[2][kMaxT], za[2][kMaxT];
-      int gi[2];
-      uint32_t fi[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        gi[u] = -1; fi[u] = 0;
-        if (k0 + u < total) { gi[u] = M.gl[k0 + u]; fi[u] = M.gf[k0 + u]; }
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-          const int w = lane + 32 * t;
-          xa[u][t] = za[u][t] = 0u;
-          if (gi[u] >= 0 && w < nqw) {
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(M.B + (size_t)gi[u] * 2 * nq);
-            xa[u][t] = row[w]; za[u][t] = row[nqw + w];
-          }
-        }
+    // row_i += f_i * pivot for every listed generator      (tableau_prime.py:306-321)
+#pragma unroll 1
+    for (int k = 0; k < total; ++k) {
+      const int gi = M.gl[k];
+      const uint32_t f = M.gf[k];
+      uint32_t* const row = reinterpret_cast<uint32_t*>(M.B + (size_t)gi * 2 * nq);
+      if (k + 1 < total) {
+        const uint32_t* nxt = reinterpret_cast<const uint32_t*>(M.B + (size_t)M.gl[k + 1] * 2 * nq);
+        if (lane < 2 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32 * lane));
       }
+      uint32_t xa[NT], za[NT];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (gi[u] < 0) break;                                     // warp-uniform
-        uint32_t* row = reinterpret_cast<uint32_t*>(M.B + (size_t)gi[u] * 2 * nq);
-        uint32_t dot = 0;
+      for (int t = 0; t < NT; ++t) {
+        const int w = lane + 32 * t;
+        xa[t] = za[t] = 0u;
+        if (w < nqw) { xa[t] = row[w]; za[t] = row[nqw + w]; }
+      }
+      uint32_t dot = 0;
 #pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-          const int w = lane + 32 * t;
-          if (w < nqw) {
-            dot = __dp4a(za[u][t], xs[t], dot);                   // Z[:,i] . xs (old Z)
-            if (xs[t]) row[w] = swar_add(Sd, xa[u][t], smul4(A, xs[t], fi[u]));
-            if (zs[t]) row[nqw + w] = swar_add(Sd, za[u][t], smul4(A, zs[t], fi[u]));
-          }
-        }
-        dot = warp_sum(dot);
-        if (lane == 0) {
-          // P_i += f*ps + po*((Z_i.xs)*f + sd*f(f-1)/2*po)      (tableau_prime.py:310-312,317-319)
-          const uint32_t f = fi[u], g = mod_d(A, (f * (f - 1u)) >> 1);
-          const uint32_t cp = mod_d(A, mod_d(A, dot) * f + sd * g * A.po);
-          M.ph8[gi[u]] = (uint8_t)mod_o(A, (uint32_t)M.ph8[gi[u]] + f * ps + A.po * cp);
-        }
+      for (int t = 0; t < NT; ++t) {
+        const int w = lane + 32 * t;
+        dot = __dp4a(za[t], xs[t], dot);                       // Z[:,i] . xs (old Z)
+        if (xs[t]) row[w] = swar_add(Sd, xa[t], smul4(A, xs[t], f));
+        if (zs[t]) row[nqw + w] = swar_add(Sd, za[t], smul4(A, zs[t], f));
+      }
+      dot = warp_sum(dot);
+      if (lane == 0) {
+        // P_i += f*ps + po*((Z_i.xs)*f + sd*f(f-1)/2*po)      (tableau_prime.py:310-312,317-319)
+        const uint32_t g = mod_d(A, (f * (f - 1u)) >> 1);
+        const uint32_t cp = mod_d(A, mod_d(A, dot) * f + sd * g * A.po);
+        M.ph8[gi] = (uint8_t)mod_o(A, (uint32_t)M.ph8[gi] + f * ps + A.po * cp);
       }
     }
     // QX8: X[r,:] += xs_r * f on the pivot's X support; column p <- 0, column np + p <- xs (also where only the old
-    // destabilizer had an entry)
-    {
-      uint32_t un[kMaxT];
-      // list the rows through a union vector staged in gf's space?  no: compact xs | odx markers directly
+    // destabilizer had an entry).  Marker byte of a row = xs_r, or 0x80 where only the old destabilizer is non-zero.
 #pragma unroll
-      for (int t = 0; t < kMaxT; ++t) {
-        // marker byte = xs_r, or 0x80 where only the old destabilizer is non-zero (xs_r < 128 always)
-        const uint32_t x = xs[t], o = odx[t];
-        uint32_t m = x;
+    for (int t = 0; t < NT; ++t) {
+      const int w = lane + 32 * t;
+      const uint32_t x = xs[t], o = odx[t];
+      uint32_t m = x;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (!((x >> (8 * k)) & 0xFFu) && ((o >> (8 * k)) & 0xFFu)) m |= 0x80u << (8 * k);
-        un[t] = m;
+      for (int k = 0; k < 4; ++k)
+        if (!((x >> (8 * k)) & 0xFFu) && ((o >> (8 * k)) & 0xFFu)) m |= 0x80u << (8 * k);
+      if (w < nqw) reinterpret_cast<uint32_t*>(M.rv)[w] = m;
+    }
+    __syncwarp();
+    const int totq = compact_bytes(reinterpret_cast<const uint32_t*>(M.rv), nqw, M.rl, M.gf, lane);
+#pragma unroll 1
+    for (int k = 0; k < totq; ++k) {
+      const int r = M.rl[k];
+      const uint32_t sv = M.gf[k] & 0x7Fu;
+      uint32_t* const row = reinterpret_cast<uint32_t*>(M.T + (int64_t)r * M.row_bytes);
+      if (k + 1 < totq) {
+        const uint32_t* nxt = reinterpret_cast<const uint32_t*>(M.T + (int64_t)M.rl[k + 1] * M.row_bytes);
+        if (lane < NQ) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32 * lane));
       }
-      // stage the markers in shared memory (rv doubles as the word vector: nq bytes), then compact in order
+      uint32_t xr[NQ];
 #pragma unroll
-      for (int t = 0; t < kMaxT; ++t) {
+      for (int t = 0; t < NQ; ++t) {
         const int w = lane + 32 * t;
-        if (w < nqw) reinterpret_cast<uint32_t*>(M.rv)[w] = un[t];
+        xr[t] = (w < Ww) ? row[w] : 0u;
       }
-      __syncwarp();
-      // (compaction reads rv and writes the values to gf, which is free again)
-      const int totq = compact_bytes(reinterpret_cast<const uint32_t*>(M.rv), nqw, M.rl, M.gf, lane);
-      const int wp = (int)(piv >> 2), wd = (int)((np + piv) >> 2);
-      const uint32_t mp = ~(0xFFu << (8 * (piv & 3))), md = ~(0xFFu << (8 * ((np + piv) & 3)));
-      for (int k0 = 0; k0 < totq; k0 += 2) {
-        uint32_t xr[2][kMaxQ];
-        int rr[2];
-        uint32_t sv[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          rr[u] = -1; sv[u] = 0;
-          if (k0 + u < totq) { rr[u] = M.rl[k0 + u]; sv[u] = M.gf[k0 + u] & 0x7Fu; }
-#pragma unroll
-          for (int t = 0; t < kMaxQ; ++t) {
-            const int w = lane + 32 * t;
-            xr[u][t] = 0u;
-            if (rr[u] >= 0 && w < Ww) xr[u][t] = reinterpret_cast<const uint32_t*>(M.T + (int64_t)rr[u] * M.row_bytes)[w];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (rr[u] < 0) break;
-          uint32_t* row = reinterpret_cast<uint32_t*>(M.T + (int64_t)rr[u] * M.row_bytes);
-#pragma unroll
-          for (int t = 0; t < kMaxQ; ++t) {
-            const int w = lane + 32 * t;
-            if (w < Ww) {
-              const uint32_t fw = reinterpret_cast<const uint32_t*>(M.f8)[w];
-              uint32_t nx = (fw && sv[u]) ? swar_add(Sd, xr[u][t], smul4(A, fw, sv[u])) : xr[u][t];
-              if (w == wp) nx &= mp;
-              if (w == wd) nx = (nx & md) | (sv[u] << (8 * ((np + piv) & 3)));
-              if (nx != xr[u][t]) row[w] = nx;
-            }
-          }
+      for (int t = 0; t < NQ; ++t) {
+        const int w = lane + 32 * t;
+        if (w < Ww) {
+          const uint32_t fw = reinterpret_cast<const uint32_t*>(M.f8)[w];
+          uint32_t nx = (fw && sv) ? swar_add(Sd, xr[t], smul4(A, fw, sv)) : xr[t];
+          if (w == wp) nx &= mp;
+          if (w == wd) nx = (nx & md) | (sv << (8 * ((np + piv) & 3)));
+          if (nx != xr[t]) row[w] = nx;
         }
       }
     }
     // destabilizer p <- (xs, zs, ps); stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333)
 #pragma unroll
-    for (int t = 0; t < kMaxT; ++t) {
+    for (int t = 0; t < NT; ++t) {
       const int w = lane + 32 * t;
       if (w < nqw) {
         Bd[w] = xs[t]; Bd[nqw + w] = zs[t];
@@ -275,43 +269,36 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
   } else {
     // ---- deterministic branch (tableau_prime.py:336-363): ordered product of the stabilizers i with f_i = destab X[q,i] ----
     const int total = compact_bytes(reinterpret_cast<const uint32_t*>(M.xq) + np / 4, np / 4, M.gl, M.gf, lane);
-    uint32_t az[kMaxT];
+    uint32_t az[NT];
 #pragma unroll
-    for (int t = 0; t < kMaxT; ++t) az[t] = 0u;
+    for (int t = 0; t < NT; ++t) az[t] = 0u;
     uint32_t cross = 0, sdg = 0, a1 = 0;
-    for (int k0 = 0; k0 < total; k0 += 2) {
-      uint32_t xa[2][kMaxT], za[2][kMaxT];
-      int gi[2];
-      uint32_t fi[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        gi[u] = -1; fi[u] = 0;
-        if (k0 + u < total) { gi[u] = M.gl[k0 + u]; fi[u] = M.gf[k0 + u]; }
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-          const int w = lane + 32 * t;
-          xa[u][t] = za[u][t] = 0u;
-          if (gi[u] >= 0 && w < nqw) {
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(M.B + (size_t)gi[u] * 2 * nq);
-            xa[u][t] = row[w]; za[u][t] = row[nqw + w];
-          }
-        }
+#pragma unroll 1
+    for (int k = 0; k < total; ++k) {
+      const int gi = M.gl[k];
+      const uint32_t f = M.gf[k], g = mod_d(A, (f * (f - 1u)) >> 1);
+      const uint32_t* const row = reinterpret_cast<const uint32_t*>(M.B + (size_t)gi * 2 * nq);
+      if (k + 1 < total) {
+        const uint32_t* nxt = reinterpret_cast<const uint32_t*>(M.B + (size_t)M.gl[k + 1] * 2 * nq);
+        if (lane < 2 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32 * lane));
       }
+      uint32_t xa[NT], za[NT];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (gi[u] < 0) break;
-        const uint32_t f = fi[u], g = mod_d(A, (f * (f - 1u)) >> 1);
-        uint32_t xz = 0;
-#pragma unroll
-        for (int t = 0; t < kMaxT; ++t) {
-          if (xa[u][t]) cross = __dp4a(smul4(A, xa[u][t], f), az[t], cross);      // ancilla_z . (f * x_i), running ancilla
-          if (za[u][t]) az[t] = swar_add(Sd, az[t], smul4(A, za[u][t], f));
-          xz = __dp4a(xa[u][t], za[u][t], xz);
-        }
-        cross = mod_d(A, cross);
-        sdg = mod_d(A, sdg + mod_d(A, xz) * g);
-        a1 += f * (uint32_t)M.ph8[gi[u]];                                          // every lane, same value
+      for (int t = 0; t < NT; ++t) {
+        const int w = lane + 32 * t;
+        xa[t] = za[t] = 0u;
+        if (w < nqw) { xa[t] = row[w]; za[t] = row[nqw + w]; }
       }
+      uint32_t xz = 0;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if (xa[t]) cross = __dp4a(smul4(A, xa[t], f), az[t], cross);            // ancilla_z . (f * x_i), running ancilla
+        if (za[t]) az[t] = swar_add(Sd, az[t], smul4(A, za[t], f));
+        xz = __dp4a(xa[t], za[t], xz);
+      }
+      cross = mod_d(A, cross);
+      sdg = mod_d(A, sdg + mod_d(A, xz) * g);
+      a1 += f * (uint32_t)M.ph8[gi];                                              // every lane, same value
     }
     const uint32_t part = mod_d(A, warp_sum(mod_d(A, cross + A.po * sdg)));
     const uint32_t ap = mod_o(A, mod_o(A, a1) + A.po * part);
@@ -322,6 +309,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
   return rec;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(32 * kWarps, 8) run_tail8_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -374,7 +362,7 @@ __global__ void __launch_bounds__(32 * kWarps, 8) run_tail8_kernel(const __grid_
       while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        const uint32_t rec = measure8(M, A, Sd, __shfl_sync(0xFFFFFFFFu, mine.y, k), (uint32_t)__shfl_sync(0xFFFFFFFFu, mine.z, k), lane);
+        const uint32_t rec = measure8<NT>(M, A, Sd, __shfl_sync(0xFFFFFFFFu, mine.y, k), (uint32_t)__shfl_sync(0xFFFFFFFFu, mine.z, k), lane);
         if (lane == k) myrec = rec;
       }
       if (is_m) p.records[shot * p.rec_stride + mine.w] = (uint8_t)myrec;

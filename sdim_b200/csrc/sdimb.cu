@@ -241,13 +241,17 @@ PlaneKernel gate_stream_kernel_for(int n, int d) {
 }
 
 // Trailing measurement run on uint8 lanes (lanes_gm.cuh): resident CTAs, scratch (counter + one B8 slab per resident warp)
+PlaneKernel run_tail8_kernel_for(int n) {
+  return n <= 128 ? lanesgm::run_tail8_kernel<1> : n <= 256 ? lanesgm::run_tail8_kernel<2> : lanesgm::run_tail8_kernel<4>;
+}
 int run_tail8_ctas(int n, int W) {
   const size_t smem = lanesgm::smem_bytes(n, W);
+  auto kern8 = run_tail8_kernel_for(n);
   int dev = 0, sms = 0, per_sm = 0;
   if (smem > (size_t)kSmemLimit || cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaFuncSetAttribute(lanesgm::run_tail8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lanesgm::run_tail8_kernel, 32 * lanesgm::kWarps, smem) != cudaSuccess || per_sm < 1) {
+      cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern8, 32 * lanesgm::kWarps, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     return 0;
   }
@@ -659,7 +663,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
     p2.gm_slab_words = (int64_t)(lanesgm::slab_bytes(a->n, L.lanes) / 4);
     int64_t grid2 = (a->shots + lanesgm::kWarps - 1) / lanesgm::kWarps;
     if (grid2 > tail8_ctas) grid2 = tail8_ctas;
-    lanesgm::run_tail8_kernel<<<(unsigned)grid2, 32 * lanesgm::kWarps, lanesgm::smem_bytes(a->n, L.lanes), (cudaStream_t)a->stream>>>(p2);
+    run_tail8_kernel_for(a->n)<<<(unsigned)grid2, 32 * lanesgm::kWarps, lanesgm::smem_bytes(a->n, L.lanes), (cudaStream_t)a->stream>>>(p2);
     g_launches++;
     if (timed8) { cudaEventRecord(g_time_ev[2], (cudaStream_t)a->stream); g_time_valid = 1; }
   }
