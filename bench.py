@@ -289,7 +289,7 @@ def bench_configs(args, dev, world, rank, barrier, reduce_max):
     from sdim_b200.dist import gather_records, shard_range
     from sdim_b200.engine import TableauEngine
     from sdim_b200.ir import compile_circuits
-    from sdim_b200.workloads import qudit_repetition_code, rotated_surface_code
+    from sdim_b200.workloads import noisy_random_clifford, qudit_repetition_code, rotated_surface_code
     scale = args.config_scale
     jobs = [
         ("config2: random Clifford d=3 n=64, depth 2000 + M on all qudits",
@@ -298,6 +298,10 @@ def bench_configs(args, dev, world, rank, barrier, reduce_max):
          rotated_surface_code(7, 7, 1e-3), max(8 * world, int(10 ** 6 * scale))),
         ("config4: qutrit repetition code distance 25, 25 rounds, N1 'f' p=1e-2, RESET ancillas",
          qudit_repetition_code(25, 25, 3, 1e-2, "f"), max(8 * world, int(10 ** 7 * scale))),
+        # not a BASELINE config: the headline circuit family at d = 5 (uint8 lanes on the HBM store, the trailing
+        # measurement run in run_tail8_kernel) — what a d >= 5 user of the headline workload gets
+        ("extra: headline shape at d=5 (noisy random Clifford n=256, depth 2000, N1 p=1e-3, M on all qudits), uint8 lanes",
+         noisy_random_clifford(256, 2000, 5), max(8 * world, int(8192 * scale))),
     ]
     out = []
     stream = torch.cuda.current_stream(dev)

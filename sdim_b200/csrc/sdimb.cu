@@ -775,6 +775,13 @@ int make_host_plan(int n, int d, int64_t shots, uint32_t flags, const int32_t* o
     kernel = plan_kernel(n, d, mode_flags, L.np);
     if (kernel < 0) return kernel;
   }
+  // uint8 lanes that fit in shared memory: from 96 qudits on, the HBM store with the trailing run of M ops in the
+  // generator-major kernel is faster (TableauEngine._auto_mode has the numbers)
+  if (kernel == 1 && mode_flags == 0 && n >= 96 && lanesgm::shape_ok(n, d) && tail8_enabled() && raw_tail_run(n, ops, n_ops) > 0 &&
+      plan_kernel(n, d, SDIMB_FORCE_GLOBAL, L.np) == 0 && plan_cluster(L, shots, SDIMB_FORCE_GLOBAL) == 0) {
+    mode_flags = SDIMB_FORCE_GLOBAL;
+    kernel = 0;
+  }
   std::vector<int32_t>& sched = hp.sched;
   const int32_t* up_ops = ops;
   int64_t up_n = n_ops;

@@ -111,6 +111,12 @@ class TableauEngine:
             kernel = self.plan(None)[0]
             if kernel == "planes-resident" or (kernel == "planes-tile" and self.prog.num_qudits > 64):
                 return "planes-global"
+        # uint8 lanes that would run resident in shared memory: from 96 qudits on, the HBM store with the trailing run of
+        # M ops in the generator-major kernel (lanes_gm.cuh) is faster (d = 5, 4096 shots: n = 96 18.0 vs 20.2 ms,
+        # n = 128 22.4 / 44.5, n = 200 17.8 / 52.6; below that shared memory wins, n = 64: 7.6 / 8.4)
+        if mode in (None, "auto") and self.tail_run_len_raw and not keep_tableau and self.prog.num_qudits >= 96 and \
+                self.plan(None)[0] == "lanes-resident":
+            return "global"
         return mode
 
     def cluster_size(self, shots: int, mode: Optional[str] = None) -> int:
