@@ -8,7 +8,9 @@
 // usual "measure every qudit") is therefore executed by a second kernel, run_tail_kernel: the interpreter leaves
 // every shot's image at its own address (KParams::img_per_shot), and ONE WARP PER SHOT
 //   - transposes the image in registers (32 x 32 bit blocks, five butterfly stages per block) into
-//       B   [2np generators][Wq = np/32 qudit words]  entries (x_l, x_h, z_l, z_h) / (x, z) for d = 2: rows contiguous
+//       B   [np stabilizers][Wq = np/32 qudit words]  entries (x_l, x_h, z_l, z_h) / (x, z) for d = 2: rows contiguous
+//       Bd  [np destabilizers][Wq]                     entries (x_l, x_h) / (x): X ONLY — the run does not keep the tableau,
+//                                                       and a destabilizer's Z part and phase never reach a record
 //       QX  [n qudits][Wb = 2np/32 lane words]        the X half of the qudit-major image, compact (no z, no padding)
 //       ph8 [2np] phases as bytes in shared memory
 //   - and runs every measurement of the run on them:
@@ -50,25 +52,43 @@ template <int D>
 struct GMImg {
   static constexpr int EW = (D == 2) ? 2 : 4;    // words per entry of B
   static constexpr int EX = EW / 2;              // words per entry of QX
-  uint32_t* B;
+  uint32_t* B;                                   // stabilizer rows: [np][Wq] entries of EW words
+  uint32_t* Bd;                                  // destabilizer rows: [np][Wq] entries of EX words — X ONLY: a run that
+                                                 // does not keep the tableau never reads a destabilizer's Z part or phase
+                                                 // (factors come from its X part, tableau_prime.py:350; rowsum writes it)
   uint32_t* QX;
   uint8_t* ph8;
   uint16_t* list;                                // [2np] scratch: compacted generator / row lists
   int n, np, Wq, Wb, gs_shift;                   // group of lanes per B row = 1 << gs_shift >= Wq
-  __device__ __forceinline__ uint32_t* bent(int g, int w) const { return B + (uint32_t)((g * Wq + w) * EW); }
-  __device__ __forceinline__ uint32_t* qent(int r, int j) const { return QX + (uint32_t)((r * Wb + j) * EX); }
-  __device__ __forceinline__ XZ ldB(int g, int w) const {
-    if (D == 3) { const uint4 v = *reinterpret_cast<const uint4*>(bent(g, w)); return XZ{E{v.x, v.y}, E{v.z, v.w}}; }
-    const uint2 v = *reinterpret_cast<const uint2*>(bent(g, w));
-    return XZ{E{v.x, 0u}, E{v.y, 0u}};
+  __device__ __forceinline__ void place(uint32_t* slab) {        // B, Bd, QX of one shot, in this order
+    B = slab;
+    Bd = B + (size_t)np * Wq * EW;
+    QX = Bd + (size_t)np * Wq * EX;
   }
+  __device__ __forceinline__ uint32_t* bent(int g, int w) const { return B + (uint32_t)((g * Wq + w) * EW); }
+  __device__ __forceinline__ uint32_t* dent(int g, int w) const { return Bd + (uint32_t)(((g - np) * Wq + w) * EX); }
+  __device__ __forceinline__ uint32_t* qent(int r, int j) const { return QX + (uint32_t)((r * Wb + j) * EX); }
   __device__ __forceinline__ E ldBx(int g, int w) const {
-    if (D == 3) { const uint2 v = *reinterpret_cast<const uint2*>(bent(g, w)); return E{v.x, v.y}; }
-    return E{bent(g, w)[0], 0u};
+    const uint32_t* e = (g >= np) ? dent(g, w) : bent(g, w);
+    if (D == 3) { const uint2 v = *reinterpret_cast<const uint2*>(e); return E{v.x, v.y}; }
+    return E{e[0], 0u};
+  }
+  __device__ __forceinline__ XZ ldB(int g, int w) const {
+    XZ r{ldBx(g, w), E{0u, 0u}};
+    if (g < np) {
+      if (D == 3) { const uint2 v = *reinterpret_cast<const uint2*>(bent(g, w) + 2); r.z = E{v.x, v.y}; }
+      else r.z = E{bent(g, w)[1], 0u};
+    }
+    return r;
   }
   __device__ __forceinline__ void stB(int g, int w, XZ v) const {
-    if (D == 3) *reinterpret_cast<uint4*>(bent(g, w)) = make_uint4(v.x.l, v.x.h, v.z.l, v.z.h);
-    else *reinterpret_cast<uint2*>(bent(g, w)) = make_uint2(v.x.l, v.z.l);
+    if (g >= np) {
+      if (D == 3) *reinterpret_cast<uint2*>(dent(g, w)) = make_uint2(v.x.l, v.x.h);
+      else dent(g, w)[0] = v.x.l;
+    } else {
+      if (D == 3) *reinterpret_cast<uint4*>(bent(g, w)) = make_uint4(v.x.l, v.x.h, v.z.l, v.z.h);
+      else *reinterpret_cast<uint2*>(bent(g, w)) = make_uint2(v.x.l, v.z.l);
+    }
   }
   __device__ __forceinline__ E ldqx(int r, int j) const {
     if (D == 3) { const uint2 v = *reinterpret_cast<const uint2*>(qent(r, j)); return E{v.x, v.y}; }
@@ -98,12 +118,15 @@ __device__ __noinline__ void gm_transpose(const GEO G, const GMImg<D> M, const b
   const int items = M.Wq * M.Wb * EW;
   for (int it = tid; it < items; it += nt) {
     const int pl = it % EW, jw = it / EW, j = jw % M.Wb, w = jw / M.Wb;
+    const bool destab = j >= M.Wq;                                     // lane words of the destabilizer half
+    if (destab && pl >= EX) continue;                                  // their Z planes are not kept (GMImg::Bd)
     uint32_t* const a = G.entry(32 * w, j) + pl;                       // + k * RS, rows k < n - 32 w
-    uint32_t* const b = M.bent(32 * j, w) + pl;                        // + k * Wq * EW
+    uint32_t* const b = destab ? M.dent(32 * j, w) + pl : M.bent(32 * j, w) + pl;   // + k * Wq * EX / EW
+    const int bs = destab ? M.Wq * EX : M.Wq * EW;
     const int alim = min(32, G.n - 32 * w);
     uint32_t* const src = to_gm ? a : b;
     uint32_t* const dst = to_gm ? b : a;
-    const int ss = to_gm ? G.RS : M.Wq * EW, ds = to_gm ? M.Wq * EW : G.RS;
+    const int ss = to_gm ? G.RS : bs, ds = to_gm ? bs : G.RS;
     const int sl = to_gm ? alim : 32, dl = to_gm ? 32 : alim;
     uint32_t m[32];
 #pragma unroll
@@ -251,7 +274,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
         if (act && has0) M.stB(i, w0, XZ{addD<D>(va[u].x, smulD<D>(pv0.x, fi)), addD<D>(va[u].z, smulD<D>(pv0.z, fi))});
         if (act && has1) M.stB(i, w1, XZ{addD<D>(vb[u].x, smulD<D>(pv1.x, fi)), addD<D>(vb[u].z, smulD<D>(pv1.z, fi))});
         for (int off = 1; off < gb; off <<= 1) dot += T.shfl_xor(dot, off);
-        if (act && sub == 0) {
+        if (act && sub == 0 && i < np) {                                  // (a destabilizer's phase is never read)
           // P_i += f*ps + po*((Z_i.xs)*f + sd*f(f-1)/2*po)      (tableau_prime.py:310-312,317-319)
           const uint32_t ph = M.ph8[i];
           M.ph8[i] = (uint8_t)((ph + fi * ps + PO * ((dot * fi + sd * ((fi * (fi - 1u)) >> 1) * PO) % D)) % ORDER);
@@ -389,7 +412,7 @@ inline size_t run_smem_bytes(int n) {  // per CTA: list (2np uint16) + ph8 (2np 
 inline size_t run_shot_stride_words(int n, int d);
 inline size_t run_slab_words(int n, int d) {   // B + QX of one tile
   const size_t np = (size_t)(n + 31) / 32 * 32, Wq = np / 32, Wb = 2 * Wq, EW = (d == 2) ? 2 : 4;
-  return (2 * np * Wq * EW + (size_t)n * Wb * (EW / 2) + 7) & ~(size_t)7;
+  return (np * Wq * EW + np * Wq * (EW / 2) + (size_t)n * Wb * (EW / 2) + 7) & ~(size_t)7;   // B, Bd (X only), QX
 }
 
 inline size_t run_shot_stride_words(int n, int d) {   // B + QX + phase planes of one shot (gm_per_shot)
@@ -415,8 +438,7 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
   while ((2 << M.gs_shift) < M.Wq) ++M.gs_shift;                        // lanes per B row: two entries per lane
   M.list = reinterpret_cast<uint16_t*>(smem) + (size_t)tile * 2 * G.np;
   M.ph8 = smem + (size_t)TILES * 4 * G.np + (size_t)tile * 2 * G.np;
-  M.B = p.gm_slab + ((int64_t)blockIdx.x * TILES + tile) * p.gm_slab_words;
-  M.QX = M.B + (size_t)2 * G.np * M.Wq * GMImg<D>::EW;
+  M.place(p.gm_slab + ((int64_t)blockIdx.x * TILES + tile) * p.gm_slab_words);
   for (;;) {
     int64_t shot = 0;
     if (lane == 0) shot = (int64_t)atomicAdd(p.shot_counter, 1u);
@@ -424,8 +446,7 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
     if (shot >= p.shots) break;
     const uint2* ph;
     if (p.gm_per_shot) {         // gate_stream_kernel already left B, QX and the phase planes of this shot in place
-      M.B = p.gm_slab + shot * p.gm_shot_stride_words;
-      M.QX = M.B + (size_t)2 * G.np * M.Wq * GMImg<D>::EW;
+      M.place(p.gm_slab + shot * p.gm_shot_stride_words);
       ph = reinterpret_cast<const uint2*>(M.B + p.gm_slab_words);
     } else {
       G.tab = p.plane_slab + shot * p.img_stride_words;          // the image the interpreter left for this shot

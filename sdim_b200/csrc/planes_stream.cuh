@@ -317,8 +317,7 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
       // into this shot's slab — HBM never sees the qudit-major image, the tail kernel skips its transposition pass
       GMImg<D> M;
       M.n = G.n; M.np = G.np; M.Wq = G.np / 32; M.Wb = G.Wb;
-      M.B = p.gm_slab + shot * p.gm_shot_stride_words;
-      M.QX = M.B + (size_t)2 * G.np * M.Wq * GMImg<D>::EW;
+      M.place(p.gm_slab + shot * p.gm_shot_stride_words);
       gm_transpose<D>(G, M, true, tid, NT);
       out = reinterpret_cast<uint2*>(M.B + p.gm_slab_words);
     } else if (SM) {                                                         // ... or once as it is, coalesced
