@@ -446,6 +446,39 @@ def test_tail_run_kernel_on_the_reference_goldens(golden_random, golden_config_s
     assert (two_kernels >= 20) if min_run == "2" else (two_kernels == 0)
 
 
+@pytest.mark.parametrize("d,n", [(3, 130), (2, 200), (3, 256), (5, 256), (7, 100)])
+def test_two_kernel_paths_edge_cases(d, n):
+    """Degenerate streams through the two-kernel paths (gate streams + generator-major tail for d = 2, 3; lane
+    interpreter + byte tail for d >= 5): nothing but the final measurement (empty front), only Pauli gates and noise in
+    front of it, a single shot, one shot more than a full wave of CTAs — records vs the C oracle."""
+    from oracle import c_oracle
+    from sdim_b200.circuit import Circuit
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    mode = None if d <= 3 else "global"
+    only_m = Circuit(n, d)
+    only_m.add_gate("M", list(range(n)))
+    paulis = Circuit(n, d)
+    for q in range(0, n, 3):
+        paulis.add_gate("X", q)
+        paulis.add_gate("Z_INV", (q + 1) % n)
+        paulis.add_gate("N1", q, prob=0.7, noise_channel="d")
+    paulis.add_gate("M", list(range(n)))
+    mixed = Circuit(n, d)
+    mixed.add_gate("H", list(range(n)))                # every final measurement is random
+    mixed.add_gate("CNOT", 0, 1)
+    mixed.add_gate("M", list(range(n)))
+    for circ in (only_m, paulis, mixed):
+        prog = compile_circuits([circ])
+        eng = TableauEngine(prog)
+        for shots in (1, 445):
+            before = _launches()
+            got = eng.run(shots, 2, 33, mode=mode).cpu().numpy()
+            assert _launches() - before == 2
+            want, _ = c_oracle.run(n, d, prog.ops, shots, 2, 33, thresh24=prog.noise_thresh24, channel=prog.noise_channel)
+            assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("off", [False, True])
 @pytest.mark.parametrize("d,n,depth", [(5, 256, 2500), (7, 97, 1500), (3, 130, 1200), (2, 200, 1500), (13, 40, 900),
                                        (127, 64, 700), (5, 500, 900), (11, 5, 300), (5, 512, 600)])
