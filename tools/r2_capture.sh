@@ -16,3 +16,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'int
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:run_tail -s 1 -c 1 -o gpurun_out/${R}_headline_tail \
     python tools/run_case.py 256 3 16384 auto headline 2 >> gpurun_out/${R}_ncu.log 2>&1
 ls -la gpurun_out/${R}_*
+( timeout 600 python __graft_entry__.py smoke ) > gpurun_out/${R}_smoke.log 2>&1; tail -1 gpurun_out/${R}_smoke.log
