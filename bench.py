@@ -691,7 +691,9 @@ def bench_ours(args):
         "dtype": "u8", "data": "synthetic",
         "config": shared_config(prog, world),
         "run": {"shots_per_gpu_per_step": shots, "mode": args.mode or "auto", "kernel": kernel_name,
-                "step_kernels": [k["kernel"].split(" (")[0] for k in kernels.values()] if kernels else [dominant],
+                "step_kernels": [k["kernel"].split(" (")[0] for k in kernels.values()] if kernels else
+                                (["gate_stream_kernel" if getattr(engine, "gate_stream", None) is not None else "interp_planes_kernel",
+                                  "run_tail_kernel"] if tail_len and kernel_name == "planes-global" else [dominant]),
                 "tableau_store_mib_per_step": (shots * L.shot_bytes / 2**20) if need_tab else 0.0,
                 "gather_ms_per_step": gather_ms if world > 1 else 0.0,
                 "gather_bytes_received_per_gpu_per_step": (world - 1) * shots * prog.n_meas},
