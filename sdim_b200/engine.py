@@ -133,6 +133,21 @@ class TableauEngine:
             self._scratch[mode_flags] = have
         return have
 
+    def device_bytes_per_shot(self, shots: int, mode: Optional[str] = None, fresh: bool = True,
+                              keep_tableau: bool = False) -> int:
+        """Device memory one more shot of a `run` costs besides its records: the HBM tableau where the kernel needs
+        one, and the per-shot slab of the two-kernel bit-plane path (B + QX, 80 KB at n = 256).  Callers size their
+        waves with it (Program.simulate_records)."""
+        mode = self._auto_mode(mode, shots, keep_tableau)
+        kernel, need_tab = self.plan(mode, fresh, keep_tableau)
+        per = self.layout.shot_bytes if need_tab else 0
+        if kernel == "planes-global" and self.tail_run_len and not keep_tableau:
+            n, d, flags = self.prog.num_qudits, self.prog.dimension, self.MODES[mode]
+            s1 = int(self.lib.sdimb_scratch_bytes_shots(n, d, flags, 1024))
+            s2 = int(self.lib.sdimb_scratch_bytes_shots(n, d, flags, 2048))
+            per += max(0, (s2 - s1) // 1024)
+        return per
+
     def fits_resident(self, mode: Optional[str] = None) -> bool:
         return not self.plan(mode)[1]
 

@@ -240,6 +240,7 @@ class Program:
         return out
 
     WAVE_RECORD_BYTES = 256 << 20      # records per launch when the shots do not need an HBM tableau each
+    WAVE_DEVICE_BYTES = 24 << 30       # per-shot device state (HBM tableaus, generator-major slabs) of one wave
 
     def _run_local(self, compiled, shots, shot_offset, seed, replay_meas, replay_noise, mode, split: bool = False,
                    on_device: bool = False):
@@ -253,12 +254,16 @@ class Program:
         rn = None if replay_noise is None else R.to_device(replay_noise, compiled.dimension)
         # Shots run in waves sized to the device: a run that needs one HBM tableau per shot (uint8 lanes in global
         # mode, or a user-supplied initial tableau) must fit next to the records; resident kernels take any count.
-        _, need_tab = engine.plan(mode, fresh=self.initial_tableau is None)
+        # ... and the two-kernel bit-plane path keeps one generator-major slab per shot of the wave in scratch.
+        dev_per_shot = engine.device_bytes_per_shot(max(shots, 1), mode, fresh=self.initial_tableau is None) if shots > 0 else 0
+        need_tab = dev_per_shot > 0
         wave = shots
         if need_tab and shots > 0:
             free_bytes, _total = torch.cuda.mem_get_info(engine.device)
-            per_shot = engine.layout.shot_bytes + (3 * compiled.n_meas + 2 * compiled.n_noise) * np.dtype(rdt).itemsize
-            wave = max(1, min(shots, int(0.6 * free_bytes) // max(per_shot, 1)))
+            per_shot = dev_per_shot + (3 * compiled.n_meas + 2 * compiled.n_noise) * np.dtype(rdt).itemsize
+            budget = min(int(0.6 * free_bytes), self.WAVE_DEVICE_BYTES)
+            wave = max(1, min(shots, budget // max(per_shot, 1)))
+            wave = min(wave, max(1, self.WAVE_RECORD_BYTES // max(compiled.n_meas * np.dtype(rdt).itemsize, 1)))
         elif shots > 0:
             wave = max(1, min(shots, self.WAVE_RECORD_BYTES // max(compiled.n_meas * np.dtype(rdt).itemsize, 1)))
         if on_device:

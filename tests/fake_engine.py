@@ -46,6 +46,9 @@ class FakeEngine:
     def plan(self, mode=None, fresh=True, keep_tableau=False):
         return "fake", (not fresh) or keep_tableau
 
+    def device_bytes_per_shot(self, shots, mode=None, fresh=True, keep_tableau=False):
+        return self.layout.shot_bytes if ((not fresh) or keep_tableau) else 0
+
     def alloc_tableau(self, shots):
         return torch.zeros((shots, self.layout.shot_bytes), dtype=torch.uint8)
 

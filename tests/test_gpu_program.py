@@ -272,6 +272,31 @@ def test_many_waves_pipeline_gives_the_same_records():
     assert np.array_equal(got.values, want[870:])
 
 
+@pytest.mark.parametrize("d,n", [(3, 140), (5, 100)])
+def test_waves_are_sized_by_the_per_shot_device_state(d, n):
+    """The two-kernel paths keep device state per shot of a wave (one generator-major slab per shot for d = 2, 3; one HBM
+    tableau per shot for uint8 lanes): Program sizes its waves by it (WAVE_DEVICE_BYTES), and the records do not
+    depend on the wave size — checked against the C oracle through the public API."""
+    from oracle import c_oracle
+    from sdim_b200 import Program
+    from make_cases import random_circuit
+    circ = random_circuit(seed=3 * n + d, n=n, d=d, depth=300, p_meas=0.0)
+    prog = Program(circ)
+    compiled = prog._compiled()
+    engine = prog._get_engine(compiled)
+    per = engine.device_bytes_per_shot(500)
+    assert per >= (10_000 if d == 3 else engine.layout.shot_bytes)
+    want = c_oracle.run_philox(compiled, 500, 0, 6)
+
+    def packed(table):
+        return table.values | (table.deterministic.astype(np.uint8) << 7)
+
+    assert np.array_equal(packed(prog.simulate_records(500, seed=6)), want)
+    small = Program(circ)
+    small.WAVE_DEVICE_BYTES = 70 * (per + 5 * compiled.n_meas)       # about 70 shots per wave
+    assert np.array_equal(packed(small.simulate_records(500, seed=6)), want)
+
+
 def test_fold_gates_gives_the_same_records():
     """Program(fold_gates=True) uploads the peephole-folded stream (sdim_b200/peephole.py): same records, same
     deterministic flags, same final tableau under the same seed."""
