@@ -26,6 +26,9 @@ struct GM8 {
   uint8_t *xq, *f8, *ph8, *gf, *rv;   // shared memory, per warp
   uint16_t *gl, *rl;
   const uint8_t* inv;  // [d] inverses mod d
+  uint8_t* stage;      // TMA staging buffer of this warp (kStageBytes), its mbarrier and the barrier's phase
+  uint64_t* bar;
+  uint32_t phase;
   int n, np, nq, W, nqw, Ww;          // nqw = nq / 4, Ww = W / 4
   int64_t row_bytes;
 };
@@ -36,7 +39,9 @@ inline size_t warp_smem_bytes(int n, int W) {
   const size_t nq = nq_of(n);
   return 4 * (size_t)W /* xq f8 ph8 gf */ + nq /* rv */ + 2 * (size_t)W /* gl */ + 2 * nq /* rl */;
 }
-inline size_t smem_bytes(int n, int W) { return kWarps * ((warp_smem_bytes(n, W) + 15) & ~(size_t)15) + 128; }
+inline size_t smem_bytes(int n, int W, bool tma) {
+  return kWarps * (((warp_smem_bytes(n, W) + 15) & ~(size_t)15) + (tma ? 4096 + 16 : 0)) + 128;
+}
 inline bool shape_ok(int n, int d) { return d <= 127 && n <= 512; }
 
 // w * s mod d on four packed lanes (s < d, every lane < d).  The slow path is one out-of-line function: inlined at its
@@ -113,16 +118,68 @@ __device__ __noinline__ void transpose_in(const GM8& M, int lane) {
   }
 }
 
+// ---- TMA bulk loads of whole rows into a per-warp staging buffer ------------------------------------------------
+// The rows of a list (generator rows of B8, qudit rows of QX8) are independent 512-byte reads, and one at a time they
+// cost one dependent L2 / DRAM round trip each (ncu: stall_long_scoreboard 45 %).  With TMA the elected lane issues up to
+// kStageRows `cp.async.bulk` copies at once — no registers, one instruction per row — into shared memory; an mbarrier
+// with the expected byte count tells the warp when all of them have landed, and the rows are then processed from
+// shared memory.  Writes stay ordinary coalesced stores.
+// MEASURED (gpurun_out/l8f_probe.txt, d = 5, 4 096 shots): slower than one row at a time with an L2 prefetch of the next
+// — n = 256 tail 6.25 vs 5.56 ms, n = 128 24.6 vs 19.7, n = 500 7.65 vs 6.95 (1 024 shots): the proxy fence + mbarrier
+// round trip per batch and 7 instead of 8 resident CTAs cost more than the overlapped row latency buys, because the 32
+// warps of an SM already overlap each other's round trips.  Kept as an opt-in form (SDIMB_TAIL8_TMA), bit-exact, tested.
+constexpr int kStageBytes = 4096;     // per warp
+constexpr int kStageRows = 8;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// rows list[k0 .. k0 + nb) of an array of rows (base, stride) -> M.stage; returns when they have landed
+__device__ __forceinline__ void stage_rows(GM8& M, const uint16_t* list, int k0, int nb, const uint8_t* base, size_t stride,
+                                           uint32_t rowbytes, int lane) {
+  // earlier ordinary stores of this warp to those rows must be visible to the async proxy, and every lane must be done
+  // with the previous contents of the staging buffer
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    mbar_expect_tx(M.bar, (uint32_t)nb * rowbytes);
+    for (int r = 0; r < nb; ++r) tma_load_row(M.stage + (size_t)r * rowbytes, base + (size_t)list[k0 + r] * stride, rowbytes, M.bar);
+  }
+  mbar_wait(M.bar, M.phase);
+  M.phase ^= 1u;
+}
+
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
 // Measurement of qudit q by one warp; returns the record byte.  NT = words per lane of one half row of B8 (1, 2, 4:
 // n <= 128, 256, 512), a QX8 row has at most 2 NT words per lane.  Rows of a list are processed one at a time (the
 // next one is prefetched into L2): with 32 warps per SM the other shots hide the round trip, and the code stays small.
-template <int NT>
-__device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const Swar& Sd, const int q, const uint32_t draw,
+template <int NT, bool TMA>
+__device__ __forceinline__ uint32_t measure8(GM8& M, const Arith& A, const Swar& Sd, const int q, const uint32_t draw,
                                              const int lane) {
   constexpr int NQ = 2 * NT;
   const int nqw = M.nqw, Ww = M.Ww, np = M.np, nq = M.nq;
+  const int KB = TMA ? min(kStageRows, kStageBytes / (2 * nq)) : 1;     // rows per staged batch (2 nq >= W)
   // ---- row q of QX8: staged, pivot = first stabilizer lane with an X component (tableau_prime.py:273-283) ----
   uint32_t piv = kNoPivot;
   {
@@ -180,11 +237,16 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
     const int total = compact_bytes(reinterpret_cast<const uint32_t*>(M.f8), Ww, M.gl, M.gf, lane);
     // row_i += f_i * pivot for every listed generator      (tableau_prime.py:306-321)
 #pragma unroll 1
-    for (int k = 0; k < total; ++k) {
+    for (int k0 = 0; k0 < total; k0 += KB) {
+     const int nb = min(KB, total - k0);
+     if (TMA) stage_rows(M, M.gl, k0, nb, M.B, (size_t)2 * nq, 2u * nq, lane);
+#pragma unroll 1
+     for (int k = k0; k < k0 + nb; ++k) {
       const int gi = M.gl[k];
       const uint32_t f = M.gf[k];
       uint32_t* const row = reinterpret_cast<uint32_t*>(M.B + (size_t)gi * 2 * nq);
-      if (k + 1 < total) {
+      const uint32_t* const src = TMA ? reinterpret_cast<const uint32_t*>(M.stage + (size_t)(k - k0) * 2 * nq) : row;
+      if (!TMA && k + 1 < total) {
         const uint32_t* nxt = reinterpret_cast<const uint32_t*>(M.B + (size_t)M.gl[k + 1] * 2 * nq);
         if (lane < 2 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32 * lane));
       }
@@ -193,7 +255,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
       for (int t = 0; t < NT; ++t) {
         const int w = lane + 32 * t;
         xa[t] = za[t] = 0u;
-        if (w < nqw) { xa[t] = row[w]; za[t] = row[nqw + w]; }
+        if (w < nqw) { xa[t] = src[w]; za[t] = src[nqw + w]; }
       }
       uint32_t dot = 0;
 #pragma unroll
@@ -210,6 +272,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
         const uint32_t cp = mod_d(A, mod_d(A, dot) * f + sd * g * A.po);
         M.ph8[gi] = (uint8_t)mod_o(A, (uint32_t)M.ph8[gi] + f * ps + A.po * cp);
       }
+     }
     }
     // QX8: X[r,:] += xs_r * f on the pivot's X support; column p <- 0, column np + p <- xs (also where only the old
     // destabilizer had an entry).  Marker byte of a row = xs_r, or 0x80 where only the old destabilizer is non-zero.
@@ -226,11 +289,16 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
     __syncwarp();
     const int totq = compact_bytes(reinterpret_cast<const uint32_t*>(M.rv), nqw, M.rl, M.gf, lane);
 #pragma unroll 1
-    for (int k = 0; k < totq; ++k) {
+    for (int k0 = 0; k0 < totq; k0 += KB) {
+     const int nb = min(KB, totq - k0);
+     if (TMA) stage_rows(M, M.rl, k0, nb, M.T, (size_t)M.row_bytes, (uint32_t)M.W, lane);
+#pragma unroll 1
+     for (int k = k0; k < k0 + nb; ++k) {
       const int r = M.rl[k];
       const uint32_t sv = M.gf[k] & 0x7Fu;
       uint32_t* const row = reinterpret_cast<uint32_t*>(M.T + (int64_t)r * M.row_bytes);
-      if (k + 1 < totq) {
+      const uint32_t* const src = TMA ? reinterpret_cast<const uint32_t*>(M.stage + (size_t)(k - k0) * M.W) : row;
+      if (!TMA && k + 1 < totq) {
         const uint32_t* nxt = reinterpret_cast<const uint32_t*>(M.T + (int64_t)M.rl[k + 1] * M.row_bytes);
         if (lane < NQ) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32 * lane));
       }
@@ -238,7 +306,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
 #pragma unroll
       for (int t = 0; t < NQ; ++t) {
         const int w = lane + 32 * t;
-        xr[t] = (w < Ww) ? row[w] : 0u;
+        xr[t] = (w < Ww) ? src[w] : 0u;
       }
 #pragma unroll
       for (int t = 0; t < NQ; ++t) {
@@ -251,6 +319,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
           if (nx != xr[t]) row[w] = nx;
         }
       }
+     }
     }
     // destabilizer p <- (xs, zs, ps); stabilizer p <- Z_q with phase -m*po   (tableau_prime.py:323-333)
 #pragma unroll
@@ -274,11 +343,16 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
     for (int t = 0; t < NT; ++t) az[t] = 0u;
     uint32_t cross = 0, sdg = 0, a1 = 0;
 #pragma unroll 1
-    for (int k = 0; k < total; ++k) {
+    for (int k0 = 0; k0 < total; k0 += KB) {
+     const int nb = min(KB, total - k0);
+     if (TMA) stage_rows(M, M.gl, k0, nb, M.B, (size_t)2 * nq, 2u * nq, lane);
+#pragma unroll 1
+     for (int k = k0; k < k0 + nb; ++k) {
       const int gi = M.gl[k];
       const uint32_t f = M.gf[k], g = mod_d(A, (f * (f - 1u)) >> 1);
-      const uint32_t* const row = reinterpret_cast<const uint32_t*>(M.B + (size_t)gi * 2 * nq);
-      if (k + 1 < total) {
+      const uint32_t* const row = TMA ? reinterpret_cast<const uint32_t*>(M.stage + (size_t)(k - k0) * 2 * nq)
+                                      : reinterpret_cast<const uint32_t*>(M.B + (size_t)gi * 2 * nq);
+      if (!TMA && k + 1 < total) {
         const uint32_t* nxt = reinterpret_cast<const uint32_t*>(M.B + (size_t)M.gl[k + 1] * 2 * nq);
         if (lane < 2 * NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32 * lane));
       }
@@ -299,6 +373,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
       cross = mod_d(A, cross);
       sdg = mod_d(A, sdg + mod_d(A, xz) * g);
       a1 += f * (uint32_t)M.ph8[gi];                                              // every lane, same value
+     }
     }
     const uint32_t part = mod_d(A, warp_sum(mod_d(A, cross + A.po * sdg)));
     const uint32_t ap = mod_o(A, mod_o(A, a1) + A.po * part);
@@ -309,7 +384,7 @@ __device__ __forceinline__ uint32_t measure8(const GM8& M, const Arith& A, const
   return rec;
 }
 
-template <int NT>
+template <int NT, bool TMA>
 __global__ void __launch_bounds__(32 * kWarps, 8) run_tail8_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -320,10 +395,15 @@ __global__ void __launch_bounds__(32 * kWarps, 8) run_tail8_kernel(const __grid_
   M.row_bytes = p.row_bytes;
   uint8_t* inv = smem;                                            // [128]
   const size_t per_warp = ((size_t)(4 * p.W + M.nq + 2 * p.W + 2 * M.nq) + 15) & ~(size_t)15;
-  uint8_t* base = smem + 128 + warp * per_warp;
+  uint8_t* base = smem + 128 + warp * (per_warp + (TMA ? kStageBytes + 16 : 0));
   M.xq = base; M.f8 = M.xq + p.W; M.ph8 = M.f8 + p.W; M.gf = M.ph8 + p.W; M.rv = M.gf + p.W;
   M.gl = reinterpret_cast<uint16_t*>(M.rv + M.nq); M.rl = M.gl + p.W;
   M.inv = inv;
+  M.stage = base + per_warp;                                      // 16-byte aligned: per_warp is a multiple of 16
+  M.bar = reinterpret_cast<uint64_t*>(M.stage + kStageBytes);
+  M.phase = 0u;
+  if (TMA && lane == 0) mbar_init(M.bar, 1);
+  if (TMA) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (uint32_t v = threadIdx.x; v < A.d; v += blockDim.x) {      // inverses mod d by search (d <= 127)
     uint32_t r = 0;
     for (uint32_t c = 1; c < A.d; ++c)
@@ -362,7 +442,7 @@ __global__ void __launch_bounds__(32 * kWarps, 8) run_tail8_kernel(const __grid_
       while (todo) {
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
-        const uint32_t rec = measure8<NT>(M, A, Sd, __shfl_sync(0xFFFFFFFFu, mine.y, k), (uint32_t)__shfl_sync(0xFFFFFFFFu, mine.z, k), lane);
+        const uint32_t rec = measure8<NT, TMA>(M, A, Sd, __shfl_sync(0xFFFFFFFFu, mine.y, k), (uint32_t)__shfl_sync(0xFFFFFFFFu, mine.z, k), lane);
         if (lane == k) myrec = rec;
       }
       if (is_m) p.records[shot * p.rec_stride + mine.w] = (uint8_t)myrec;

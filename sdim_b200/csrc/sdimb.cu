@@ -241,11 +241,16 @@ PlaneKernel gate_stream_kernel_for(int n, int d) {
 }
 
 // Trailing measurement run on uint8 lanes (lanes_gm.cuh): resident CTAs, scratch (counter + one B8 slab per resident warp)
+// TMA staging of the row lists (lanes_gm.cuh): correct, but 12-25 % slower than ordinary loads + L2 prefetch on B200 (d = 5, 4096
+// shots: n = 256 tail 6.25 vs 5.56 ms, n = 128 24.6 vs 19.7) — opt-in developer knob, both forms under test
+bool tail8_tma() { return std::getenv("SDIMB_TAIL8_TMA") != nullptr; }
 PlaneKernel run_tail8_kernel_for(int n) {
-  return n <= 128 ? lanesgm::run_tail8_kernel<1> : n <= 256 ? lanesgm::run_tail8_kernel<2> : lanesgm::run_tail8_kernel<4>;
+  if (tail8_tma())
+    return n <= 128 ? lanesgm::run_tail8_kernel<1, true> : n <= 256 ? lanesgm::run_tail8_kernel<2, true> : lanesgm::run_tail8_kernel<4, true>;
+  return n <= 128 ? lanesgm::run_tail8_kernel<1, false> : n <= 256 ? lanesgm::run_tail8_kernel<2, false> : lanesgm::run_tail8_kernel<4, false>;
 }
 int run_tail8_ctas(int n, int W) {
-  const size_t smem = lanesgm::smem_bytes(n, W);
+  const size_t smem = lanesgm::smem_bytes(n, W, tail8_tma());
   auto kern8 = run_tail8_kernel_for(n);
   int dev = 0, sms = 0, per_sm = 0;
   if (smem > (size_t)kSmemLimit || cudaGetDevice(&dev) != cudaSuccess ||
@@ -663,7 +668,7 @@ int sdimb_run(const SdimbRunArgs* caller) {
     p2.gm_slab_words = (int64_t)(lanesgm::slab_bytes(a->n, L.lanes) / 4);
     int64_t grid2 = (a->shots + lanesgm::kWarps - 1) / lanesgm::kWarps;
     if (grid2 > tail8_ctas) grid2 = tail8_ctas;
-    run_tail8_kernel_for(a->n)<<<(unsigned)grid2, 32 * lanesgm::kWarps, lanesgm::smem_bytes(a->n, L.lanes), (cudaStream_t)a->stream>>>(p2);
+    run_tail8_kernel_for(a->n)<<<(unsigned)grid2, 32 * lanesgm::kWarps, lanesgm::smem_bytes(a->n, L.lanes, tail8_tma()), (cudaStream_t)a->stream>>>(p2);
     g_launches++;
     if (timed8) { cudaEventRecord(g_time_ev[2], (cudaStream_t)a->stream); g_time_valid = 1; }
   }
@@ -752,7 +757,7 @@ uint64_t host_plan_knobs(int n, int d) {
   uint64_t k = 0;
   auto mix = [&](uint64_t v) { k = (k ^ v) * 0x100000001B3ull; };
   mix(gate_stream_shape_ok(n, d)); mix(gate_stream_in_smem(n, d)); mix((uint64_t)gate_stream_warps(n, d));
-  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d)); mix(tail8_enabled());
+  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d)); mix(tail8_enabled()); mix(tail8_tma());
   for (const char* name : {"SDIMB_GM_MIN_RUN", "SDIMB_CLUSTER_SIZE", "SDIMB_CLUSTER_THREADS"}) {
     const char* v = std::getenv(name);
     mix(v ? (uint64_t)std::atoll(v) + 1 : 0);

@@ -479,7 +479,7 @@ def test_two_kernel_paths_edge_cases(d, n):
             assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("off", [False, True])
+@pytest.mark.parametrize("off", [False, True, "tma"])
 @pytest.mark.parametrize("d,n,depth", [(5, 256, 2500), (7, 97, 1500), (3, 130, 1200), (2, 200, 1500), (13, 40, 900),
                                        (127, 64, 700), (5, 500, 900), (11, 5, 300), (5, 512, 600)])
 def test_lanes_tail_run_kernel_matches_c_oracle(monkeypatch, d, n, depth, off):
@@ -491,7 +491,10 @@ def test_lanes_tail_run_kernel_matches_c_oracle(monkeypatch, d, n, depth, off):
     from make_cases import random_program
     from oracle import c_oracle
     from sdim_b200.engine import TableauEngine, simulate_host
-    if off:
+    if off == "tma":               # the row lists staged by TMA bulk copies (cp.async.bulk + mbarrier) instead of loads
+        monkeypatch.setenv("SDIMB_TAIL8_TMA", "1")
+        off = False
+    elif off:
         monkeypatch.setenv("SDIMB_NO_TAIL8", "1")
     prog = random_program(seed=500 * d + n, n=n, d=d, depth=depth)
     eng = TableauEngine(prog)
