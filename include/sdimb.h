@@ -178,7 +178,8 @@ int sdimb_export(const void* tableau, int n, int d, int64_t shot,
 /* Same job as sdimb_run with HOST buffers only: schedules the op stream (sdimb_schedule), copies it and the noise
  * tables in, simulates from |0...0>, copies the records out through pinned staging and synchronises.  Device
  * scratch, the staging buffer, the stream and the events live in a grow-only workspace of the CURRENT DEVICE that
- * later calls reuse (calls on one device are serialised internally; sdimb_release_workspace frees all of them).  This is the call a non-PyTorch host
+ * later calls reuse (calls on one device are serialised internally; sdimb_release_workspace frees all of them).  If `records`
+ * lies in pinned host memory (cudaHostAlloc / cudaHostRegister) the device writes it directly, without the staging copy.  This is the call a non-PyTorch host
  * (e.g. the reference itself through ctypes) makes; `elapsed_ms` (nullable) receives the device time of the
  * whole call measured with CUDA events. */
 int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset,

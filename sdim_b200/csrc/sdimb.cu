@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -876,6 +877,13 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   // function of (n, d, shots, flags, op stream, developer knobs); the workspace keeps the plan of its last program, so
   // a caller that simulates one program batch after batch (Program.simulate's waves, bench.py's steps) pays the
   // scheduler and the gate-stream compiler once.  The op stream is compared byte for byte.
+  // SDIMB_HOST_PROFILE (developer knob): wall-clock microseconds of the stages of this call on stderr
+  const bool prof = std::getenv("SDIMB_HOST_PROFILE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() * 1e-3;
+  };
+  const auto t_in = now();
   int cur_dev = 0;
   if (cudaGetDevice(&cur_dev) != cudaSuccess || cur_dev < 0 || cur_dev >= kMaxDevices) { cudaGetLastError(); return SDIMB_ECUDA; }
   HostWorkspace& g_ws = g_ws_by_device[cur_dev];
@@ -911,8 +919,18 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
   const size_t b_scr = align256((size_t)sdimb_scratch_bytes_shots(n, d, mode_flags, tail_len ? shots : 0));
   const size_t total = b_ops + b_rec + b_rm + b_rn + b_th + b_ch + b_tab + b_gs + b_scr + 256;
 
-  if (!g_ws.prepare(cur_dev, total, b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
+  const auto t_plan = now();
+  // `records` in pinned (page-locked or registered) host memory: the device writes it directly; pageable memory goes
+  // through the workspace's pinned staging buffer and one host copy
+  bool direct_out = false;
+  {
+    cudaPointerAttributes attr;
+    if (records && cudaPointerGetAttributes(&attr, records) == cudaSuccess) direct_out = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  if (!g_ws.prepare(cur_dev, total, direct_out ? 0 : b_rec + 256)) { cudaGetLastError(); return SDIMB_ECUDA; }
   cudaStream_t st = g_ws.stream;
+  auto t_h2d = t_plan, t_run = t_plan, t_sync = t_plan;
   uint8_t* base = (uint8_t*)g_ws.dev;
   uint8_t* d_ops = base; base += b_ops;
   uint8_t* d_rec = base; base += b_rec;
@@ -932,6 +950,7 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     if (d_th && cudaMemcpyAsync(d_th, noise_thresh24, (size_t)n_noise * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_ch && cudaMemcpyAsync(d_ch, noise_channel, (size_t)n_noise, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
     if (d_gs && cudaMemcpyAsync(d_gs, gstream.data(), (size_t)gs_rows * 16, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    t_h2d = now();
     SdimbRunArgs a;
     std::memset(&a, 0, sizeof(a));
     a.struct_size = sizeof(a);
@@ -948,14 +967,19 @@ int sdimb_simulate_host(int n, int d, int64_t shots, int64_t shot_offset, const 
     a.gate_stream = (const int32_t*)d_gs; a.gate_stream_rows = gs_rows;
     rc = sdimb_run(&a);
     if (rc) break;
+    t_run = now();
     rc = SDIMB_ECUDA;
     const size_t rec_bytes = (size_t)shots * n_meas * eb;
-    if (rec_bytes && cudaMemcpyAsync(g_ws.pin, d_rec, rec_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+    if (rec_bytes && cudaMemcpyAsync(direct_out ? (void*)records : g_ws.pin, d_rec, rec_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
     if (cudaEventRecord(g_ws.e1, st) != cudaSuccess) break;
     if (cudaStreamSynchronize(st) != cudaSuccess) break;
-    if (rec_bytes) std::memcpy(records, g_ws.pin, rec_bytes);
+    t_sync = now();
+    if (rec_bytes && !direct_out) std::memcpy(records, g_ws.pin, rec_bytes);
     if (elapsed_ms && cudaEventElapsedTime(elapsed_ms, g_ws.e0, g_ws.e1) != cudaSuccess) break;
     rc = SDIMB_OK;
+    if (prof)
+      std::fprintf(stderr, "sdimb_simulate_host: plan %.0f us, arena %.0f, h2d enqueue %.0f, sdimb_run %.0f, wait %.0f, copy out %.0f\n",
+                   us(t_in, t_plan), us(t_plan, t_plan), us(t_plan, t_h2d), us(t_h2d, t_run), us(t_run, t_sync), us(t_sync, now()));
   } while (0);
   if (rc == SDIMB_ECUDA) cudaGetLastError();
   return rc;

@@ -288,12 +288,20 @@ class TableauEngine:
 
 def simulate_host(prog: CompiledProgram, shots: int, shot_offset: int = 0, seed: int = 0,
                   replay_meas: Optional[np.ndarray] = None, replay_noise: Optional[np.ndarray] = None,
-                  mode: Optional[str] = None):
-    """Host-buffer entry (sdimb_simulate_host): numpy in, numpy records out, plus device ms of the call."""
+                  mode: Optional[str] = None, out: Optional[np.ndarray] = None):
+    """Host-buffer entry (sdimb_simulate_host): numpy in, numpy records out, plus device ms of the call.
+
+    `out`: a C-contiguous [shots, n_meas] array of the record dtype to receive the records instead of a fresh one; if it
+    lives in pinned memory (e.g. `torch.empty(..., pin_memory=True).numpy()`) the device writes it directly."""
     lib = N.lib()
     ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
     rdt = R.np_dtype(prog.dimension)
-    rec = np.empty((shots, prog.n_meas), dtype=rdt)
+    if out is None:
+        rec = np.empty((shots, prog.n_meas), dtype=rdt)
+    else:
+        if out.shape != (shots, prog.n_meas) or out.dtype != rdt or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+            raise ValueError(f"out must be a writeable C-contiguous {rdt.__name__}[{shots}, {prog.n_meas}] array")
+        rec = out
     thr = np.ascontiguousarray(prog.noise_thresh24, dtype=np.uint32)
     ch = np.ascontiguousarray(prog.noise_channel, dtype=np.uint8)
     rm = None if replay_meas is None else np.ascontiguousarray(replay_meas, dtype=rdt)

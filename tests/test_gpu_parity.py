@@ -446,6 +446,28 @@ def test_tail_run_kernel_on_the_reference_goldens(golden_random, golden_config_s
     assert (two_kernels >= 20) if min_run == "2" else (two_kernels == 0)
 
 
+def test_host_entry_writes_pinned_output_directly():
+    """sdimb_simulate_host with `records` in pinned host memory (the device writes it directly, no staging copy), in a
+    caller-provided pageable array, and in a fresh one: the same records; bad `out` arrays are rejected."""
+    import torch
+    from make_cases import random_program
+    from oracle import c_oracle
+    from sdim_b200.engine import simulate_host
+    prog = random_program(seed=12, n=70, d=3, depth=500)
+    want = c_oracle.run_philox(prog, 700, 5, 3)
+    fresh, _ = simulate_host(prog, 700, 5, 3)
+    pinned = torch.zeros((700, prog.n_meas), dtype=torch.uint8, pin_memory=True).numpy()
+    got, _ = simulate_host(prog, 700, 5, 3, out=pinned)
+    assert got is pinned
+    pageable = np.zeros((700, prog.n_meas), dtype=np.uint8)
+    simulate_host(prog, 700, 5, 3, out=pageable)
+    assert np.array_equal(fresh, want) and np.array_equal(pinned, want) and np.array_equal(pageable, want)
+    with pytest.raises(ValueError):
+        simulate_host(prog, 700, 5, 3, out=np.zeros((699, prog.n_meas), dtype=np.uint8))
+    with pytest.raises(ValueError):
+        simulate_host(prog, 700, 5, 3, out=np.zeros((700, prog.n_meas), dtype=np.int32))
+
+
 @pytest.mark.parametrize("d,n", [(3, 130), (2, 200), (3, 256), (5, 256), (7, 100)])
 def test_two_kernel_paths_edge_cases(d, n):
     """Degenerate streams through the two-kernel paths (gate streams + generator-major tail for d = 2, 3; lane
