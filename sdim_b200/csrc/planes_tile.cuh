@@ -67,6 +67,16 @@ inline size_t tile_stride_words(int n, int d) {
   const size_t row = (size_t)tile_lps(n) * EW;     // words one tile touches per gate
   return row < 32 ? w + row : w;
 }
+// Global-image form: the tiles' images live in caller scratch (L1 / L2), shared memory keeps only the lists and the
+// noise events, so that registers, not shared memory, bound the warps in flight (config 3: 8 -> 20+ warps per SM; the
+// shared-memory form ran at 12 % warps-active, 33 % issue-active, top stall "wait": too few warps to hide even the
+// ALU latency of its own dependent instructions).
+#ifndef SDIMB_TILE_GLB_CTAS
+#define SDIMB_TILE_GLB_CTAS 20     // one-warp CTAs per SM the global-image form is compiled for (<= 102 registers)
+#endif
+inline size_t tile_glb_img_stride_words(int n, int d) { return (tile_img_words(n, d) + 31) & ~(size_t)31; }
+inline size_t tile_glb_lists_words(int n) { return ((size_t)(n + 31) / 32 * 32 + 31) & ~(size_t)31; }   // ar + br per tile
+inline size_t tile_glb_smem_bytes(int n) { return 4 * ((32 / (size_t)tile_lps(n)) * tile_glb_lists_words(n) + 32) + 16; }
 inline size_t tile_smem_bytes(int n, int d) {      // one warp: its tiles + the packed noise events of a batch
   return 4 * ((32 / (size_t)tile_lps(n)) * tile_stride_words(n, d) + 32) + 16;
 }
@@ -384,8 +394,8 @@ __device__ __forceinline__ uint32_t t_measure(const TW<LPS>& T, const TImg<D>& G
   return rec;
 }
 
-template <int D, int LPS, bool UNI>
-__global__ void __launch_bounds__(32) interp_tile_kernel(const __grid_constant__ KParams p) {
+template <int D, int LPS, bool UNI, bool GLB = false>
+__global__ void __launch_bounds__(32, GLB ? SDIMB_TILE_GLB_CTAS : 1) interp_tile_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TPW = 32 / LPS, EW = TImg<D>::EW;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -399,14 +409,26 @@ __global__ void __launch_bounds__(32) interp_tile_kernel(const __grid_constant__
   G.RS = EW * G.Wb;
   const int img_words = (p.n * G.RS + 3) & ~3;
   uint32_t* const sm = reinterpret_cast<uint32_t*>(smem);
-  G.tab = sm + (size_t)tw * p.tile_stride_words;
-  G.ar = reinterpret_cast<uint16_t*>(G.tab + img_words);
-  G.br = G.ar + G.np;
   TImg<D> G0 = G;                                                        // tile 0 of the warp (UNI: the image the walks read)
-  G0.tab = sm;
-  G0.ar = reinterpret_cast<uint16_t*>(G0.tab + img_words);
-  G0.br = G0.ar + G.np;
-  uint32_t* const evs = sm + (size_t)TPW * p.tile_stride_words;          // [32] packed N1 events of the current batch
+  uint32_t* evs;                                                         // [32] packed N1 events of the current batch
+  if (GLB) {                   // images in caller scratch, one per resident tile; lists and events in shared memory
+    uint32_t* const img0 = p.plane_slab + (int64_t)blockIdx.x * TPW * p.img_stride_words;
+    G.tab = img0 + (int64_t)tw * p.img_stride_words;
+    G.ar = reinterpret_cast<uint16_t*>(sm + (size_t)tw * p.tile_stride_words);
+    G.br = G.ar + G.np;
+    G0.tab = img0;
+    G0.ar = reinterpret_cast<uint16_t*>(sm);
+    G0.br = G0.ar + G.np;
+    evs = sm + (size_t)TPW * p.tile_stride_words;
+  } else {
+    G.tab = sm + (size_t)tw * p.tile_stride_words;
+    G.ar = reinterpret_cast<uint16_t*>(G.tab + img_words);
+    G.br = G.ar + G.np;
+    G0.tab = sm;
+    G0.ar = reinterpret_cast<uint16_t*>(G0.tab + img_words);
+    G0.br = G0.ar + G.np;
+    evs = sm + (size_t)TPW * p.tile_stride_words;
+  }
   const bool on = j < G.Wb;
   const int jj = on ? j : 0;                                             // idle lanes of a tile (Wb < LPS) shadow word 0, never store
 

@@ -118,13 +118,23 @@ int plan_kernel(int n, int d, uint32_t flags, int np) {
 // The tile interpreter (planes_tile.cuh): kernel for (d, lanes per shot).
 using PlaneKernel = void (*)(const KParams);
 // uni: every shot starts from |0...0> (SDIMB_FRESH): the tiles of a warp hold identical X / Z blocks, see t_measure
-PlaneKernel tile_kernel_for(int n, int d, bool uni) {
+template <bool GLB>
+PlaneKernel tile_kernel_glb(int n, int d, bool uni) {
   if (uni) {
-    if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4, true> : planes::interp_tile_kernel<3, 4, true>;
-    return (d == 2) ? planes::interp_tile_kernel<2, 8, true> : planes::interp_tile_kernel<3, 8, true>;
+    if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4, true, GLB> : planes::interp_tile_kernel<3, 4, true, GLB>;
+    return (d == 2) ? planes::interp_tile_kernel<2, 8, true, GLB> : planes::interp_tile_kernel<3, 8, true, GLB>;
   }
-  if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4, false> : planes::interp_tile_kernel<3, 4, false>;
-  return (d == 2) ? planes::interp_tile_kernel<2, 8, false> : planes::interp_tile_kernel<3, 8, false>;
+  if (planes::tile_lps(n) == 4) return (d == 2) ? planes::interp_tile_kernel<2, 4, false, GLB> : planes::interp_tile_kernel<3, 4, false, GLB>;
+  return (d == 2) ? planes::interp_tile_kernel<2, 8, false, GLB> : planes::interp_tile_kernel<3, 8, false, GLB>;
+}
+PlaneKernel tile_kernel_for(int n, int d, bool uni, bool glb = false) { return glb ? tile_kernel_glb<true>(n, d, uni) : tile_kernel_glb<false>(n, d, uni); }
+// The tile interpreter keeps its images in caller scratch (L1 / L2) when the caller brought scratch for them: 20 warps per
+// SM instead of the 8 that shared memory admits.  Same-box A/B (gpurun_out/t6_breakdown.txt, ms per 2e5 shots): config 3
+// 34.4 -> 28.9, config 4 30.4 -> 20.7, config 2 (1e5 shots) 15.8 -> 14.5; 24 and 32 CTAs per SM (80 / 64 registers) are
+// no better.  SDIMB_TILE_SMEM (developer knob) keeps the shared-memory images (tests run both).
+bool tile_glb_wanted() { return std::getenv("SDIMB_TILE_SMEM") == nullptr; }
+size_t tile_glb_scratch_bytes(int n, int d) {     // counter + one image per tile of every CTA a B200 keeps resident
+  return 256 + (size_t)148 * SDIMB_TILE_GLB_CTAS * (32 / planes::tile_lps(n)) * 4 * planes::tile_glb_img_stride_words(n, d);
 }
 
 // The global-image plane interpreter for (d, interleaved image or not): see SDIMB_PG_IL_MIN_NP in planes.cuh.
@@ -443,9 +453,11 @@ int sdimb_run(const SdimbRunArgs* caller) {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDIMB_ECUDA;
   if (kernel == 5) {     // bit planes, several shots per warp: one-warp CTAs, 32 / LPS shots claimed at a time
     const bool no_uni = std::getenv("SDIMB_TILE_NO_UNI") != nullptr;            // developer knob (tests, A/B timings)
-    auto kern = tile_kernel_for(a->n, a->d, (a->flags & SDIMB_FRESH) && !no_uni);
-    const size_t smem = planes::tile_smem_bytes(a->n, a->d);
     const int tpw = 32 / planes::tile_lps(a->n);
+    // images in caller scratch (global-image form) when asked for and the scratch holds one image per resident tile
+    const bool glb = tile_glb_wanted() && a->scratch && a->scratch_bytes >= (int64_t)tile_glb_scratch_bytes(a->n, a->d);
+    auto kern = tile_kernel_for(a->n, a->d, (a->flags & SDIMB_FRESH) && !no_uni, glb);
+    const size_t smem = glb ? planes::tile_glb_smem_bytes(a->n) : planes::tile_smem_bytes(a->n, a->d);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem) != cudaSuccess || per_sm < 1) {
       cudaGetLastError();
@@ -459,6 +471,13 @@ int sdimb_run(const SdimbRunArgs* caller) {
       if (cudaMemsetAsync(p.shot_counter, 0, sizeof(unsigned int), (cudaStream_t)a->stream) != cudaSuccess) return SDIMB_ECUDA;
     }
     p.tile_stride_words = (int64_t)planes::tile_stride_words(a->n, a->d);
+    if (glb) {
+      const int64_t cap = (a->scratch_bytes - 256) / (int64_t)(tpw * 4 * planes::tile_glb_img_stride_words(a->n, a->d));
+      if (grid > cap) grid = cap;
+      p.tile_stride_words = (int64_t)planes::tile_glb_lists_words(a->n);
+      p.img_stride_words = (int64_t)planes::tile_glb_img_stride_words(a->n, a->d);
+      p.plane_slab = (uint32_t*)((uint8_t*)a->scratch + 256);
+    }
     kern<<<(unsigned)grid, 32, smem, (cudaStream_t)a->stream>>>(p);
     g_launches++;
     return cudaGetLastError() == cudaSuccess ? SDIMB_OK : SDIMB_ECUDA;
@@ -758,7 +777,7 @@ uint64_t host_plan_knobs(int n, int d) {
   uint64_t k = 0;
   auto mix = [&](uint64_t v) { k = (k ^ v) * 0x100000001B3ull; };
   mix(gate_stream_shape_ok(n, d)); mix(gate_stream_in_smem(n, d)); mix((uint64_t)gate_stream_warps(n, d));
-  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d)); mix(tail8_enabled()); mix(tail8_tma());
+  mix(planes_interleaved(n)); mix(tile_shape_ok(n, d)); mix(tail8_enabled()); mix(tail8_tma()); mix(tile_glb_wanted());
   for (const char* name : {"SDIMB_GM_MIN_RUN", "SDIMB_CLUSTER_SIZE", "SDIMB_CLUSTER_THREADS"}) {
     const char* v = std::getenv(name);
     mix(v ? (uint64_t)std::atoll(v) + 1 : 0);
@@ -1276,6 +1295,7 @@ int64_t sdimb_scratch_bytes(int n, int d, uint32_t flags) {
   SdimbLayout L;
   if (sdimb_layout(n, d, &L)) return 0;
   const int k = plan_kernel(n, d, flags, L.np);
+  if (k == 5 && tile_glb_wanted()) return (int64_t)tile_glb_scratch_bytes(n, d);
   if (k == 2 || k == 5) return 256;   // the shot counter
   if (k == 3) {             // the shot counter + one image per CTA the device keeps resident (148 x 8 without a device)
     int ctas = planes_global_ctas(n, d, nullptr);

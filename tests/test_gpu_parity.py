@@ -124,9 +124,11 @@ def test_philox_mode_matches_c_oracle(d, n, depth, mode):
         assert len({got[s].tobytes() for s in range(shots)}) > 1    # noise/draws really differ between shots
 
 
+@pytest.mark.parametrize("img", ["scratch", "shared"])
 @pytest.mark.parametrize("uni", [True, False])
-def test_tile_interpreter_both_measurement_forms(golden_random, golden_config_sizes, monkeypatch, uni):
-    """The tile interpreter (several shots per warp, n <= 128) with its measurement walks shared by the warp (fresh
+def test_tile_interpreter_both_measurement_forms(golden_random, golden_config_sizes, monkeypatch, uni, img):
+    """The tile interpreter (several shots per warp, n <= 128) with its images in caller scratch (the default, 20 warps
+    per SM) and in shared memory (SDIMB_TILE_SMEM), and with its measurement walks shared by the warp (fresh
     batches: identical X / Z blocks in every tile) and per tile (SDIMB_TILE_NO_UNI, the form non-fresh runs take):
     reference goldens incl. final tableaus, the config-size goldens that fit, and free-running shots that differ in
     noise and outcomes against the C oracle — with shot counts that leave tiles of the last warp empty."""
@@ -137,6 +139,8 @@ def test_tile_interpreter_both_measurement_forms(golden_random, golden_config_si
     from sdim_b200.ir import compile_circuits
     if not uni:
         monkeypatch.setenv("SDIMB_TILE_NO_UNI", "1")
+    if img == "shared":
+        monkeypatch.setenv("SDIMB_TILE_SMEM", "1")
     checked = 0
     cases = [c for c in golden_random if c["d"] <= 3] + [c for c in golden_config_sizes if c["n"] <= 128]
     for case in cases:
