@@ -455,7 +455,20 @@ int sdimb_run(const SdimbRunArgs* caller) {
     const bool no_uni = std::getenv("SDIMB_TILE_NO_UNI") != nullptr;            // developer knob (tests, A/B timings)
     const int tpw = 32 / planes::tile_lps(a->n);
     // images in caller scratch (global-image form) when asked for and the scratch holds one image per resident tile
-    const bool glb = tile_glb_wanted() && a->scratch && a->scratch_bytes >= (int64_t)tile_glb_scratch_bytes(a->n, a->d);
+    // ... and the call has at least three times the warps the shared-memory form keeps resident: below that the extra
+    // warps do not exist and shared memory's latency wins (config 2 at its 10^4 shots: 2.10 vs 2.53 ms)
+    bool glb = tile_glb_wanted() && a->scratch && a->scratch_bytes >= (int64_t)tile_glb_scratch_bytes(a->n, a->d);
+    if (glb && !std::getenv("SDIMB_TILE_GLB")) {            // (SDIMB_TILE_GLB: developer knob, always scratch images)
+      auto ksm = tile_kernel_for(a->n, a->d, (a->flags & SDIMB_FRESH) && !no_uni, false);
+      const size_t ssm = planes::tile_smem_bytes(a->n, a->d);
+      int psm = 0;
+      if (cudaFuncSetAttribute(ksm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm) != cudaSuccess ||
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&psm, ksm, 32, ssm) != cudaSuccess || psm < 1) {
+        cudaGetLastError();
+        psm = 1;
+      }
+      glb = (a->shots + tpw - 1) / tpw >= 3ll * sms * psm;
+    }
     auto kern = tile_kernel_for(a->n, a->d, (a->flags & SDIMB_FRESH) && !no_uni, glb);
     const size_t smem = glb ? planes::tile_glb_smem_bytes(a->n) : planes::tile_smem_bytes(a->n, a->d);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||

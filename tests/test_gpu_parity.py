@@ -141,6 +141,8 @@ def test_tile_interpreter_both_measurement_forms(golden_random, golden_config_si
         monkeypatch.setenv("SDIMB_TILE_NO_UNI", "1")
     if img == "shared":
         monkeypatch.setenv("SDIMB_TILE_SMEM", "1")
+    else:
+        monkeypatch.setenv("SDIMB_TILE_GLB", "1")          # also for the few shots of this test
     checked = 0
     cases = [c for c in golden_random if c["d"] <= 3] + [c for c in golden_config_sizes if c["n"] <= 128]
     for case in cases:
