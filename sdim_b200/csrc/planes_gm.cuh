@@ -144,6 +144,52 @@ __device__ __noinline__ void gm_transpose(const GEO G, const GMImg<D> M, const b
   }
 }
 
+// The same transposition for the kernel that ran the gates on a SHARED-MEMORY image (gate_stream_kernel): to B / Bd / QX
+// only, shared-space loads with 32-bit addresses, no per-element predicates on full 32-row blocks.  (The general
+// routine above spent ~11 instructions per loaded word on generic addressing and predication: a quarter of the front
+// kernel's instructions.)
+template <int D, class GEO>
+__device__ __noinline__ void gm_transpose_out_smem(const GEO G, const GMImg<D> M, const int tid, const int nt) {
+  constexpr int EW = GMImg<D>::EW, EX = GMImg<D>::EX;
+  const int items = M.Wq * M.Wb * EW;
+  const uint32_t ssb = 4u * (uint32_t)G.RS;                               // bytes between two rows of the image
+  const int64_t qs = (int64_t)M.Wb * EX;                                  // words between two rows of QX
+  for (int it = tid; it < items; it += nt) {
+    const int pl = it % EW, jw = it / EW, j = jw % M.Wb, w = jw / M.Wb;
+    const bool destab = j >= M.Wq;
+    if (destab && pl >= EX) continue;                                     // Z planes of destabilizers are not kept
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(G.entry(32 * w, j) + pl);
+    uint32_t* b = destab ? M.dent(32 * j, w) + pl : M.bent(32 * j, w) + pl;
+    const int64_t bs = destab ? (int64_t)M.Wq * EX : (int64_t)M.Wq * EW;
+    const int alim = min(32, G.n - 32 * w);
+    uint32_t m[32];
+    if (alim == 32) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m[k]) : "r"(sa + (uint32_t)k * ssb));
+      if (pl < EX) {
+        uint32_t* qx = M.qent(32 * w, j) + pl;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { *qx = m[k]; qx += qs; }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        m[k] = 0u;
+        if (k < alim) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m[k]) : "r"(sa + (uint32_t)k * ssb));
+      }
+      if (pl < EX) {
+        uint32_t* const qx = M.qent(32 * w, j) + pl;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k < alim) qx[k * qs] = m[k];
+      }
+    }
+    transpose32(m);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { *b = m[k]; b += bs; }
+  }
+}
+
 // ---- one shot per TILE of LPS lanes ---------------------------------------------------------------------------
 // At n = 256 a row of QX has 16 lane words and a row of B 8 entries: half a warp holds everything a measurement
 // touches at once.  A shot therefore belongs to a tile of LPS = 4..32 lanes (the power of two >= Wb); the tiles of a

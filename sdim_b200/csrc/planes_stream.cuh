@@ -318,7 +318,7 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
       GMImg<D> M;
       M.n = G.n; M.np = G.np; M.Wq = G.np / 32; M.Wb = G.Wb;
       M.place(p.gm_slab + shot * p.gm_shot_stride_words);
-      gm_transpose<D>(G, M, true, tid, NT);
+      gm_transpose_out_smem<D>(G, M, tid, NT);
       out = reinterpret_cast<uint2*>(M.B + p.gm_slab_words);
     } else if (SM) {                                                         // ... or once as it is, coalesced
       for (int i = tid; i < row_words / 4; i += NT)
