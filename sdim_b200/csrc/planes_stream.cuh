@@ -65,6 +65,51 @@ inline size_t gate_stream_smem_bytes(int n, int64_t n_noise, int nw) {
   return 8 * (size_t)nw * gpw * Wb + 2 * 4 * (((size_t)n_noise + 31) / 32) + 16;   // fired bits per event and per layer
 }
 
+// This lane's window on the image: byte offsets of rows come from the stream.  SM: explicit shared-space accesses with
+// a 32-bit address computed once per shot (through a generic pointer the compiler rebuilt the CTA's shared window
+// address — S2R SR_CgaCtaId + LEA — in every iteration of the gate loop).
+template <int D, bool SM>
+struct RowAcc {
+  uint32_t s;       // shared address of lane word j of row 0 (SM)
+  uint8_t* g;       // generic pointer to the same (global image)
+  __device__ __forceinline__ XZ ld(int off) const {
+    if (SM) {
+      if (D == 3) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + off) : "memory");
+        return XZ{E{v.x, v.y}, E{v.z, v.w}};
+      }
+      uint2 v;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(s + off) : "memory");
+      return XZ{E{v.x, 0u}, E{v.y, 0u}};
+    }
+    if (D == 3) { const uint4 v = *reinterpret_cast<const uint4*>(g + off); return XZ{E{v.x, v.y}, E{v.z, v.w}}; }
+    const uint2 v = *reinterpret_cast<const uint2*>(g + off);
+    return XZ{E{v.x, 0u}, E{v.y, 0u}};
+  }
+  __device__ __forceinline__ void st(int off, XZ v) const {
+    if (SM) {
+      if (D == 3) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s + off), "r"(v.x.l), "r"(v.x.h), "r"(v.z.l), "r"(v.z.h) : "memory");
+      else asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s + off), "r"(v.x.l), "r"(v.z.l) : "memory");
+    } else if (D == 3) *reinterpret_cast<uint4*>(g + off) = make_uint4(v.x.l, v.x.h, v.z.l, v.z.h);
+    else *reinterpret_cast<uint2*>(g + off) = make_uint2(v.x.l, v.z.l);
+  }
+  __device__ __forceinline__ void stx(int off, E x) const {
+    if (SM) {
+      if (D == 3) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s + off), "r"(x.l), "r"(x.h) : "memory");
+      else asm volatile("st.shared.u32 [%0], %1;" ::"r"(s + off), "r"(x.l) : "memory");
+    } else if (D == 3) *reinterpret_cast<uint2*>(g + off) = make_uint2(x.l, x.h);
+    else *reinterpret_cast<uint32_t*>(g + off) = x.l;
+  }
+  __device__ __forceinline__ void stz(int off, E z) const {
+    if (SM) {
+      if (D == 3) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s + off + 8), "r"(z.l), "r"(z.h) : "memory");
+      else asm volatile("st.shared.u32 [%0], %1;" ::"r"(s + off + 4), "r"(z.l) : "memory");
+    } else if (D == 3) *reinterpret_cast<uint2*>(g + off + 8) = make_uint2(z.l, z.h);
+    else *reinterpret_cast<uint32_t*>(g + off + 4) = z.l;
+  }
+};
+
 template <int D, bool IL, bool SM>
 __global__ void __launch_bounds__(SM ? 32 * kGateStreamMaxWarps : 32 * SDIMB_SCHED_WARPS, SM ? 3 : SDIMB_GS_CTAS)
 gate_stream_kernel(const __grid_constant__ KParams p) {
@@ -105,6 +150,9 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
     uint32_t* const gimg = p.plane_slab + shot * p.img_stride_words;          // the image run_tail_kernel picks up
     G.tab = SM ? img : gimg;
     uint8_t* const tabj = reinterpret_cast<uint8_t*>(G.tab + joff);            // this lane's word of row 0
+    RowAcc<D, SM> R;
+    R.g = tabj;
+    R.s = SM ? (uint32_t)__cvta_generic_to_shared(tabj) : 0u;
     // ---- |0...0>, or pack from the uint8 store (same as interp_planes_kernel) ----
     for (int i = tid; i < row_words / 4; i += NT) reinterpret_cast<uint4*>(G.tab)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < NW * GPW * Wb; i += NT) acc[i] = make_uint2(0u, 0u);
@@ -197,8 +245,6 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
         const int opz = __shfl_sync(0xFFFFFFFFu, cur.z, src);
         const bool on = lane_on && (opx & GS_ON);
         const bool inv = (opx & GS_INV) != 0;
-        uint32_t* const ra = reinterpret_cast<uint32_t*>(tabj + opy);
-        uint32_t* const rb = reinterpret_cast<uint32_t*>(tabj + opz);
         switch (opx & 0xFF) {
         case GS_END: goto stream_done;
         case GS_SYNC: {
@@ -233,72 +279,61 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
         }
         case GS_H:
           if (on) {
-            const XZ v = G.ld_at(ra);
+            const XZ v = R.ld(opy);
             if (D == 3) {
               ph = add3(ph, neg3(mul3(v.x, v.z)));                          // phase -= x*z
-              const XZ nv = inv ? XZ{v.z, neg3(v.x)} : XZ{neg3(v.z), v.x};  // H: (x,z)<-(-z,x); H^-1: (x,z)<-(z,-x)
-              *reinterpret_cast<uint4*>(ra) = make_uint4(nv.x.l, nv.x.h, nv.z.l, nv.z.h);
+              R.st(opy, inv ? XZ{v.z, neg3(v.x)} : XZ{neg3(v.z), v.x});     // H: (x,z)<-(-z,x); H^-1: (x,z)<-(z,-x)
             } else {
               ph.h ^= v.x.l & v.z.l;                                        // phase += 2*x*z (mod 4); H == H^-1
-              *reinterpret_cast<uint2*>(ra) = make_uint2(v.z.l, v.x.l);
+              R.st(opy, XZ{v.z, v.x});
             }
           }
           break;
         case GS_P:
           if (on) {
-            const XZ v = G.ld_at(ra);
+            const XZ v = R.ld(opy);
             if (D == 3) {
               ph = add3(ph, inv ? E{0u, v.x.h} : E{v.x.h, 0u});             // phase +-= x(x-1)/2 = [x == 2]
-              const E z = add3(v.z, inv ? neg3(v.x) : v.x);                 // z +-= x
-              *reinterpret_cast<uint2*>(ra + 2) = make_uint2(z.l, z.h);
+              R.stz(opy, add3(v.z, inv ? neg3(v.x) : v.x));                 // z +-= x
             } else {
               if (inv) { const uint32_t borrow = ~ph.l & v.x.l; ph.l ^= v.x.l; ph.h ^= borrow; }   // phase -= x (mod 4)
               else { const uint32_t carry = ph.l & v.x.l; ph.l ^= v.x.l; ph.h ^= carry; }          // phase += x^2 = x
-              ra[1] = v.z.l ^ v.x.l;
+              R.stz(opy, E{v.z.l ^ v.x.l, 0u});
             }
           }
           break;
         case GS_CNOT:
           if (on) {
-            const XZ va = G.ld_at(ra), vb = G.ld_at(rb);
+            const XZ va = R.ld(opy), vb = R.ld(opz);
             if (D == 3) {
-              const E xb = add3(vb.x, inv ? neg3(va.x) : va.x);             // x[t] +-= x[c]
-              const E za = add3(va.z, inv ? vb.z : neg3(vb.z));             // z[c] -+= z[t]
-              *reinterpret_cast<uint2*>(rb) = make_uint2(xb.l, xb.h);
-              *reinterpret_cast<uint2*>(ra + 2) = make_uint2(za.l, za.h);
+              R.stx(opz, add3(vb.x, inv ? neg3(va.x) : va.x));              // x[t] +-= x[c]
+              R.stz(opy, add3(va.z, inv ? vb.z : neg3(vb.z)));              // z[c] -+= z[t]
             } else {
-              rb[0] = vb.x.l ^ va.x.l;
-              ra[1] = va.z.l ^ vb.z.l;
+              R.stx(opz, E{vb.x.l ^ va.x.l, 0u});
+              R.stz(opy, E{va.z.l ^ vb.z.l, 0u});
             }
           }
           break;
         case GS_CZ:
           if (on) {
-            const XZ va = G.ld_at(ra), vb = G.ld_at(rb);
+            const XZ va = R.ld(opy), vb = R.ld(opz);
             if (D == 3) {
               const E prod = mul3(va.x, vb.x);
               ph = add3(ph, inv ? neg3(prod) : prod);                       // phase +-= x[a]*x[b]
-              const E za = add3(va.z, inv ? neg3(vb.x) : vb.x), zb = add3(vb.z, inv ? neg3(va.x) : va.x);
-              *reinterpret_cast<uint2*>(ra + 2) = make_uint2(za.l, za.h);
-              *reinterpret_cast<uint2*>(rb + 2) = make_uint2(zb.l, zb.h);
+              R.stz(opy, add3(va.z, inv ? neg3(vb.x) : vb.x));
+              R.stz(opz, add3(vb.z, inv ? neg3(va.x) : va.x));
             } else {
               ph.h ^= va.x.l & vb.x.l;
-              ra[1] = va.z.l ^ vb.x.l;
-              rb[1] = vb.z.l ^ va.x.l;
+              R.stz(opy, E{va.z.l ^ vb.x.l, 0u});
+              R.stz(opz, E{vb.z.l ^ va.x.l, 0u});
             }
           }
           break;
         case GS_SWAP:
           if (on) {
-            if (D == 3) {
-              const uint4 va = *reinterpret_cast<const uint4*>(ra), vb = *reinterpret_cast<const uint4*>(rb);
-              *reinterpret_cast<uint4*>(ra) = vb;
-              *reinterpret_cast<uint4*>(rb) = va;
-            } else {
-              const uint2 va = *reinterpret_cast<const uint2*>(ra), vb = *reinterpret_cast<const uint2*>(rb);
-              *reinterpret_cast<uint2*>(ra) = vb;
-              *reinterpret_cast<uint2*>(rb) = va;
-            }
+            const XZ va = R.ld(opy), vb = R.ld(opz);
+            R.st(opy, vb);
+            R.st(opz, va);
           }
           break;
         default: break;
