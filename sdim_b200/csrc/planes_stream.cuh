@@ -125,8 +125,9 @@ gate_stream_kernel(const __grid_constant__ KParams p) {
   const int Wb = G.Wb, row_words = (p.n * G.RS + 3) & ~3;
   const int4* const S = reinterpret_cast<const int4*>(p.gate_stream);
   const int4 hdr = __ldg(S), misc = __ldg(S + 1), geo = __ldg(S + 2);
-  // not a stream compiled for this launch shape / image
-  if (hdr.x != kGateStreamMagic || hdr.z != NW || geo.x != 4 * G.RS || geo.y != (IL ? 1 : 0)) return;
+  // not a stream compiled for this launch shape / image (a caller mixing library builds or developer knobs between
+  // sdimb_gate_stream and sdimb_run): fail loudly — the launch ends in a CUDA error, never in silent garbage records
+  if (hdr.x != kGateStreamMagic || hdr.z != NW || geo.x != 4 * G.RS || geo.y != (IL ? 1 : 0)) __trap();
   const int GPW = hdr.y, n_tab = hdr.w, tab_base = misc.x, n_pauli = misc.w;
   const int gsub = lane / Wb, j = lane - gsub * Wb;
   const bool lane_on = gsub < GPW;
