@@ -466,7 +466,9 @@ inline size_t run_shot_stride_words(int n, int d) {   // B + QX + phase planes o
   return (run_slab_words(n, d) + 2 * Wb + 7) & ~(size_t)7;
 }
 
-template <int D, bool IL, int LPS>
+// PRE: the kernel that ran the gates left B / Bd / QX in place (KParams::gm_per_shot): no transposition code in this
+// instantiation.
+template <int D, bool IL, int LPS, bool PRE = false>
 __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(const __grid_constant__ KParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   constexpr int TILES = kRunThreads / LPS;
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
     shot = T.shfl(shot, 0);
     if (shot >= p.shots) break;
     const uint2* ph;
-    if (p.gm_per_shot) {         // gate_stream_kernel already left B, QX and the phase planes of this shot in place
+    if (PRE || p.gm_per_shot) {  // gate_stream_kernel already left B, QX and the phase planes of this shot in place
       M.place(p.gm_slab + shot * p.gm_shot_stride_words);
       ph = reinterpret_cast<const uint2*>(M.B + p.gm_slab_words);
     } else {
@@ -502,7 +504,7 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
       const uint2 w = ph[g >> 5];
       M.ph8[g] = (uint8_t)(((w.x >> (g & 31)) & 1u) | (((w.y >> (g & 31)) & 1u) << 1));
     }
-    if (!p.gm_per_shot) gm_transpose<D>(G, M, true, lane, LPS);
+    if (!PRE && !p.gm_per_shot) gm_transpose<D>(G, M, true, lane, LPS);
     T.sync();
     for (int64_t i0 = p.tail_start; i0 < p.n_ops; i0 += LPS) {
       int4 mine = make_int4(SDIMB_OP_I, 0, 0, 0);

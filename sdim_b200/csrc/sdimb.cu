@@ -176,20 +176,22 @@ int planes_global_ctas(int n, int d, size_t* smem_out) {
 }
 
 // Trailing measurement run on a generator-major image (planes_gm.cuh): kernel, resident CTAs, scratch layout.
-template <int LPS>
+template <int LPS, bool PRE>
 PlaneKernel run_tail_kernel_lps(int d, bool il) {
-  if (il) return (d == 2) ? planes::run_tail_kernel<2, true, LPS> : planes::run_tail_kernel<3, true, LPS>;
-  return (d == 2) ? planes::run_tail_kernel<2, false, LPS> : planes::run_tail_kernel<3, false, LPS>;
+  if (il) return (d == 2) ? planes::run_tail_kernel<2, true, LPS, PRE> : planes::run_tail_kernel<3, true, LPS, PRE>;
+  return (d == 2) ? planes::run_tail_kernel<2, false, LPS, PRE> : planes::run_tail_kernel<3, false, LPS, PRE>;
 }
-PlaneKernel run_tail_kernel_for(int n, int d) {
+template <bool PRE>
+PlaneKernel run_tail_kernel_pre(int n, int d) {
   const bool il = planes_interleaved(n);
   switch (planes::run_lps(n)) {
-    case 4: return run_tail_kernel_lps<4>(d, il);
-    case 8: return run_tail_kernel_lps<8>(d, il);
-    case 16: return run_tail_kernel_lps<16>(d, il);
-    default: return run_tail_kernel_lps<32>(d, il);
+    case 4: return run_tail_kernel_lps<4, PRE>(d, il);
+    case 8: return run_tail_kernel_lps<8, PRE>(d, il);
+    case 16: return run_tail_kernel_lps<16, PRE>(d, il);
+    default: return run_tail_kernel_lps<32, PRE>(d, il);
   }
 }
+PlaneKernel run_tail_kernel_for(int n, int d, bool pre = false) { return pre ? run_tail_kernel_pre<true>(n, d) : run_tail_kernel_pre<false>(n, d); }
 bool tail_run_shape_ok(int n, int d) { return (d == 2 || d == 3) && (n + 31) / 32 * 32 <= 512; }   // Wb <= 32
 int run_tail_ctas(int n, int d) {
   auto kern = run_tail_kernel_for(n, d);
@@ -600,7 +602,11 @@ int sdimb_run(const SdimbRunArgs* caller) {
       const int tiles = planes::kRunThreads / planes::run_lps(a->n);
       int64_t grid2 = (a->shots + tiles - 1) / tiles;
       if (grid2 > run_ctas_max) grid2 = run_ctas_max;
-      auto kern2 = run_tail_kernel_for(a->n, a->d);
+      auto kern2 = run_tail_kernel_for(a->n, a->d, fused);
+      if (fused && cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)planes::run_smem_bytes(a->n)) != cudaSuccess) {
+        cudaGetLastError();
+        return SDIMB_ECUDA;
+      }
       kern2<<<(unsigned)grid2, planes::kRunThreads, planes::run_smem_bytes(a->n), (cudaStream_t)a->stream>>>(p2);
       g_launches++;
       if (timed) { cudaEventRecord(g_time_ev[2], (cudaStream_t)a->stream); g_time_valid = 1; }
