@@ -201,13 +201,42 @@ def config_cases():
     return out
 
 
-def main_configs():
+def lanes_cases():
+    """(name, n, d, ops, noise_ab) of one-shot cases for the uint8-LANE kernels at multi-word sizes (d = 5, 7, 11): the
+    headline circuit family (noisy random Clifford + M on all qudits: the stream shape run_tail8_kernel takes) and
+    streams with mid-circuit M / M_X / RESET in front of the final measurement.  Noise as in config_cases (Philox seed
+    2026, shot 0, probabilities boosted so that events fire)."""
+    from sdim_b200.ir import compile_circuits
+    from sdim_b200.rng import noise_draws, prob_to_thresh24
+    from sdim_b200.workloads import noisy_random_clifford
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN_DIR)))
+    from make_cases import random_circuit
+    out = []
+
+    def add(name, circ, boost=1.0):
+        prog = compile_circuits([circ])
+        noise = np.zeros((0, 2), dtype=np.int64)
+        if prog.n_noise:
+            thr = np.array([prob_to_thresh24(min(1.0, boost * p)) for p in prog.noise_prob], dtype=np.uint32)
+            noise = noise_draws(2026, prog.dimension, np.array([0]), thr, prog.noise_channel)[0].astype(np.int64)
+        out.append((name, prog.num_qudits, prog.dimension, prog.ops.tolist(), noise))
+
+    add("headline_shape_n100_d5", noisy_random_clifford(100, 700, 5, seed=3, prob=1e-3, channel="d"), boost=30.0)
+    add("headline_shape_n160_d7", noisy_random_clifford(160, 900, 7, seed=4, prob=1e-3, channel="d"), boost=30.0)
+    add("headline_shape_n256_d5", noisy_random_clifford(256, 1200, 5, seed=1, prob=1e-3, channel="d"), boost=30.0)
+    add("mixed_stream_n97_d7", random_circuit(seed=71, n=97, d=7, depth=500))
+    add("mixed_stream_n130_d11", random_circuit(seed=72, n=130, d=11, depth=500))
+    return out
+
+
+def main_configs(cases=None, filename="config_sizes.npz"):
     """One reference shot per BASELINE.json config size (n = 64, 97, 49, 256): pins both oracles, and through them
     every GPU mode, where round 1's goldens (n <= 13) could not see — multi-word lane rows, the headline shape.
-    Stored compactly (uint8 / int32 arrays in one .npz); records rows are (qudit, deterministic, value)."""
+    Stored compactly (uint8 / int32 arrays in one .npz); records rows are (qudit, deterministic, value).
+    `--lanes` writes lanes_sizes.npz from lanes_cases() in the same format."""
     import time
     blob, names = {}, []
-    for name, n, d, ops, noise in config_cases():
+    for name, n, d, ops, noise in (cases if cases is not None else config_cases()):
         t0 = time.time()
         recs, arrs = rh.ref_run(n, d, ops, noise, draw_seed=2026)
         recs2, arrs2 = rh.ref_run_eager_modulo(n, d, ops, noise, draw_seed=2026)
@@ -225,7 +254,7 @@ def main_configs():
         print(f"{name}: n={n} d={d} ops={len(ops)} noise fired={int((noise.sum(axis=1) > 0).sum())} "
               f"records={len(recs)} ({n_rand} random) {time.time() - t0:.1f}s")
     blob["names"] = np.array(names)
-    path = os.path.join(GOLDEN_DIR, "config_sizes.npz")
+    path = os.path.join(GOLDEN_DIR, filename)
     np.savez_compressed(path, **blob)
     print(f"wrote {path} ({os.path.getsize(path)} bytes)")
 
@@ -233,6 +262,8 @@ def main_configs():
 if __name__ == "__main__":
     if "--configs" in sys.argv:
         main_configs()
+    elif "--lanes" in sys.argv:
+        main_configs(lanes_cases(), "lanes_sizes.npz")
     elif "--large" in sys.argv:
         main_large()
     elif "--wide" in sys.argv:

@@ -68,6 +68,26 @@ def golden_wide_primes():
         return json.load(fh)["cases"]
 
 
+def _load_npz_cases(filename):
+    import numpy as np
+    out = []
+    with np.load(os.path.join(GOLDEN_DIR, filename)) as z:
+        for name in z["names"]:
+            name = str(name)
+            n, d = (int(v) for v in z[name + "/nd"])
+            out.append({"name": name, "n": n, "d": d, "ops": z[name + "/ops"], "noise_ab": z[name + "/noise_ab"],
+                        "records": z[name + "/records"],
+                        "final": {k: z[name + "/" + k].astype(np.int64) for k in ("x", "z", "p", "dx", "dz", "dp")}})
+    return out
+
+
+@pytest.fixture(scope="session")
+def golden_lanes_sizes():
+    """tests/golden/lanes_sizes.npz (oracle/make_golden.py --lanes): one shot of the UNMODIFIED reference per case for the
+    uint8-lane kernels at multi-word sizes (d = 5, 7, 11; n = 97 ... 256), same format as golden_config_sizes."""
+    return _load_npz_cases("lanes_sizes.npz")
+
+
 @pytest.fixture(scope="session")
 def golden_config_sizes():
     """tests/golden/config_sizes.npz (oracle/make_golden.py --configs): one shot of the UNMODIFIED reference per

@@ -507,6 +507,44 @@ def test_two_kernel_paths_edge_cases(d, n):
             assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("form", ["tail8", "tail8-tma", "one-kernel", "keep"])
+def test_lane_kernels_on_the_reference_goldens(golden_lanes_sizes, monkeypatch, form):
+    """Outputs of the UNMODIFIED reference at d = 5, 7, 11 and n = 97 ... 256 (tests/golden/lanes_sizes.npz) replayed into
+    the uint8-lane kernels: the two-kernel path (lane interpreter + run_tail8_kernel, with ordinary loads and with TMA
+    staging), the interpreter alone, and — tableau kept — all six final arrays, in every mode that holds the shape."""
+    import torch
+    from sdim_b200.engine import TableauEngine
+    from sdim_b200.ir import compile_circuits
+    if form == "tail8-tma":
+        monkeypatch.setenv("SDIMB_TAIL8_TMA", "1")
+    if form == "one-kernel":
+        monkeypatch.setenv("SDIMB_NO_TAIL8", "1")
+    for case in golden_lanes_sizes:
+        n, d, ops = case["n"], case["d"], case["ops"]
+        prog = compile_circuits([circuit_from_ops(n, d, ops)])
+        eng = TableauEngine(prog)
+        want = np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+        shots = 6
+        rm = torch.from_numpy(np.tile((want & 0x7F)[None, :], (shots, 1)))
+        rn = torch.from_numpy(np.tile(case["noise_ab"][None], (shots, 1, 1)))
+        if form == "keep":
+            for mode in ("global", "resident", "global-cta"):
+                try:
+                    eng.plan(mode)
+                except ValueError:
+                    continue
+                got = eng.run(shots, 0, 99, rm, rn, keep_tableau=True, mode=mode).cpu().numpy()
+                assert all(np.array_equal(got[s], want) for s in range(shots)), (case["name"], mode)
+                arrs = eng.export(eng.tableau, shots - 1)
+                for key in ("x", "z", "p", "dx", "dz", "dp"):
+                    assert np.array_equal(arrs[key], case["final"][key]), (case["name"], mode, key)
+            continue
+        before = _launches()
+        got = eng.run(shots, 0, 99, rm, rn).cpu().numpy()              # auto: HBM store (n >= 96), tail run in the second kernel
+        assert _launches() - before == (1 if form == "one-kernel" else 2), case["name"]
+        assert all(np.array_equal(got[s], want) for s in range(shots)), (case["name"], form)
+
+
 @pytest.mark.parametrize("off", [False, True, "tma"])
 @pytest.mark.parametrize("d,n,depth", [(5, 256, 2500), (7, 97, 1500), (3, 130, 1200), (2, 200, 1500), (13, 40, 900),
                                        (127, 64, 700), (5, 500, 900), (11, 5, 300), (5, 512, 600)])

@@ -124,6 +124,31 @@ def test_oracles_match_reference_goldens_at_config_sizes(golden_config_sizes):
                 assert np.array_equal(arr, case["final"][key]), (case["name"], key)
 
 
+def test_oracles_match_reference_goldens_for_the_lane_kernels(golden_lanes_sizes):
+    """One reference shot per case at d = 5, 7, 11 and n = 97 ... 256 (oracle/make_golden.py --lanes): the headline
+    circuit family in the dimensions the uint8 lanes serve, and streams with mid-circuit M / M_X / RESET.  Pins the C
+    oracle (and the numpy one at n <= 100) where the GPU tests of the lane interpreter and of run_tail8_kernel lean on it."""
+    assert {(c["n"], c["d"]) for c in golden_lanes_sizes} == {(100, 5), (160, 7), (256, 5), (97, 7), (130, 11)}
+    assert sum(int((c["records"][:, 1] == 0).sum()) for c in golden_lanes_sizes) > 300      # random measurements
+    for case in golden_lanes_sizes:
+        n, d, ops = case["n"], case["d"], case["ops"]
+        want = np.array([(m & 0x7F) | (0x80 if det else 0) for _, det, m in case["records"]], dtype=np.uint8)
+        noise = case["noise_ab"]
+        assert int((noise.sum(axis=1) > 0).sum()) >= 10
+        if c_oracle.available():
+            rec, fin = c_oracle.run(n, d, ops, 1, replay_meas=(want & 0x7F)[None, :],
+                                    replay_noise=noise.reshape(1, -1, 2), want_final=True)
+            assert np.array_equal(rec[0], want), case["name"]
+            for key in KEYS:
+                assert np.array_equal(fin[key], case["final"][key]), (case["name"], key)
+        if n <= 100:
+            draws = [int(r[2]) for r in case["records"]]
+            recs, t = run_shot(n, d, ops.tolist(), lambda k: draws[k], noise.astype(np.int64))
+            assert recs == [(int(q), bool(det), int(m)) for q, det, m in case["records"]], case["name"]
+            for key, arr in zip(KEYS, t.arrays()):
+                assert np.array_equal(arr, case["final"][key]), (case["name"], key)
+
+
 def test_shipped_circuit_goldens(golden_shipped):
     """circuits/css_steane_final.chp -> 1,1,0,1,1,0 all deterministic; circuits/epr.chp -> qudit 1 random."""
     st = golden_shipped["circuits/css_steane_final.chp"]
