@@ -1,7 +1,7 @@
 #!/bin/bash
 # dev helper: 2-GPU bench under torchrun (run through gpurun --gpus 2)
 N=${1:-2}
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 --shots 16384 2>gpurun_out/n$N.err | tail -1 > gpurun_out/bench_r1_n$N.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 2>gpurun_out/n$N.err | tail -1 > gpurun_out/bench_r1_n$N.json
 python - <<PY
 import json
 j = json.load(open("gpurun_out/bench_r1_n$N.json"))
