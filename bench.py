@@ -720,9 +720,11 @@ def bench_ours(args):
                      "traffic": traffic,
                      "achieved_dram": (traffic / launch_s / 1e9) if traffic else None,
                      "frac_dram": (traffic / launch_s / 1e9 / peak) if traffic else None,
-                     "limiter": "latency of dependent row accesses at half occupancy, with real DRAM traffic at "
-                                "frac_dram of the HBM peak (see issue and DESIGN.md section 4); `achieved` is the "
-                                "contract's algorithmic-bytes reading (effective GB/s)",
+                     "limiter": "instruction issue (see `issue.frac`) and the latency of dependent row accesses at 42 % "
+                                "warps-active, not HBM: real DRAM traffic is `frac_dram` of the HBM peak.  `achieved` / "
+                                "`frac` is the contract's reading — SURVEY 8d algorithmic bytes at ONE BYTE per entry over "
+                                "the kernel's live-timed duration — and exceeds 1 because the bit planes move a quarter "
+                                "of those bytes (DESIGN.md section 4.1)",
                      "issue": issue, "ncu_capture": capture,
                      "kernel": dominant, "peak_source": peak_src,
                      "step_kernels": kernels, "step_ms": step_s * 1e3,
