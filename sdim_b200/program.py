@@ -408,8 +408,9 @@ class Program:
         values = np.zeros((shots, compiled.n_meas), dtype=R.np_dtype(compiled.dimension))
         det = np.zeros((shots, compiled.n_meas), dtype=bool)
         snaps = [[None] * compiled.n_meas for _ in range(shots)] if options.record_tableau else None
-        user_ops = [op for c in self.circuits for op in c.operations if op.gate_id != 0]
-        length = len(user_ops)
+        # the reference's step numbering (sdim/program.py:301,311-346): `time` restarts in every circuit and counts I
+        # gates, "Final step" compares it with the total number of operations of all circuits
+        length = sum(len(c.operations) for c in self.circuits)
         last = None
         for s in range(shots):
             store = self._initial_store(engine, 1)
@@ -419,14 +420,19 @@ class Program:
             rec = torch.zeros((1, compiled.n_meas), dtype=R.torch_dtype(compiled.dimension), device=engine.device)
             srm = None if rm is None else rm[s:s + 1]
             srn = None if rn is None else rn[s:s + 1]
-            if options.verbose:
-                print("Initial state")
-                ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, engine.export(store, 0)).print_tableau()
-                print("\n")
-            for i in range(compiled.n_ops):
-                engine.run(1, s, seed, srm, srn, keep_tableau=True, mode=mode, tableau=store, fresh=False,
-                           op_range=(i, i + 1), records=rec)
-                op, _, _, slot = (int(v) for v in compiled.ops[i])
+            steps = [(t, g) for c in self.circuits for t, g in enumerate(c.operations)]
+            i = -1                                       # index of the current instruction in the compiled stream (I gates are not in it)
+            for time, g in steps:
+                if time == 0 and options.verbose:
+                    print("Initial state")
+                    ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, engine.export(store, 0)).print_tableau()
+                    print("\n")
+                op = slot = -1
+                if g.gate_id != 0:
+                    i += 1
+                    engine.run(1, s, seed, srm, srn, keep_tableau=True, mode=mode, tableau=store, fresh=False,
+                               op_range=(i, i + 1), records=rec)
+                    op, _, _, slot = (int(v) for v in compiled.ops[i])
                 if snaps is not None and op in MEASURE_OPS:
                     arrays = engine.export(store, 0)
                     if op == OP_RESET:
@@ -437,9 +443,8 @@ class Program:
                         arrays = undo_reset_correction(arrays, int(compiled.ops[i][1]), outcome, compiled.dimension)
                     snaps[s][slot] = ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension, arrays)
                 if options.show_gate:
-                    g = user_ops[i]
                     info = g.target_index if g.target_index is not None else ""
-                    print("Time step" if i < length - 1 else "Final step", i, "\t", g.name, g.qudit_index, info)
+                    print("Time step" if time < length - 1 else "Final step", time, "\t", g.name, g.qudit_index, info)
                 if options.verbose:
                     ExtendedTableau.from_arrays(compiled.num_qudits, compiled.dimension,
                                                 engine.export(store, 0)).print_tableau()

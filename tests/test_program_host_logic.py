@@ -90,9 +90,24 @@ def test_verbose_and_show_gate_step_every_op(capsys):
     P = Program(c)
     res = P.simulate(shots=1, verbose=True, show_gate=True, show_measurement=True, seed=5)
     out = capsys.readouterr().out
-    assert "Initial state" in out and "Time step 0" in out and "Final step 3" in out and "Measured qudit (0)" in out
+    # the reference's numbering (sdim/program.py:311-346): `time` counts I gates; "Final step" at time = total ops - 1
+    assert "Initial state" in out and "Time step 0 \t H 0" in out and "Time step 1 \t I 1" in out and "Time step 2 \t CNOT 0 1" in out
+    assert "Time step 3 \t M 0" in out and "Final step 4 \t M 1" in out and "Measured qudit (0)" in out
     assert res[0].measurement_value == res[1].measurement_value and res[1].deterministic and not res[0].deterministic
-    assert [r[1] for r in P._engine.runs] == [(i, i + 1) for i in range(4)]     # one launch per op, I dropped
+    assert [r[1] for r in P._engine.runs] == [(i, i + 1) for i in range(4)]     # one launch per op, I not launched
+
+
+def test_show_gate_numbering_restarts_in_every_appended_circuit(capsys):
+    a = Circuit(2, 3); a.add_gate("H", 0); a.add_gate("CNOT", 0, 1)
+    b = Circuit(2, 3); b.add_gate("I", 0); b.add_gate("M", 1)
+    P = Program(a)
+    P.append_circuit(b)
+    P.simulate(shots=1, verbose=True, show_gate=True, seed=1)
+    out = capsys.readouterr().out
+    lines = [ln for ln in out.splitlines() if "step" in ln]
+    # `time` restarts with each circuit; with 4 operations in total only time = 3 would be the "Final step" (reference :341-344)
+    assert [ln.split("\t")[0].strip() for ln in lines] == ["Time step 0", "Time step 1", "Time step 0", "Time step 1"]
+    assert out.count("Initial state") == 2                                      # once per circuit (reference :313-316)
 
 
 def test_fold_gates_uploads_the_folded_stream_and_changes_nothing():
