@@ -120,3 +120,14 @@ def test_gate_stream_rejects_what_it_cannot_compile():
     assert gs is not None and int(gs[1][2]) == 2 and _decode(gs, 3).tolist() == [[5, 0, -1, -1], [9, 0, 1, -1]]
     empty = N.gate_stream(n, 3, np.zeros((0, 4), dtype=np.int32))
     assert empty is not None and int(empty[1][2]) == 0
+
+
+def test_gate_stream_gives_up_above_its_noise_table_limit():
+    """More than 65 536 N1 ops in the stretch: the fired bits would not fit the kernel's shared-memory table; the
+    compiler returns SDIMB_EINVAL and the caller runs the interpreter (TableauEngine.gate_stream is None then)."""
+    n, k = 8, 65537
+    ops = np.zeros((k + 1, 4), dtype=np.int32)
+    ops[:k, 0], ops[:k, 1], ops[:k, 2], ops[:k, 3] = 17, np.arange(k) % n, -1, np.arange(k)
+    ops[k] = (5, 0, -1, -1)
+    assert N.gate_stream(n, 3, ops) is None
+    assert N.gate_stream(n, 3, ops[1:]) is not None            # 65 536 events: still compiled
