@@ -57,9 +57,27 @@ struct GMImg {
                                                  // does not keep the tableau never reads a destabilizer's Z part or phase
                                                  // (factors come from its X part, tableau_prime.py:350; rowsum writes it)
   uint32_t* QX;
-  uint8_t* ph8;
-  uint16_t* list;                                // [2np] scratch: compacted generator / row lists
+  uint32_t ph8;                                  // shared-space ADDRESSES (32-bit) of the tile's phase bytes [2np] and
+  uint32_t list;                                 // of its scratch list [2np] uint16: explicit ld/st.shared below — through
+                                                 // generic pointers the compiler rebuilt the CTA's shared window (S2R
+                                                 // SR_CgaCtaId + LEA) at many of the ~15 access sites of a measurement
   int n, np, Wq, Wb, gs_shift;                   // group of lanes per B row = 1 << gs_shift >= Wq
+  __device__ __forceinline__ uint32_t ldl(int k) const {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(list + 2u * (uint32_t)k) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void stl(int k, uint32_t v) const {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(list + 2u * (uint32_t)k), "r"(v) : "memory");
+  }
+  __device__ __forceinline__ uint32_t ldp(int i) const {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ph8 + (uint32_t)i) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void stp(int i, uint32_t v) const {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(ph8 + (uint32_t)i), "r"(v) : "memory");
+  }
   __device__ __forceinline__ void place(uint32_t* slab) {        // B, Bd, QX of one shot, in this order
     B = slab;
     Bd = B + (size_t)np * Wq * EW;
@@ -221,8 +239,8 @@ struct Tile {
 
 // Set bits of up to two mask words per lane (word indices w0 < w1 ascending with the lane) -> list entries
 // (32 * w + bit) | value << 12, in ascending order; returns the total (tile-uniform).
-template <int LPS>
-__device__ __forceinline__ int gm_compact(const Tile<LPS>& T, uint16_t* list, uint32_t m0, E v0, int w0, uint32_t m1, E v1,
+template <int LPS, class IMG>
+__device__ __forceinline__ int gm_compact(const Tile<LPS>& T, const IMG& M, uint32_t m0, E v0, int w0, uint32_t m1, E v1,
                                           int w1) {
   const int c0 = __popc(m0), cnt = c0 + __popc(m1);
   int incl = cnt;
@@ -235,12 +253,12 @@ __device__ __forceinline__ int gm_compact(const Tile<LPS>& T, uint16_t* list, ui
   while (m0) {
     const int b = __ffs(m0) - 1;
     m0 &= m0 - 1;
-    list[pos++] = (uint16_t)((32 * w0 + b) | (bit2(v0, b) << 12));
+    M.stl(pos++, (uint32_t)(32 * w0 + b) | (bit2(v0, b) << 12));
   }
   while (m1) {
     const int b = __ffs(m1) - 1;
     m1 &= m1 - 1;
-    list[pos++] = (uint16_t)((32 * w1 + b) | (bit2(v1, b) << 12));
+    M.stl(pos++, (uint32_t)(32 * w1 + b) | (bit2(v1, b) << 12));
   }
   const int total = T.shfl(incl, LPS - 1);
   T.sync();
@@ -289,14 +307,14 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
     const uint32_t e = (D == 3) ? bit2(E{T.shfl(xq.l, jp), T.shfl(xq.h, jp)}, bp) : 1u;
     E f = negD<D>(xq);                                   // f_i = -X[q,i]; the pivot and its destabilizer are replaced below
     if (lane == jp || lane == Wq + jp) { f.l &= ~(1u << bp); f.h &= ~(1u << bp); }
-    const int total = gm_compact<LPS>(T, M.list, f.l | f.h, f, lane, 0u, ezero, 0);
+    const int total = gm_compact<LPS>(T, M, f.l | f.h, f, lane, 0u, ezero, 0);
     // first batch of generator rows: requested before anything waits for the pivot row
     XZ va[UB], vb[UB];
     uint32_t ent[UB];
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       const int k = u * ng + grp;
-      ent[u] = (k < total) ? (uint32_t)M.list[k] | 0x8000u : 0u;
+      ent[u] = (k < total) ? M.ldl(k) | 0x8000u : 0u;
       va[u] = vb[u] = zero;
       if ((ent[u] & 0x8000u) && has0) va[u] = M.ldB(ent[u] & 0xFFFu, w0);
       if ((ent[u] & 0x8000u) && has1) vb[u] = M.ldB(ent[u] & 0xFFFu, w1);
@@ -304,7 +322,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
     uint32_t sdp = popsum<D>(mulD<D>(pv0.x, pv0.z)) + popsum<D>(mulD<D>(pv1.x, pv1.z));
     for (int off = 1; off < gb; off <<= 1) sdp += T.shfl_xor(sdp, off);
     const uint32_t sd_raw = sdp % D;
-    const uint32_t ps_old = M.ph8[piv];
+    const uint32_t ps_old = M.ldp(piv);
     const uint32_t ps = (ps_old * e + PO * ((sd_raw * ((e * (e - 1u)) >> 1)) % D)) % ORDER;
     const uint32_t sd = (sd_raw * e * e) % D;
     if (D == 3 && e == 2u) { pv0.x = neg3(pv0.x); pv0.z = neg3(pv0.z); pv1.x = neg3(pv1.x); pv1.z = neg3(pv1.z); }
@@ -322,8 +340,8 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
         for (int off = 1; off < gb; off <<= 1) dot += T.shfl_xor(dot, off);
         if (act && sub == 0 && i < np) {                                  // (a destabilizer's phase is never read)
           // P_i += f*ps + po*((Z_i.xs)*f + sd*f(f-1)/2*po)      (tableau_prime.py:310-312,317-319)
-          const uint32_t ph = M.ph8[i];
-          M.ph8[i] = (uint8_t)((ph + fi * ps + PO * ((dot * fi + sd * ((fi * (fi - 1u)) >> 1) * PO) % D)) % ORDER);
+          const uint32_t ph = M.ldp(i);
+          M.stp(i, (ph + fi * ps + PO * ((dot * fi + sd * ((fi * (fi - 1u)) >> 1) * PO) % D)) % ORDER);
         }
       }
       k0 += UB * ng;
@@ -331,7 +349,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
         const int k = k0 + u * ng + grp;
-        ent[u] = (k < total) ? (uint32_t)M.list[k] | 0x8000u : 0u;
+        ent[u] = (k < total) ? M.ldl(k) | 0x8000u : 0u;
         va[u] = vb[u] = zero;
         if ((ent[u] & 0x8000u) && has0) va[u] = M.ldB(ent[u] & 0xFFFu, w0);
         if ((ent[u] & 0x8000u) && has1) vb[u] = M.ldB(ent[u] & 0xFFFu, w1);
@@ -343,7 +361,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
     // QX rows: gq = 2 gb lanes per row, lane `subq` holds lane words 2 subq and 2 subq + 1.
     {
       const bool lead = grp == 0;                                        // group 0 lists the rows
-      const int totq = gm_compact<LPS>(T, M.list, (lead && has0) ? (pv0.x.l | pv0.x.h | dx0.l | dx0.h) : 0u, pv0.x, w0,
+      const int totq = gm_compact<LPS>(T, M, (lead && has0) ? (pv0.x.l | pv0.x.h | dx0.l | dx0.h) : 0u, pv0.x, w0,
                                        (lead && has1) ? (pv1.x.l | pv1.x.h | dx1.l | dx1.h) : 0u, pv1.x, w1);
       const int gq = 2 << M.gs_shift, subq = lane & (gq - 1), grpq = lane >> (M.gs_shift + 1), ngq = LPS >> (M.gs_shift + 1);
       const int j0 = 2 * subq, j1 = 2 * subq + 1;
@@ -360,7 +378,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
           en[u] = 0u;
           xa[u] = xb[u] = ezero;
           if (k < totq && hq) {
-            const uint32_t t = M.list[k];
+            const uint32_t t = M.ldl(k);
             if (((t >> 12) && any_f) || fix) { en[u] = t | 0x8000u; M.ldqx2(t & 0xFFFu, j0, xa[u], xb[u]); }
           }
         }
@@ -387,8 +405,8 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
       if (has1) { M.stB(np + piv, w1, pv1); M.stB(piv, w1, u1); }
     }
     if (lane == 0) {
-      M.ph8[np + piv] = (uint8_t)ps;
-      M.ph8[piv] = (uint8_t)((ORDER - draw * PO) % ORDER);
+      M.stp(np + piv, ps);
+      M.stp(piv, (ORDER - draw * PO) % ORDER);
     }
     rec = draw;        // replayed or Philox, resolved when the op was fetched (reference: random.choice, :332)
   } else {
@@ -398,7 +416,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
     if (lane >= Wq && lane < Wb) fd = xq;
     const E fsh{T.shfl_down(fd.l, Wq & (LPS - 1)), T.shfl_down(fd.h, Wq & (LPS - 1))};   // lane j: destabilizer word j
     const E fl = (lane < Wq && Wq < LPS) ? fsh : ezero;
-    const int total = gm_compact<LPS>(T, M.list, fl.l | fl.h, fl, lane, 0u, ezero, 0);   // ordered (stabilizer | f << 12)
+    const int total = gm_compact<LPS>(T, M, fl.l | fl.h, fl, lane, 0u, ezero, 0);   // ordered (stabilizer | f << 12)
     E az0 = ezero, az1 = ezero;
     uint32_t cross = 0, sdg = 0, a1 = 0;
     for (int k0 = 0; k0 < total; k0 += UB) {
@@ -406,7 +424,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
       uint32_t ent[UB];
 #pragma unroll
       for (int u = 0; u < UB; ++u) {
-        ent[u] = (k0 + u < total) ? (uint32_t)M.list[k0 + u] : 0u;
+        ent[u] = (k0 + u < total) ? M.ldl(k0 + u) : 0u;
         va[u] = vb[u] = zero;
         if (k0 + u < total && has0) va[u] = M.ldB(ent[u] & 0xFFFu, w0);
         if (k0 + u < total && has1) vb[u] = M.ldB(ent[u] & 0xFFFu, w1);
@@ -419,7 +437,7 @@ __device__ __forceinline__ uint32_t gm_measure(const Tile<LPS>& T, const GMImg<D
         az0 = addD<D>(az0, smulD<D>(va[u].z, fi));                         // running ancilla
         az1 = addD<D>(az1, smulD<D>(vb[u].z, fi));
         if (D == 3 && fi == 2u) sdg += popsum<D>(mulD<D>(va[u].x, va[u].z)) + popsum<D>(mulD<D>(vb[u].x, vb[u].z));
-        a1 += fi * M.ph8[ent[u] & 0xFFFu];
+        a1 += fi * M.ldp(ent[u] & 0xFFFu);
       }
     }
     uint32_t part = cross + PO * sdg;
@@ -484,8 +502,8 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
   M.n = G.n; M.np = G.np; M.Wq = G.np / 32; M.Wb = G.Wb;
   M.gs_shift = 0;
   while ((2 << M.gs_shift) < M.Wq) ++M.gs_shift;                        // lanes per B row: two entries per lane
-  M.list = reinterpret_cast<uint16_t*>(smem) + (size_t)tile * 2 * G.np;
-  M.ph8 = smem + (size_t)TILES * 4 * G.np + (size_t)tile * 2 * G.np;
+  M.list = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(tile * 4 * G.np);
+  M.ph8 = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(TILES * 4 * G.np + tile * 2 * G.np);
   M.place(p.gm_slab + ((int64_t)blockIdx.x * TILES + tile) * p.gm_slab_words);
   for (;;) {
     int64_t shot = 0;
@@ -502,7 +520,7 @@ __global__ void __launch_bounds__(kRunThreads, kRunCtasPerSm) run_tail_kernel(co
     }
     for (int g = lane; g < 2 * G.np; g += LPS) {
       const uint2 w = ph[g >> 5];
-      M.ph8[g] = (uint8_t)(((w.x >> (g & 31)) & 1u) | (((w.y >> (g & 31)) & 1u) << 1));
+      M.stp(g, ((w.x >> (g & 31)) & 1u) | (((w.y >> (g & 31)) & 1u) << 1));
     }
     if (!PRE && !p.gm_per_shot) gm_transpose<D>(G, M, true, lane, LPS);
     T.sync();
