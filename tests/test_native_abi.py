@@ -65,6 +65,14 @@ def test_error_codes_map_to_value_errors():
     assert lib.sdimb_run(C.byref(a)) == N.EDIM
     a.d, a.shots = 3, -1
     assert lib.sdimb_run(C.byref(a)) == N.EINVAL
+    # callers built against the struct of ABI versions 1-3 (without tail_run_len / without the gate-stream fields) are
+    # accepted; any other size is not.  shots = 0 returns before anything touches the device.
+    a.shots = 0
+    full = C.sizeof(N.SdimbRunArgs)
+    for size, want in ((full, N.OK), (N.SdimbRunArgs.gate_stream.offset, N.OK), (N.SdimbRunArgs.tail_run_len.offset, N.OK),
+                       (full - 4, N.EINVAL), (full + 8, N.EINVAL)):
+        a.struct_size = size
+        assert lib.sdimb_run(C.byref(a)) == want, size
     # host entry validates the op stream before touching the device
     import numpy as np
     ops = np.array([[99, 0, -1, -1]], dtype=np.int32)
