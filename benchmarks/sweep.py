@@ -30,8 +30,13 @@ def point(n, d, shots, reps=2):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    path = kernel
+    if kernel == "planes-global" and eng.tail_run_len and n <= 512:
+        path = ("gate_stream_kernel" if eng.gate_stream is not None else "interp_planes_kernel") + " + run_tail_kernel"
+    elif kernel == "lanes-global" and eng.tail_run_len_raw and not csize and n <= 512 and d <= 127:
+        path = "lane interpreter + run_tail8_kernel"
     return {"n": n, "d": d, "shots": shots, "ops": prog.n_ops, "gates_per_shot": prog.n_user_gates,
-            "kernel": kernel + (f" ({csize}-CTA clusters)" if csize else ""), "ms": ms,
+            "kernel": kernel + (f" ({csize}-CTA clusters)" if csize else ""), "path": path, "ms": ms,
             "shot_gates_per_sec": shots * prog.n_user_gates / ms * 1e3}
 
 
